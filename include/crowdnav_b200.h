@@ -1,0 +1,229 @@
+/*
+ * crowdnav_b200.h -- C ABI of libcrowdnav_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for the rollout hot path of evan-tan/CrowdNav_DSRNN:
+ *   crowd step  (CrowdSimDict.step,  crowd_sim/envs/crowd_sim_dict.py:205-271)
+ *   reset       (CrowdSimDict.reset, crowd_sim/envs/crowd_sim_dict.py:105-203)
+ *   DS-RNN fwd  (SRNN.forward,       pytorchBaselines/a2c_ppo_acktr/srnn_model.py:409-504)
+ *
+ * The reference has no FFI of its own for this path except the third-party
+ * `rvo2` module (crowd_nav/policy/orca.py:87-136); the functions below are what
+ * a binding for the whole batched path replaces it with.  Plain pointers and
+ * sizes only; no torch types.  All pointers named *_dev are DEVICE pointers
+ * owned by the caller.  Every call is asynchronous on `stream` (a
+ * cudaStream_t passed as void*).  Every function returns CN_OK or a negative
+ * error code; cn_last_error() returns the text for the calling thread.
+ */
+#ifndef CROWDNAV_B200_H
+#define CROWDNAV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CN_ABI_VERSION 1
+#define CN_MAX_HUMANS 32          /* one 32-lane group per ORCA solve */
+#define CN_MAX_SCENARIOS 8
+#define CN_STEP_TABLE_WORDS 128   /* bit table over step indices: up to 4096 steps per episode */
+
+enum { CN_OK = 0, CN_ERR_ARG = -1, CN_ERR_CUDA = -2, CN_ERR_UNSUPPORTED = -3, CN_ERR_STATE = -4 };
+
+/* config.action_space.kinematics (crowd_nav/configs/config.py:136-138) */
+enum { CN_HOLONOMIC = 0, CN_UNICYCLE = 1 };
+/* scenario strings of config.sim.train_val_sim / test_sim (config.py:17-35; crowd_sim.py:306-354) */
+enum {
+    CN_SCN_CIRCLE_CROSSING = 0, CN_SCN_SQUARE_CROSSING = 1, CN_SCN_PARALLEL_TRAFFIC = 2,
+    CN_SCN_PERPENDICULAR_TRAFFIC = 3, CN_SCN_SIDE_PREF_PASSING = 4, CN_SCN_SIDE_PREF_OVERTAKING = 5,
+    CN_SCN_SIDE_PREF_CROSSING = 6
+};
+/* event classes of crowd_sim/envs/utils/info.py:1-38 */
+enum { CN_EV_NOTHING = 0, CN_EV_DANGER = 1, CN_EV_REACH_GOAL = 2, CN_EV_COLLISION = 3, CN_EV_TIMEOUT = 4 };
+/* env.phase (pytorchBaselines/a2c_ppo_acktr/envs.py:70-73) */
+enum { CN_PHASE_TRAIN = 0, CN_PHASE_VAL = 1, CN_PHASE_TEST = 2 };
+
+/*
+ * Flattened crowd_nav/configs/config.py (consumed by CrowdSim.configure,
+ * crowd_sim/envs/crowd_sim.py:93-246, and Agent.__init__, utils/agent.py:16-35).
+ * Doubles where the reference holds Python floats.
+ */
+typedef struct CnConfig {
+    int32_t abi_version;              /* CN_ABI_VERSION */
+    int32_t human_num;                /* sim.human_num, 1..CN_MAX_HUMANS */
+    int32_t kinematics;               /* CN_HOLONOMIC / CN_UNICYCLE */
+    int32_t robot_visible;            /* robot.visible: humans' ORCA sees the robot */
+    int32_t randomize_attributes;     /* env.randomize_attributes */
+    int32_t potential_based;          /* reward.potential_based */
+    int32_t exponential;              /* reward.exponential */
+    int32_t time_factor;              /* reward.time_factor */
+    int32_t random_goal_changing;     /* humans.random_goal_changing */
+    int32_t end_goal_changing;        /* humans.end_goal_changing */
+    int32_t side_preference;          /* test.side_preference */
+    int32_t social_metrics;           /* test.social_metrics */
+    int32_t phase;                    /* CN_PHASE_* (selects scenario list, seed offset, case size) */
+    int32_t nenv;                     /* env.nenv: case_counter stride (crowd_sim_dict.py:162-164) */
+    int32_t n_scenarios;              /* length of the active scenario list */
+    int32_t scenarios[CN_MAX_SCENARIOS];
+    int32_t max_spawn_tries;          /* bounded rejection (deviation from the unbounded loops) */
+    int32_t max_goal_tries;
+    int32_t max_robot_tries;
+    int32_t timeout_step;             /* first step index whose float64-accumulated global_time >= time_limit-1 */
+    int32_t env_id_offset;            /* global id of local env 0 (multi-GPU sharding; RNG is keyed by global id) */
+    int32_t reserved0;
+    uint32_t goal_change_steps[CN_STEP_TABLE_WORDS]; /* bit s set: after s steps global_time % 5 == 0 (crowd_sim_dict.py:262) */
+    uint64_t base_seed;               /* env.seed (thisSeed = base_seed + global env id, envs.py:66-68) */
+    uint64_t seed_offset;             /* counter_offset[phase] (crowd_sim_dict.py:147-151) */
+    uint64_t case_size;               /* case_size[phase] (crowd_sim.py:115-119) */
+    double time_step;                 /* env.time_step */
+    double time_limit;                /* env.time_limit */
+    double success_reward;
+    double collision_penalty;
+    double discomfort_dist;           /* reward.discomfort_dist_back */
+    double discomfort_penalty_factor; /* already multiplied by time_step (config.py:73-74) */
+    double potential_factor;
+    double exp_factor;
+    double exp_denom;
+    double circle_radius;
+    double square_width;
+    double robot_fov;                 /* radians = pi * robot.FOV */
+    double human_fov;                 /* radians = pi * humans.FOV */
+    double robot_radius;
+    double robot_v_pref;
+    double human_radius;              /* used when !randomize_attributes and for the dummy human */
+    double human_v_pref;
+    double min_personal_space;        /* social.min_personal_space */
+    double max_walking_speed;         /* social.max_walking_speed */
+    double goal_change_chance;
+    double end_goal_change_chance;
+    float orca_neighbor_dist;         /* orca.* are narrowed to float at the rvo2 boundary */
+    float orca_safety_space;
+    float orca_time_horizon;
+    float reserved1;
+} CnConfig;
+
+/*
+ * Canonical (test/injection) view of the env state, all DEVICE pointers,
+ * row-major, n_envs rows.  Field order follows Agent.get_full_state_list
+ * (utils/agent.py:116-127).  NULL members are skipped.
+ */
+typedef struct CnStateView {
+    float *robot;      /* [N, 9]  px,py,vx,vy,radius,gx,gy,v_pref,theta */
+    float *humans;     /* [N, H, 9] same field order */
+    float *belief;     /* [N, H, 5] last_human_states px,py,vx,vy,r (crowd_sim.py:199,429-455) */
+    float *extras;     /* [N, 4]  desiredVelocity[0], potential, last_acceleration x,y */
+    int32_t *counters; /* [N, 4]  step_count, scenario_counter, case_counter, current_scenario */
+    float *episode_return; /* [N]  running sum of rewards (bench.Monitor) */
+} CnStateView;
+
+/* Observation dict of CrowdSimDict.generate_ob (crowd_sim_dict.py:72-103), float32. */
+typedef struct CnObsOut {
+    float *robot_node;      /* [N, 1, 7] px,py,r,gx,gy,v_pref,theta */
+    float *temporal_edges;  /* [N, 1, 2] vx,vy */
+    float *spatial_edges;   /* [N, H, 2] belief_p - robot_p */
+    uint32_t *visible_mask; /* [N] bit i: human i inside the robot FOV (crowd_sim.py:851-865) */
+} CnObsOut;
+
+/* Per-step outputs of CrowdSimDict.step (crowd_sim_dict.py:205-271) + Monitor. */
+typedef struct CnStepOut {
+    CnObsOut obs;           /* post-step observation; the RESET observation where done (shmem_vec_env.py:165-168) */
+    float *reward;          /* [N] */
+    uint8_t *done;          /* [N] */
+    int32_t *event;         /* [N] CN_EV_* */
+    int32_t *scenario;      /* [N] CN_SCN_* of the episode the step belonged to */
+    float *info;            /* [N, CN_INFO_DIM] see CN_INFO_* */
+    float *episode_return;  /* [N] valid where done */
+    int32_t *episode_length;/* [N] valid where done */
+    uint32_t *goal_changed; /* [N] bit i: human i was given a new goal after this step (may be NULL) */
+} CnStepOut;
+
+/* columns of CnStepOut.info (step_info keys, crowd_sim.py:973-1030) */
+enum {
+    CN_INFO_DMIN = 0,            /* Danger.min_dist (inf when no human was scanned) */
+    CN_INFO_AGGREGATE_NAV_TIME = 1,
+    CN_INFO_PATH_VIOLATION = 2,
+    CN_INFO_PERSONAL_VIOLATION = 3,
+    CN_INFO_JERK_COST = 4,
+    CN_INFO_DIST_TO_GOAL = 5,
+    CN_INFO_SPEED_VIOLATION = 6,
+    CN_INFO_SIDE_LEFT = 7,
+    CN_INFO_SIDE_RIGHT = 8,
+    CN_INFO_SEPARATION = 9,
+    CN_INFO_DIM = 12
+};
+
+typedef struct CnEnv CnEnv;
+
+const char *cn_last_error(void);
+int cn_abi_version(void);
+
+/* bytes of device memory the SoA state of n_envs needs; the caller allocates it */
+size_t cn_env_state_bytes(const CnConfig *cfg, int n_envs);
+int cn_env_create(const CnConfig *cfg, int n_envs, int device, void *state_dev, size_t state_bytes, CnEnv **out);
+int cn_env_destroy(CnEnv *env);
+/* CrowdSimDict.reset for the envs whose mask byte is non-zero (all when mask_dev == NULL) */
+int cn_env_reset(CnEnv *env, const uint8_t *mask_dev, const CnObsOut *obs, void *stream);
+/* CrowdSimDict.step on every env; action_dev [N,2] float32 raw policy output (clip_action is applied inside).
+ * auto_reset != 0 reproduces the vec-env worker: done envs are reset and return the reset observation. */
+int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut *out, int auto_reset, void *stream);
+int cn_env_set_state(CnEnv *env, const CnStateView *view, void *stream);
+int cn_env_get_state(CnEnv *env, const CnStateView *view, void *stream);
+/* regenerate the observation from the current state without stepping (generate_ob(reset=True) semantics) */
+int cn_env_observe(CnEnv *env, const CnObsOut *obs, void *stream);
+
+/*
+ * DS-RNN policy forward (SRNN.forward infer=True + DiagGaussian.fc_mean,
+ * srnn_model.py:409-504, distributions.py:85-94).  Weights are DEVICE float32
+ * tensors in the reference's own state_dict layout (row-major [out, in]).
+ */
+typedef struct CnDsrnnWeights {
+    /* humanhumanEdgeRNN_temporal / _spatial: encoder_linear [64,2],[64]; gru weight_ih [768,64], weight_hh [768,256], biases [768] */
+    const float *t_enc_w, *t_enc_b, *t_w_ih, *t_w_hh, *t_b_ih, *t_b_hh;
+    const float *s_enc_w, *s_enc_b, *s_w_ih, *s_w_hh, *s_b_ih, *s_b_hh;
+    /* attn.temporal_edge_layer.0 / spatial_edge_layer.0: [64,256],[64] */
+    const float *att_t_w, *att_t_b, *att_s_w, *att_s_b;
+    /* robot_linear [3,7],[3] */
+    const float *robot_w, *robot_b;
+    /* humanNodeRNN: encoder_linear [64,3],[64]; edge_attention_embed [64,512],[64]; gru [384,128],[384,128],[384],[384]; output_linear [256,128],[256] */
+    const float *n_enc_w, *n_enc_b, *n_att_w, *n_att_b, *n_w_ih, *n_w_hh, *n_b_ih, *n_b_hh, *n_out_w, *n_out_b;
+    /* actor.0, actor.2, critic.0, critic.2: [256,256],[256]; critic_linear [1,256],[1]; dist.fc_mean [2,256],[2] */
+    const float *actor0_w, *actor0_b, *actor2_w, *actor2_b;
+    const float *critic0_w, *critic0_b, *critic2_w, *critic2_b;
+    const float *critic_lin_w, *critic_lin_b, *mean_w, *mean_b;
+} CnDsrnnWeights;
+
+typedef struct CnDsrnnIO {
+    const float *robot_node;     /* [N,1,7] */
+    const float *temporal_edges; /* [N,1,2] */
+    const float *spatial_edges;  /* [N,H,2] */
+    const float *h_node_in;      /* [N,1,128]   rnn_hxs["human_node_rnn"] */
+    const float *h_edge_in;      /* [N,H+1,256] rnn_hxs["human_human_edge_rnn"] (row 0 temporal, 1..H spatial) */
+    const float *masks;          /* [N,1] 0 where the episode just ended */
+    float *h_node_out;           /* [N,1,128] */
+    float *h_edge_out;           /* [N,H+1,256] */
+    float *value;                /* [N,1] critic_linear output */
+    float *action_mean;          /* [N,2] dist.fc_mean output */
+    float *actor_features;       /* [N,256] hidden_actor (may be NULL) */
+} CnDsrnnIO;
+
+typedef struct CnDsrnn CnDsrnn;
+
+/* precision of the tensor-core contractions */
+enum { CN_PREC_FP32 = 0, CN_PREC_BF16X3 = 1, CN_PREC_BF16 = 2 };
+
+int cn_dsrnn_create(const CnDsrnnWeights *w, int device, void *stream, CnDsrnn **out);
+int cn_dsrnn_destroy(CnDsrnn *m);
+/* re-read (and re-pack) the weights after an optimiser step */
+int cn_dsrnn_update_weights(CnDsrnn *m, const CnDsrnnWeights *w, void *stream);
+size_t cn_dsrnn_workspace_bytes(int n_envs, int human_num);
+int cn_dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnDsrnnIO *io, int precision,
+                     void *workspace_dev, size_t workspace_bytes, void *stream);
+/* number of kernels the last forward / step call launched (bench.py's gpu_launches claim) */
+int cn_dsrnn_last_launches(const CnDsrnn *m);
+int cn_env_last_launches(const CnEnv *env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROWDNAV_B200_H */
