@@ -1,0 +1,76 @@
+"""Loader of the C-ABI CUDA library (csrc/ -> libcrowdnav_b200.so, include/crowdnav_b200.h).
+
+There is NO CPU fallback: `load()` raises when the library is missing or does
+not export every symbol the header declares, and every compute entry point
+goes through `check()`, which raises with cn_last_error() on failure.
+"""
+import ctypes as C
+import os
+import subprocess
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcrowdnav_b200.so")
+
+# every function include/crowdnav_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "cn_last_error": (C.c_char_p, []),
+    "cn_abi_version": (C.c_int, []),
+    "cn_env_state_bytes": (C.c_size_t, [C.POINTER(abi.CnConfig), C.c_int]),
+    "cn_env_create": (C.c_int, [C.POINTER(abi.CnConfig), C.c_int, C.c_int, _P, C.c_size_t, C.POINTER(_P)]),
+    "cn_env_destroy": (C.c_int, [_P]),
+    "cn_env_reset": (C.c_int, [_P, _P, C.POINTER(abi.CnObsOut), _P]),
+    "cn_env_step": (C.c_int, [_P, _P, C.POINTER(abi.CnStepOut), C.c_int, _P]),
+    "cn_env_set_state": (C.c_int, [_P, C.POINTER(abi.CnStateView), _P]),
+    "cn_env_get_state": (C.c_int, [_P, C.POINTER(abi.CnStateView), _P]),
+    "cn_env_observe": (C.c_int, [_P, C.POINTER(abi.CnObsOut), _P]),
+    "cn_env_last_launches": (C.c_int, [_P]),
+    "cn_dsrnn_create": (C.c_int, [C.POINTER(abi.CnDsrnnWeights), C.c_int, _P, C.POINTER(_P)]),
+    "cn_dsrnn_destroy": (C.c_int, [_P]),
+    "cn_dsrnn_update_weights": (C.c_int, [_P, C.POINTER(abi.CnDsrnnWeights), _P]),
+    "cn_dsrnn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "cn_dsrnn_forward": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(abi.CnDsrnnIO), C.c_int, _P, C.c_size_t, _P]),
+    "cn_dsrnn_last_launches": (C.c_int, [_P]),
+}
+
+_LIB = None
+
+
+class CrowdNavLibraryError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], stdout=out)
+
+
+def load():
+    """dlopen libcrowdnav_b200.so and bind every declared symbol; raises if anything is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise CrowdNavLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise CrowdNavLibraryError(f"{LIB_PATH} does not export {name}") from exc
+        fn.restype, fn.argtypes = restype, argtypes
+    if lib.cn_abi_version() != abi.ABI_VERSION:
+        raise CrowdNavLibraryError("ABI version mismatch: library %d, python %d" % (lib.cn_abi_version(), abi.ABI_VERSION))
+    _LIB = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().cn_last_error()
+        raise CrowdNavLibraryError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -1,0 +1,217 @@
+// c_abi.cu -- extern "C" entry points of libcrowdnav_b200.so (include/crowdnav_b200.h).
+// Host-side only: argument validation, handle bookkeeping, kernel launches.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "env_common.cuh"
+#include "dsrnn.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CN_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t err__ = (call);                                                     \
+        if (err__ != cudaSuccess) return fail(CN_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(err__)); \
+    } while (0)
+
+extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, cudaStream_t stream);
+extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, cudaStream_t stream);
+extern "C" int cn_launch_crowd_observe(const EnvParams *P, const CnObsOut *obs, cudaStream_t stream);
+extern "C" int cn_launch_state_convert(const EnvParams *P, const CnStateView *v, int dir, cudaStream_t stream);
+
+struct CnEnv {
+    EnvParams p;
+    int device;
+    int last_launches;
+};
+
+extern "C" const char *cn_last_error(void) { return g_err; }
+extern "C" int cn_abi_version(void) { return CN_ABI_VERSION; }
+
+static int check_config(const CnConfig *cfg)
+{
+    if (!cfg) return fail(CN_ERR_ARG, "cfg is NULL");
+    if (cfg->abi_version != CN_ABI_VERSION) return fail(CN_ERR_ARG, "CnConfig.abi_version %d != %d", cfg->abi_version, CN_ABI_VERSION);
+    if (cfg->human_num < 1 || cfg->human_num + (cfg->robot_visible ? 1 : 0) > CN_MAX_HUMANS)
+        return fail(CN_ERR_ARG, "human_num %d out of range 1..%d", cfg->human_num, CN_MAX_HUMANS - (cfg->robot_visible ? 1 : 0));
+    if (cfg->kinematics != CN_HOLONOMIC && cfg->kinematics != CN_UNICYCLE) return fail(CN_ERR_ARG, "unknown kinematics %d", cfg->kinematics);
+    if (cfg->n_scenarios < 1 || cfg->n_scenarios > CN_MAX_SCENARIOS) return fail(CN_ERR_ARG, "n_scenarios %d out of range", cfg->n_scenarios);
+    for (int i = 0; i < cfg->n_scenarios; ++i)
+        if (cfg->scenarios[i] < 0 || cfg->scenarios[i] > CN_SCN_SIDE_PREF_CROSSING) return fail(CN_ERR_ARG, "unknown scenario id %d", cfg->scenarios[i]);
+    if (!(cfg->time_step > 0.0) || cfg->timeout_step < 0) return fail(CN_ERR_ARG, "bad time_step/timeout_step");
+    if (cfg->max_spawn_tries < 1 || cfg->max_goal_tries < 1 || cfg->max_robot_tries < 1) return fail(CN_ERR_ARG, "max_*_tries must be >= 1");
+    if (cfg->case_size == 0) return fail(CN_ERR_ARG, "case_size must be > 0");
+    if (cfg->social_metrics && cfg->n_scenarios != 4) return fail(CN_ERR_ARG, "social_metrics needs exactly 4 scenarios (crowd_sim_dict.py:116)");
+    return CN_OK;
+}
+
+extern "C" size_t cn_env_state_bytes(const CnConfig *cfg, int n_envs)
+{
+    if (check_config(cfg) != CN_OK || n_envs < 1) return 0;
+    return cn_carve(nullptr, nullptr, n_envs, cfg->human_num);
+}
+
+extern "C" int cn_env_create(const CnConfig *cfg, int n_envs, int device, void *state_dev, size_t state_bytes, CnEnv **out)
+{
+    if (!out) return fail(CN_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = check_config(cfg);
+    if (rc != CN_OK) return rc;
+    if (n_envs < 1) return fail(CN_ERR_ARG, "n_envs must be >= 1");
+    const size_t need = cn_carve(nullptr, nullptr, n_envs, cfg->human_num);
+    if (!state_dev || state_bytes < need) return fail(CN_ERR_ARG, "state buffer too small: %zu < %zu", state_bytes, need);
+    if (((uintptr_t)state_dev & 255) != 0) return fail(CN_ERR_ARG, "state buffer must be 256-byte aligned");
+    int count = 0;
+    CN_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(CN_ERR_ARG, "device %d not present (%d devices)", device, count);
+    cudaDeviceProp prop;
+    CN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(CN_ERR_UNSUPPORTED, "libcrowdnav_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    CnEnv *env = new (std::nothrow) CnEnv();
+    if (!env) return fail(CN_ERR_STATE, "out of host memory");
+    env->p.cfg = *cfg;
+    env->p.n_envs = n_envs;
+    env->device = device;
+    env->last_launches = 0;
+    cn_carve(&env->p.a, state_dev, n_envs, cfg->human_num);
+    *out = env;
+    return CN_OK;
+}
+
+extern "C" int cn_env_destroy(CnEnv *env)
+{
+    delete env;
+    return CN_OK;
+}
+
+static int check_obs(const CnObsOut *obs)
+{
+    if (!obs || !obs->robot_node || !obs->temporal_edges || !obs->spatial_edges)
+        return fail(CN_ERR_ARG, "CnObsOut needs robot_node, temporal_edges and spatial_edges");
+    if (((uintptr_t)obs->spatial_edges & 7) != 0) return fail(CN_ERR_ARG, "spatial_edges must be 8-byte aligned");
+    return CN_OK;
+}
+
+extern "C" int cn_env_reset(CnEnv *env, const uint8_t *mask_dev, const CnObsOut *obs, void *stream)
+{
+    if (!env) return fail(CN_ERR_ARG, "env is NULL");
+    int rc = check_obs(obs);
+    if (rc != CN_OK) return rc;
+    CN_CUDA(cudaSetDevice(env->device));
+    CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, obs, mask_dev, (cudaStream_t)stream));
+    env->last_launches = 1;
+    return CN_OK;
+}
+
+extern "C" int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut *out, int auto_reset, void *stream)
+{
+    if (!env) return fail(CN_ERR_ARG, "env is NULL");
+    if (!action_dev || !out) return fail(CN_ERR_ARG, "action/out is NULL");
+    int rc = check_obs(&out->obs);
+    if (rc != CN_OK) return rc;
+    if (!out->reward || !out->done || !out->event) return fail(CN_ERR_ARG, "CnStepOut needs reward, done and event");
+    CN_CUDA(cudaSetDevice(env->device));
+    CN_CUDA((cudaError_t)cn_launch_crowd_step(&env->p, out, action_dev, (cudaStream_t)stream));
+    env->last_launches = 1;
+    if (auto_reset) {
+        CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, &out->obs, out->done, (cudaStream_t)stream));
+        env->last_launches = 2;
+    }
+    return CN_OK;
+}
+
+extern "C" int cn_env_observe(CnEnv *env, const CnObsOut *obs, void *stream)
+{
+    if (!env) return fail(CN_ERR_ARG, "env is NULL");
+    int rc = check_obs(obs);
+    if (rc != CN_OK) return rc;
+    CN_CUDA(cudaSetDevice(env->device));
+    CN_CUDA((cudaError_t)cn_launch_crowd_observe(&env->p, obs, (cudaStream_t)stream));
+    env->last_launches = 1;
+    return CN_OK;
+}
+
+static int convert(CnEnv *env, const CnStateView *view, int dir, void *stream)
+{
+    if (!env || !view) return fail(CN_ERR_ARG, "env/view is NULL");
+    CN_CUDA(cudaSetDevice(env->device));
+    CN_CUDA((cudaError_t)cn_launch_state_convert(&env->p, view, dir, (cudaStream_t)stream));
+    env->last_launches = 1;
+    return CN_OK;
+}
+
+extern "C" int cn_env_set_state(CnEnv *env, const CnStateView *view, void *stream) { return convert(env, view, 0, stream); }
+extern "C" int cn_env_get_state(CnEnv *env, const CnStateView *view, void *stream) { return convert(env, view, 1, stream); }
+extern "C" int cn_env_last_launches(const CnEnv *env) { return env ? env->last_launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ DS-RNN
+extern "C" int cn_dsrnn_create(const CnDsrnnWeights *w, int device, void *stream, CnDsrnn **out)
+{
+    if (!out) return fail(CN_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!w) return fail(CN_ERR_ARG, "weights is NULL");
+    const void *const *ptrs = reinterpret_cast<const void *const *>(w);
+    for (size_t i = 0; i < sizeof(CnDsrnnWeights) / sizeof(void *); ++i)
+        if (!ptrs[i]) return fail(CN_ERR_ARG, "CnDsrnnWeights member %zu is NULL", i);
+    int count = 0;
+    CN_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(CN_ERR_ARG, "device %d not present (%d devices)", device, count);
+    cudaDeviceProp prop;
+    CN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(CN_ERR_UNSUPPORTED, "libcrowdnav_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    CN_CUDA(cudaSetDevice(device));
+    CnDsrnn *m = nullptr;
+    const char *msg = dsrnn_create(w, device, (cudaStream_t)stream, &m);
+    if (msg) return fail(CN_ERR_CUDA, "dsrnn_create: %s", msg);
+    *out = m;
+    return CN_OK;
+}
+
+extern "C" int cn_dsrnn_destroy(CnDsrnn *m)
+{
+    if (m) dsrnn_destroy(m);
+    return CN_OK;
+}
+
+extern "C" int cn_dsrnn_update_weights(CnDsrnn *m, const CnDsrnnWeights *w, void *stream)
+{
+    if (!m || !w) return fail(CN_ERR_ARG, "model/weights is NULL");
+    const char *msg = dsrnn_update_weights(m, w, (cudaStream_t)stream);
+    if (msg) return fail(CN_ERR_CUDA, "dsrnn_update_weights: %s", msg);
+    return CN_OK;
+}
+
+extern "C" size_t cn_dsrnn_workspace_bytes(int n_envs, int human_num)
+{
+    if (n_envs < 1 || human_num < 1 || human_num > CN_MAX_HUMANS) return 0;
+    return dsrnn_workspace_bytes(n_envs, human_num);
+}
+
+extern "C" int cn_dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnDsrnnIO *io, int precision,
+                                void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    if (!m || !io) return fail(CN_ERR_ARG, "model/io is NULL");
+    if (n_envs < 1 || human_num < 1 || human_num > CN_MAX_HUMANS) return fail(CN_ERR_ARG, "bad n_envs/human_num");
+    if (!io->robot_node || !io->temporal_edges || !io->spatial_edges || !io->h_node_in || !io->h_edge_in || !io->masks ||
+        !io->h_node_out || !io->h_edge_out || !io->value || !io->action_mean)
+        return fail(CN_ERR_ARG, "CnDsrnnIO has a NULL required member");
+    if (precision != CN_PREC_FP32 && precision != CN_PREC_BF16X3 && precision != CN_PREC_BF16)
+        return fail(CN_ERR_ARG, "unknown precision %d", precision);
+    const size_t need = dsrnn_workspace_bytes(n_envs, human_num);
+    if (!workspace_dev || workspace_bytes < need) return fail(CN_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, need);
+    const char *msg = dsrnn_forward(m, n_envs, human_num, io, precision, workspace_dev, (cudaStream_t)stream);
+    if (msg) return fail(CN_ERR_CUDA, "dsrnn_forward: %s", msg);
+    return CN_OK;
+}
+
+extern "C" int cn_dsrnn_last_launches(const CnDsrnn *m) { return m ? dsrnn_last_launches(m) : 0; }

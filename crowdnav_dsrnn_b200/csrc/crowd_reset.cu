@@ -1,0 +1,258 @@
+// crowd_reset.cu -- K2: device-side episode reset (sm_100a), plus the observation-only kernel and the
+// canonical <-> SoA state converters used by the parity tests.  Compile with -fmad=false.
+//
+// CrowdSimDict.reset (crowd_sim/envs/crowd_sim_dict.py:105-203): scenario choice, robot spawn
+// (crowd_sim.py:626-660), per-human attributes (agent.py:44-50) and spawn/goal by scenario
+// (crowd_sim.py:296-393) with the min-distance rejection rule, belief initialisation
+// (crowd_sim.py:443-445), potential, counters.  One warp per env; lane t evaluates try t of the
+// (bounded) rejection loops, the first accepted lane wins -- identical to the sequential loop
+// because every candidate is a pure function of (episode key, human, try) under the counter-based
+// Philox4x32-10 contract (oracle/crowd_oracle.c restates the same contract sequentially).
+#include "env_common.cuh"
+
+#define RESET_THREADS 128
+
+__device__ __forceinline__ void write_reset_obs(const EnvParams &P, const CnObsOut &obs, int e, int lane, int H,
+                                                float4 rpv, float4 rgr, float theta, bool reset_flag)
+{
+    // generate_ob (crowd_sim_dict.py:72-103) from the state in HBM; reset_flag picks the (15,15,0,0,0.3) belief
+    const CnConfig &cfg = P.cfg;
+    bool vis = false;
+    if (lane < H) {
+        const size_t hi = (size_t)e * H + lane;
+        const float4 hpv = P.a.hum_pv[hi];
+        if (cfg.robot_fov >= 2.0 * CN_PI) vis = !((double)hpv.x - (double)rpv.x == 0.0 && (double)hpv.y - (double)rpv.y == 0.0);
+        else vis = detect_visible_d(cfg.kinematics, rpv.x, rpv.y, rpv.z, rpv.w, theta, hpv.x, hpv.y, cfg.robot_fov);
+        float4 bel;
+        if (vis) { bel = hpv; P.a.hum_br[hi] = P.a.hum_gr[hi].z; }
+        else if (reset_flag) { bel = make_float4(15.0f, 15.0f, 0.0f, 0.0f); P.a.hum_br[hi] = 0.3f; }
+        else {
+            bel = P.a.hum_bel[hi];
+            bel.x = (float)((double)bel.x + (double)bel.z * cfg.time_step);
+            bel.y = (float)((double)bel.y + (double)bel.w * cfg.time_step);
+        }
+        P.a.hum_bel[hi] = bel;
+        if (obs.spatial_edges)
+            reinterpret_cast<float2 *>(obs.spatial_edges)[hi] =
+                make_float2((float)((double)bel.x - (double)rpv.x), (float)((double)bel.y - (double)rpv.y));
+    }
+    const unsigned vis_bits = __ballot_sync(0xffffffffu, vis);
+    if (lane < 7 && obs.robot_node) {
+        const float v = lane == 0 ? rpv.x : lane == 1 ? rpv.y : lane == 2 ? rgr.z : lane == 3 ? rgr.x
+                      : lane == 4 ? rgr.y : lane == 5 ? rgr.w : theta;
+        obs.robot_node[(size_t)e * 7 + lane] = v;
+    } else if (lane >= 7 && lane < 9 && obs.temporal_edges) {
+        obs.temporal_edges[(size_t)e * 2 + (lane - 7)] = lane == 7 ? rpv.z : rpv.w;
+    }
+    if (lane == 0 && obs.visible_mask) obs.visible_mask[e] = vis_bits;
+}
+
+// grid: ceil(N / 4) CTAs of 4 warps, one warp per env; envs whose mask byte is 0 return immediately.
+__global__ void __launch_bounds__(RESET_THREADS)
+crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnObsOut obs,
+                   const uint8_t *__restrict__ mask)
+{
+    __shared__ float4 s_h[RESET_THREADS / 32][CN_MAX_HUMANS];   // px, py, radius of the humans spawned so far
+    const CnConfig &cfg = P.cfg;
+    const int H = cfg.human_num;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (RESET_THREADS / 32) + warp;
+    if (e >= P.n_envs) return;
+    if (mask && !mask[e]) return;
+    const unsigned FULL = 0xffffffffu;
+    int4 ctr = P.a.ctr[e];
+    const uint64_t key = episode_key(cfg, ctr.z, e);
+    const uint4 g0 = philox4x32(key, 0, 0, 0, RNG_RESET);
+    int scn_idx;
+    if (cfg.social_metrics) scn_idx = (int)((uint32_t)ctr.y % 4u);
+    else { scn_idx = (int)(u01(g0.x) * cfg.n_scenarios); if (scn_idx >= cfg.n_scenarios) scn_idx = cfg.n_scenarios - 1; }
+    const int scenario = cfg.scenarios[scn_idx];
+    const double R = cfg.circle_radius;
+
+    // ---- robot (crowd_sim.py:626-660)
+    double rpx, rpy, rgx = 0.0, rgy = 0.0, rth;
+    if (cfg.kinematics == CN_UNICYCLE || !(cfg.social_metrics || cfg.side_preference)) {
+        const bool uni = cfg.kinematics == CN_UNICYCLE;
+        const double angle = u01(g0.y) * CN_PI * 2.0;
+        double cpx = R * cos(angle), cpy = R * sin(angle), cgx = 0.0, cgy = 0.0;
+        bool found = false;
+        for (int t0 = 0; t0 < cfg.max_robot_tries && !found; t0 += 32) {
+            const int t = t0 + lane;
+            const uint4 x = philox4x32(key, (uint32_t)t, 1, 0, RNG_RESET);
+            if (uni) { cgx = -R + 2.0 * R * u01(x.x); cgy = -R + 2.0 * R * u01(x.y); }
+            else {
+                cpx = -R + 2.0 * R * u01(x.x); cpy = -R + 2.0 * R * u01(x.y);
+                cgx = -R + 2.0 * R * u01(x.z); cgy = -R + 2.0 * R * u01(x.w);
+            }
+            const bool in_range = t < cfg.max_robot_tries;
+            const bool ok = in_range && norm2d(cpx - cgx, cpy - cgy) >= 6.0;
+            const unsigned okb = __ballot_sync(FULL, ok);
+            int src;
+            if (okb) { src = __ffs(okb) - 1; found = true; }
+            else if (t0 + 32 >= cfg.max_robot_tries) { src = (cfg.max_robot_tries - 1) & 31; found = true; }  // keep the last try
+            else continue;
+            cpx = shfl_d(FULL, cpx, src); cpy = shfl_d(FULL, cpy, src);
+            cgx = shfl_d(FULL, cgx, src); cgy = shfl_d(FULL, cgy, src);
+        }
+        rpx = cpx; rpy = cpy; rgx = cgx; rgy = cgy;
+        rth = uni ? u01(g0.z) * 2.0 * CN_PI : CN_PI / 2.0;
+    } else {
+        rpx = 0.0; rpy = -R; rgx = 0.0; rgy = R; rth = CN_PI / 2.0;
+    }
+    const float4 rpv = make_float4((float)rpx, (float)rpy, 0.0f, 0.0f);
+    const float4 rgr = make_float4((float)rgx, (float)rgy, (float)cfg.robot_radius, (float)cfg.robot_v_pref);
+
+    // ---- humans, sequentially; tries in parallel (crowd_sim.py:359-393)
+    for (int i = 0; i < H; ++i) {
+        double v_pref = cfg.human_v_pref, radius = cfg.human_radius;
+        if (cfg.randomize_attributes) {
+            const uint4 x = philox4x32(key, 0, (uint32_t)i, 0, RNG_ATTR);
+            v_pref = 0.5 + (1.5 - 0.5) * u01(x.x);
+            radius = 0.3 + (0.5 - 0.3) * u01(x.y);
+        }
+        const float radius_f = (float)radius;
+        SpawnCand c;
+        bool found = false;
+        for (int t0 = 0; t0 < cfg.max_spawn_tries && !found; t0 += 32) {
+            const int t = t0 + lane;
+            const uint4 xa = philox4x32(key, (uint32_t)t, (uint32_t)i, 0, RNG_SPAWN);
+            const uint4 xb = philox4x32(key, (uint32_t)t, (uint32_t)i, 1, RNG_SPAWN);
+            const double u6[6] = {u01(xa.x), u01(xa.y), u01(xa.z), u01(xa.w), u01(xb.x), u01(xb.y)};
+            c = agent_attributes(cfg, scenario, (double)radius_f, v_pref, (double)rgr.z, u6);
+            bool collide;
+            {
+                const double md = (cfg.kinematics == CN_UNICYCLE) ? R / 2.0 : (double)radius_f + (double)rgr.z + cfg.discomfort_dist;
+                collide = norm2d(c.px - (double)rpv.x, c.py - (double)rpv.y) < md;
+            }
+            for (int k = 0; k < i && !collide; ++k) {
+                const float4 a = s_h[warp][k];
+                const double md = (double)radius_f + (double)a.z + cfg.discomfort_dist;
+                if (norm2d(c.px - (double)a.x, c.py - (double)a.y) < md) collide = true;
+            }
+            const bool ok = t < cfg.max_spawn_tries && !collide;
+            const unsigned okb = __ballot_sync(FULL, ok);
+            int src;
+            if (okb) { src = __ffs(okb) - 1; found = true; }
+            else if (t0 + 32 >= cfg.max_spawn_tries) { src = (cfg.max_spawn_tries - 1) & 31; found = true; }
+            else continue;
+            c.px = shfl_d(FULL, c.px, src); c.py = shfl_d(FULL, c.py, src);
+            c.gx = shfl_d(FULL, c.gx, src); c.gy = shfl_d(FULL, c.gy, src);
+            c.heading = shfl_d(FULL, c.heading, src); c.v_pref = shfl_d(FULL, c.v_pref, src);
+        }
+        const float4 pv = make_float4((float)c.px, (float)c.py, 0.0f, 0.0f);
+        const float4 gr = make_float4((float)c.gx, (float)c.gy, radius_f, (float)c.v_pref);
+        if (lane == 0) {
+            const size_t hi = (size_t)e * H + i;
+            s_h[warp][i] = make_float4(pv.x, pv.y, radius_f, 0.0f);
+            P.a.hum_pv[hi] = pv;
+            P.a.hum_gr[hi] = gr;
+            P.a.hum_th[hi] = (float)c.heading;
+        }
+        __syncwarp();
+    }
+
+    // ---- counters, potential, observation
+    ctr.x = 0;
+    ctr.z = (int)(uint32_t)(((uint64_t)(uint32_t)ctr.z + (uint64_t)cfg.nenv) % cfg.case_size);
+    ctr.w = scenario;
+    ctr.y += 1;
+    __threadfence_block();
+    write_reset_obs(P, obs, e, lane, H, rpv, rgr, (float)rth, true);
+    if (lane == 0) {
+        float4 rx = P.a.rob_x[e];
+        rx.x = (float)rth;
+        rx.y = 0.0f;
+        rx.z = (float)(-fabs(norm2d((double)rpv.x - (double)rgr.x, (double)rpv.y - (double)rgr.y)));
+        rx.w = 0.0f;
+        P.a.rob_pv[e] = rpv;
+        P.a.rob_gr[e] = rgr;
+        P.a.rob_x[e] = rx;
+        P.a.ctr[e] = ctr;
+    }
+}
+
+__global__ void __launch_bounds__(RESET_THREADS)
+crowd_observe_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnObsOut obs)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (RESET_THREADS / 32) + warp;
+    if (e >= P.n_envs) return;
+    write_reset_obs(P, obs, e, lane, P.cfg.human_num, P.a.rob_pv[e], P.a.rob_gr[e], P.a.rob_x[e].x, true);
+}
+
+// canonical [N,9]/[N,H,9]/[N,H,5]/[N,4]/[N,4]/[N] view  <->  SoA   (dir 0: view -> SoA, 1: SoA -> view)
+__global__ void state_convert_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnStateView v, int dir)
+{
+    const int H = P.cfg.human_num;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nh = (size_t)P.n_envs * H;
+    if (idx < nh) {
+        if (v.humans) {
+            float *h = v.humans + idx * 9;
+            if (dir == 0) {
+                P.a.hum_pv[idx] = make_float4(h[0], h[1], h[2], h[3]);
+                P.a.hum_gr[idx] = make_float4(h[5], h[6], h[4], h[7]);
+                P.a.hum_th[idx] = h[8];
+            } else {
+                const float4 pv = P.a.hum_pv[idx], gr = P.a.hum_gr[idx];
+                h[0] = pv.x; h[1] = pv.y; h[2] = pv.z; h[3] = pv.w; h[4] = gr.z; h[5] = gr.x; h[6] = gr.y; h[7] = gr.w;
+                h[8] = P.a.hum_th[idx];
+            }
+        }
+        if (v.belief) {
+            float *b = v.belief + idx * 5;
+            if (dir == 0) { P.a.hum_bel[idx] = make_float4(b[0], b[1], b[2], b[3]); P.a.hum_br[idx] = b[4]; }
+            else { const float4 q = P.a.hum_bel[idx]; b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w; b[4] = P.a.hum_br[idx]; }
+        }
+    }
+    if (idx < (size_t)P.n_envs) {
+        float4 rx = P.a.rob_x[idx];
+        if (v.robot) {
+            float *r = v.robot + idx * 9;
+            if (dir == 0) {
+                P.a.rob_pv[idx] = make_float4(r[0], r[1], r[2], r[3]);
+                P.a.rob_gr[idx] = make_float4(r[5], r[6], r[4], r[7]);
+                rx.x = r[8];
+            } else {
+                const float4 pv = P.a.rob_pv[idx], gr = P.a.rob_gr[idx];
+                r[0] = pv.x; r[1] = pv.y; r[2] = pv.z; r[3] = pv.w; r[4] = gr.z; r[5] = gr.x; r[6] = gr.y; r[7] = gr.w; r[8] = rx.x;
+            }
+        }
+        if (v.extras) {
+            float *x = v.extras + idx * 4;
+            if (dir == 0) { rx.y = x[0]; rx.z = x[1]; P.a.rob_acc[idx] = make_float2(x[2], x[3]); }
+            else { const float2 a = P.a.rob_acc[idx]; x[0] = rx.y; x[1] = rx.z; x[2] = a.x; x[3] = a.y; }
+        }
+        if (v.episode_return) {
+            if (dir == 0) rx.w = v.episode_return[idx]; else v.episode_return[idx] = rx.w;
+        }
+        if (dir == 0) P.a.rob_x[idx] = rx;
+        if (v.counters) {
+            int32_t *c = v.counters + idx * 4;
+            if (dir == 0) P.a.ctr[idx] = make_int4(c[0], c[1], c[2], c[3]);
+            else { const int4 q = P.a.ctr[idx]; c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w; }
+        }
+    }
+}
+
+extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, cudaStream_t stream)
+{
+    const int per = RESET_THREADS / 32;
+    crowd_reset_kernel<<<(P->n_envs + per - 1) / per, RESET_THREADS, 0, stream>>>(*P, *obs, mask);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cn_launch_crowd_observe(const EnvParams *P, const CnObsOut *obs, cudaStream_t stream)
+{
+    const int per = RESET_THREADS / 32;
+    crowd_observe_kernel<<<(P->n_envs + per - 1) / per, RESET_THREADS, 0, stream>>>(*P, *obs);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cn_launch_state_convert(const EnvParams *P, const CnStateView *v, int dir, cudaStream_t stream)
+{
+    const size_t total = (size_t)P->n_envs * P->cfg.human_num;
+    const int threads = 256;
+    state_convert_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(*P, *v, dir);
+    return (int)cudaGetLastError();
+}

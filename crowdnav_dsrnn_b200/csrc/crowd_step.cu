@@ -1,0 +1,682 @@
+// crowd_step.cu -- K1: the fused crowd-step kernel (sm_100a).  Compile with -fmad=false.
+//
+// One launch does, for every env, what CrowdSimDict.step does
+// (crowd_sim/envs/crowd_sim_dict.py:205-271):
+//   phase A  every human's ORCA solve (crowd_nav/policy/orca.py:64-139 -> RVO2
+//            computeNeighbors / computeNewVelocity / linearProgram1-3), one G-lane
+//            group per human: lane l owns neighbour l, builds its half-plane, the
+//            group ranks the neighbours by (distSq, index) with shuffles, and the
+//            incremental LP runs with ballots (first violated constraint) and
+//            shuffle reductions (feasible interval on the violated line);
+//   phase B  one warp per env, lane i owns human i: clip_action (srnn.py:18-48),
+//            unicycle accumulation, calc_reward on the PRE-step state
+//            (crowd_sim.py:907-1094), integration (agent.py:172-212), FOV mask +
+//            belief update + observation writes (crowd_sim_dict.py:72-103,
+//            crowd_sim.py:429-455, 820-865) and goal re-sampling
+//            (crowd_sim.py:724-811) from the counter-based RNG.
+// The CTA stages its E consecutive envs' humans in shared memory with coalesced
+// float4 loads; nothing is re-read from HBM.  ORCA arithmetic is fp32 without
+// FMA contraction (bit-identical to a stock x86-64 build of RVO2 and to
+// oracle/orca_core.h); everything the reference does in Python floats is fp64.
+#include "env_common.cuh"
+
+#define ORCA_EPS 0.00001f
+#define STEP_THREADS 256
+
+template <int G> struct GroupOps {
+    static constexpr unsigned kLow = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+    unsigned gmask;  // lanes of this group inside the warp
+    int gbase;       // first lane of the group
+    int gl;          // lane index inside the group
+    __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(gmask, v, src, G); }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(gmask, p) >> gbase) & kLow; }
+    __device__ __forceinline__ float rmax(float v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(gmask, v, o, G));
+        return v;
+    }
+    __device__ __forceinline__ float rmin(float v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gmask, v, o, G));
+        return v;
+    }
+};
+
+struct Line { float px, py, dx, dy; };
+
+__device__ __forceinline__ float det2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
+
+// linearProgram1: optimise on line k subject to the valid lines of lanes < k and the speed disc
+template <int G>
+__device__ __forceinline__ bool lp1_group(const GroupOps<G> &g, const Line &ln, bool valid, int k, float radius,
+                                          float optx, float opty, bool dir_opt, float &rx, float &ry)
+{
+    const float kpx = g.shfl(ln.px, k), kpy = g.shfl(ln.py, k), kdx = g.shfl(ln.dx, k), kdy = g.shfl(ln.dy, k);
+    const float dp = kpx * kdx + kpy * kdy;
+    const float disc = dp * dp + radius * radius - (kpx * kpx + kpy * kpy);
+    if (disc < 0.0f) return false;
+    const float sq = sqrtf(disc);
+    float t_left = -dp - sq, t_right = -dp + sq;
+    bool fail = false;
+    float tl = -INFINITY, tr = INFINITY;
+    if (valid && g.gl < k) {
+        const float den = det2(kdx, kdy, ln.dx, ln.dy);
+        const float num = det2(ln.dx, ln.dy, kpx - ln.px, kpy - ln.py);
+        if (fabsf(den) <= ORCA_EPS) fail = num < 0.0f;
+        else {
+            const float t = num / den;
+            if (den >= 0.0f) tr = t; else tl = t;
+        }
+    }
+    const bool any_fail = g.ballot(fail) != 0u;
+    tl = g.rmax(tl);
+    tr = g.rmin(tr);
+    if (t_left < tl) t_left = tl;
+    if (tr < t_right) t_right = tr;
+    if (any_fail || t_left > t_right) return false;
+    float t;
+    if (dir_opt) t = (optx * kdx + opty * kdy > 0.0f) ? t_right : t_left;
+    else {
+        t = kdx * (optx - kpx) + kdy * (opty - kpy);
+        if (t < t_left) t = t_left; else if (t > t_right) t = t_right;
+    }
+    rx = kpx + t * kdx; ry = kpy + t * kdy;
+    return true;
+}
+
+// linearProgram2 over the lanes' lines in lane order; returns the failing index or -1 when all lines hold
+template <int G>
+__device__ __forceinline__ int lp2_group(const GroupOps<G> &g, const Line &ln, bool valid, float radius,
+                                         float optx, float opty, bool dir_opt, float &rx, float &ry)
+{
+    if (dir_opt) { rx = radius * optx; ry = radius * opty; }
+    else if (optx * optx + opty * opty > radius * radius) {
+        const float inv = 1.0f / sqrtf(optx * optx + opty * opty);
+        rx = radius * (optx * inv); ry = radius * (opty * inv);
+    } else { rx = optx; ry = opty; }
+    int next = 0;
+    while (true) {
+        const bool viol = valid && g.gl >= next && det2(ln.dx, ln.dy, ln.px - rx, ln.py - ry) > 0.0f;
+        const unsigned b = g.ballot(viol);
+        if (b == 0u) return -1;
+        const int k = __ffs(b) - 1;
+        const float tx = rx, ty = ry;
+        if (!lp1_group<G>(g, ln, valid, k, radius, optx, opty, dir_opt, rx, ry)) { rx = tx; ry = ty; return k; }
+        next = k + 1;
+    }
+}
+
+// linearProgram3 (no obstacle lines): minimise the maximum penetration from line `begin` on
+template <int G>
+__device__ __forceinline__ void lp3_group(const GroupOps<G> &g, const Line &ln, int n, int begin, float radius,
+                                          float &rx, float &ry)
+{
+    float distance = 0.0f;
+    for (int i = begin; i < n; ++i) {
+        const float kpx = g.shfl(ln.px, i), kpy = g.shfl(ln.py, i), kdx = g.shfl(ln.dx, i), kdy = g.shfl(ln.dy, i);
+        if (det2(kdx, kdy, kpx - rx, kpy - ry) > distance) {
+            Line pl; pl.px = pl.py = pl.dx = pl.dy = 0.0f;
+            bool pvalid = false;
+            if (g.gl < i) {
+                const float d = det2(kdx, kdy, ln.dx, ln.dy);
+                if (fabsf(d) <= ORCA_EPS) {
+                    if (!(kdx * ln.dx + kdy * ln.dy > 0.0f)) {
+                        pl.px = 0.5f * (kpx + ln.px); pl.py = 0.5f * (kpy + ln.py); pvalid = true;
+                    }
+                } else {
+                    const float t = det2(ln.dx, ln.dy, kpx - ln.px, kpy - ln.py) / d;
+                    pl.px = kpx + t * kdx; pl.py = kpy + t * kdy; pvalid = true;
+                }
+                if (pvalid) {
+                    const float ex = ln.dx - kdx, ey = ln.dy - kdy;
+                    const float inv = 1.0f / sqrtf(ex * ex + ey * ey);
+                    pl.dx = ex * inv; pl.dy = ey * inv;
+                }
+            }
+            const float tx = rx, ty = ry;
+            if (lp2_group<G>(g, pl, pvalid, radius, -kdy, kdx, true, rx, ry) >= 0) { rx = tx; ry = ty; }
+            distance = det2(kdx, kdy, kpx - rx, kpy - ry);
+        }
+    }
+}
+
+// One human's ORCA solve by one G-lane group.  s_pv/s_gr/s_th: this env's humans (pre-step).
+template <int G>
+__device__ __forceinline__ float2 orca_group(const CnConfig &cfg, const GroupOps<G> &g, int i, int H,
+                                             const float4 *s_pv, const float4 *s_gr, const float *s_th,
+                                             float4 rob_pv, float rob_radius, float rob_theta, float4 *s_scratch)
+{
+    const float4 me = s_pv[i];
+    const float4 me_g = s_gr[i];
+    const float radius = (float)((double)me_g.z + 0.01 + (double)cfg.orca_safety_space);
+    const float max_speed = me_g.w;
+    // preferred velocity (orca.py:118-122), Python floats -> narrowed at the rvo2 boundary
+    const double gdx = (double)me_g.x - (double)me.x, gdy = (double)me_g.y - (double)me.y;
+    const double gsp = norm2d(gdx, gdy);
+    const float prefx = (float)(gsp > 1.0 ? gdx / gsp : gdx);
+    const float prefy = (float)(gsp > 1.0 ? gdy / gsp : gdy);
+
+    const int M = H - 1 + (cfg.robot_visible ? 1 : 0);
+    const bool have = g.gl < M;
+    float ox = 0.f, oy = 0.f, ovx = 0.f, ovy = 0.f, orad = 0.f;
+    if (have) {
+        const bool limited = cfg.human_fov < 2.0 * CN_PI;
+        const double my_th = (limited && cfg.kinematics != CN_HOLONOMIC) ? (double)s_th[i] : 0.0;
+        bool vis = true;
+        double raw_r;
+        if (g.gl < H - 1) {
+            const int j = g.gl + (g.gl >= i ? 1 : 0);
+            const float4 o = s_pv[j];
+            ox = o.x; oy = o.y; ovx = o.z; ovy = o.w; raw_r = (double)s_gr[j].z;
+            if (limited) vis = detect_visible_d(cfg.kinematics, me.x, me.y, me.z, me.w, my_th, ox, oy, cfg.human_fov);
+            if (!vis) raw_r = cfg.human_radius;
+        } else {
+            ox = rob_pv.x; oy = rob_pv.y; ovx = rob_pv.z; ovy = rob_pv.w; raw_r = (double)rob_radius;
+            if (limited) vis = detect_visible_d(cfg.kinematics, me.x, me.y, me.z, me.w, my_th, ox, oy, cfg.human_fov);
+            if (!vis) raw_r = cfg.robot_radius;
+        }
+        if (!vis) { ox = 7.0f; oy = 7.0f; ovx = 0.0f; ovy = 0.0f; }   // dummy_human, crowd_sim.py:161-163
+        orad = (float)(raw_r + 0.01 + (double)cfg.orca_safety_space);
+    }
+    (void)rob_theta;
+
+    // computeNeighbors: everyone strictly inside neighborDist, ascending (distSq, index)
+    const float ddx = me.x - ox, ddy = me.y - oy;
+    const float dist_sq = ddx * ddx + ddy * ddy;
+    const bool in = have && dist_sq < cfg.orca_neighbor_dist * cfg.orca_neighbor_dist;
+    const unsigned in_bits = g.ballot(in);
+    const int n = __popc(in_bits);
+    int rank = 0;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const float dk = g.shfl(dist_sq, k);
+        if (((in_bits >> k) & 1u) && (dk < dist_sq || (dk == dist_sq && k < g.gl))) ++rank;
+    }
+
+    // computeNewVelocity: this lane's half-plane
+    Line ln; ln.px = ln.py = ln.dx = ln.dy = 0.0f;
+    if (in) {
+        const float rpx = ox - me.x, rpy = oy - me.y;
+        const float rvx = me.z - ovx, rvy = me.w - ovy;
+        const float dsq = rpx * rpx + rpy * rpy;
+        const float R = radius + orad;
+        const float R2 = R * R;
+        float ux, uy;
+        if (dsq > R2) {
+            const float inv_tau = 1.0f / cfg.orca_time_horizon;
+            const float wx = rvx - inv_tau * rpx, wy = rvy - inv_tau * rpy;
+            const float wl2 = wx * wx + wy * wy;
+            const float dp1 = wx * rpx + wy * rpy;
+            if (dp1 < 0.0f && dp1 * dp1 > R2 * wl2) {
+                const float wl = sqrtf(wl2);
+                const float inv = 1.0f / wl;
+                const float uwx = wx * inv, uwy = wy * inv;
+                ln.dx = uwy; ln.dy = -uwx;
+                const float sc = R * inv_tau - wl;
+                ux = sc * uwx; uy = sc * uwy;
+            } else {
+                const float leg = sqrtf(dsq - R2);
+                const float inv = 1.0f / dsq;
+                if (det2(rpx, rpy, wx, wy) > 0.0f) {
+                    ln.dx = (rpx * leg - rpy * R) * inv; ln.dy = (rpx * R + rpy * leg) * inv;
+                } else {
+                    ln.dx = -((rpx * leg + rpy * R) * inv); ln.dy = -((-rpx * R + rpy * leg) * inv);
+                }
+                const float dp2 = rvx * ln.dx + rvy * ln.dy;
+                ux = dp2 * ln.dx - rvx; uy = dp2 * ln.dy - rvy;
+            }
+        } else {
+            const float inv_dt = 1.0f / (float)cfg.time_step;
+            const float wx = rvx - inv_dt * rpx, wy = rvy - inv_dt * rpy;
+            const float wl = sqrtf(wx * wx + wy * wy);
+            const float inv = 1.0f / wl;
+            const float uwx = wx * inv, uwy = wy * inv;
+            ln.dx = uwy; ln.dy = -uwx;
+            const float sc = R * inv_dt - wl;
+            ux = sc * uwx; uy = sc * uwy;
+        }
+        ln.px = me.z + 0.5f * ux; ln.py = me.w + 0.5f * uy;
+        s_scratch[rank] = make_float4(ln.px, ln.py, ln.dx, ln.dy);
+    }
+    __syncwarp(g.gmask);
+    const bool valid = g.gl < n;
+    if (valid) { const float4 t = s_scratch[g.gl]; ln.px = t.x; ln.py = t.y; ln.dx = t.z; ln.dy = t.w; }
+    __syncwarp(g.gmask);
+
+    float rx, ry;
+    const int fail = lp2_group<G>(g, ln, valid, max_speed, prefx, prefy, false, rx, ry);
+    if (fail >= 0) lp3_group<G>(g, ln, n, fail, max_speed, rx, ry);
+    return make_float2(rx, ry);
+}
+
+// ---------------------------------------------------------------------------------------------- phase B helpers
+__device__ __forceinline__ void velocity_rect_d(double px, double py, double vx, double vy, double radius, double q[4][2])
+{
+    const double w = 2.0 * radius * 1.0;
+    const double L = 3.0 * sqrt(vx * vx + vy * vy);
+    const double heading = atan2(vy, vx);
+    const double dth = heading - CN_PI / 2.0;
+    const double xos = px + radius * cos(heading);
+    const double yos = py + radius * sin(heading);
+    double c = cos(dth), s = sin(dth);
+    if (fabs(c) < 2.5e-16) c = 0.0;
+    if (fabs(s) < 2.5e-16) s = 0.0;
+    const double bx[4] = {w / 2, w / 2, -w / 2, -w / 2};
+    const double by[4] = {-L / 2, L / 2, L / 2, -L / 2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double x = bx[k] + 0.0, y = by[k] + L / 2;
+        const double xr = c * x + (-s) * y + 0.0;
+        const double yr = s * x + c * y + 0.0;
+        q[k][0] = xr + xos; q[k][1] = yr + yos;
+    }
+}
+
+__device__ __forceinline__ bool rects_intersect_d(const double a[4][2], const double b[4][2])
+{
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double p0x = which ? b[k][0] : a[k][0], p0y = which ? b[k][1] : a[k][1];
+            const double p1x = which ? b[(k + 1) & 3][0] : a[(k + 1) & 3][0];
+            const double p1y = which ? b[(k + 1) & 3][1] : a[(k + 1) & 3][1];
+            const double ax = -(p1y - p0y), ay = p1x - p0x;
+            double a0 = INFINITY, a1 = -INFINITY, b0 = INFINITY, b1 = -INFINITY;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const double va = a[m][0] * ax + a[m][1] * ay;
+                const double vb = b[m][0] * ax + b[m][1] * ay;
+                a0 = va < a0 ? va : a0; a1 = va > a1 ? va : a1;
+                b0 = vb < b0 ? vb : b0; b1 = vb > b1 ? vb : b1;
+            }
+            if (a1 < b0 || b1 < a0) return false;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ bool inside_world_d(double px, double py, double r, double t)
+{
+    const double wx[5] = {-t, t, t, -t, -t};
+    const double wy[5] = {-t, -t, t, t, -t};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double ax = wx[k], ay = wy[k];
+        const double dx = wx[k + 1] - ax, dy = wy[k + 1] - ay;
+        const double l2 = dx * dx + dy * dy;
+        double tt = ((px - ax) * dx + (py - ay) * dy) / l2;
+        tt = tt < 0.0 ? 0.0 : (tt > 1.0 ? 1.0 : tt);
+        const double cx = ax + tt * dx, cy = ay + tt * dy;
+        const double d2 = (px - cx) * (px - cx) + (py - cy) * (py - cy);
+        if (d2 <= r * r) return false;
+    }
+    return true;
+}
+
+// does goal (gx,gy) of human i come within min_dist of any other agent's position or goal (crowd_sim.py:750-759)
+__device__ __forceinline__ bool goal_collides(const CnConfig &cfg, int H, int i, double gx, double gy, const float4 *s_pv,
+                                              const float4 *s_gr, float4 rob_pv, float4 rob_gr)
+{
+    const double ri = (double)s_gr[i].z, dd = cfg.discomfort_dist;
+    {
+        const double md = ri + (double)rob_gr.z + dd;
+        if (norm2d(gx - (double)rob_pv.x, gy - (double)rob_pv.y) < md ||
+            norm2d(gx - (double)rob_gr.x, gy - (double)rob_gr.y) < md) return true;
+    }
+    for (int k = 0; k < H; ++k) {
+        if (k == i) continue;
+        const float4 p = s_pv[k], q = s_gr[k];
+        const double md = ri + (double)q.z + dd;
+        if (norm2d(gx - (double)p.x, gy - (double)p.y) < md || norm2d(gx - (double)q.x, gy - (double)q.y) < md) return true;
+    }
+    return false;
+}
+
+// one warp finishes one env: reward/done/info, integration, observation, goal updates
+__device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &out, const float *__restrict__ action, int e,
+                                         int lane, float4 *s_pv, float4 *s_gr, const float2 *s_nv)
+{
+    const CnConfig &cfg = P.cfg;
+    const int H = cfg.human_num;
+    const unsigned FULL = 0xffffffffu;
+    const double dt = cfg.time_step;
+    float4 rpv = P.a.rob_pv[e];
+    float4 rgr = P.a.rob_gr[e];
+    float4 rx = P.a.rob_x[e];          // theta, desired_v, potential, episode_return
+    float2 racc = P.a.rob_acc[e];
+    int4 ctr = P.a.ctr[e];
+
+    // ---- clip_action in float32 (srnn.py:18-48)
+    float a0 = action[2 * (size_t)e], a1 = action[2 * (size_t)e + 1];
+    double act_v = 0.0, act_r = 0.0, avx, avy;
+    if (cfg.kinematics == CN_HOLONOMIC) {
+        const float nrm = sqrtf(a0 * a0 + a1 * a1);
+        if (nrm > rgr.w) { a0 = a0 / nrm * rgr.w; a1 = a1 / nrm * rgr.w; }
+        avx = a0; avy = a1;
+    } else {
+        a0 = fminf(fmaxf(a0, -0.1f), 0.1f);
+        a1 = fminf(fmaxf(a1, -0.1f), 0.1f);
+        double dv = (double)rx.y + (double)a0;
+        const double vp = rgr.w;
+        dv = dv < -vp ? -vp : (dv > vp ? vp : dv);
+        rx.y = (float)dv;
+        act_v = (double)rx.y; act_r = (double)a1;
+        avx = act_v * cos((double)rx.x + act_r);     // patch P1 velocity for SM4/SM5
+        avy = act_v * sin((double)rx.x + act_r);
+    }
+
+    // ---- calc_reward on the pre-step state; lane i <-> human i
+    const bool act = lane < H;
+    const float4 hpv = act ? s_pv[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 hgr = act ? s_gr[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const double hdx = (double)hpv.x - (double)rpv.x, hdy = (double)hpv.y - (double)rpv.y;
+    const double closest = sqrt(hdx * hdx + hdy * hdy) - (double)hgr.z - (double)rgr.z;
+    const unsigned cbits = __ballot_sync(FULL, act && closest < 0.0);
+    const int first_coll = cbits ? (__ffs(cbits) - 1) : H;
+    const bool collision = cbits != 0u;
+    const bool counted = act && lane < first_coll;
+    double dmin = counted ? closest : (double)INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = shfl_d(FULL, dmin, lane ^ o);
+        dmin = other < dmin ? other : dmin;
+    }
+    double rvr[4][2], hvr[4][2];
+    velocity_rect_d(rpv.x, rpv.y, rpv.z, rpv.w, rgr.z, rvr);
+    velocity_rect_d(hpv.x, hpv.y, hpv.z, hpv.w, hgr.z, hvr);
+    const int vec_viol = __popc(__ballot_sync(FULL, counted && rects_intersect_d(rvr, hvr)));
+    const bool h_reached = norm2d((double)hpv.x - (double)hgr.x, (double)hpv.y - (double)hgr.y) < (double)hgr.z;
+    int agg_nav = __popc(__ballot_sync(FULL, counted && !h_reached));
+    const double dgoal = norm2d((double)rpv.x - (double)rgr.x, (double)rpv.y - (double)rgr.y);
+    const bool reaching_goal = dgoal < (double)rgr.z;
+    if (!reaching_goal) agg_nav += 1;
+
+    // ---- robot end pose (agent.py:172-212)
+    double npx, npy, nth = rx.x, nvx, nvy;
+    if (cfg.kinematics == CN_HOLONOMIC) {
+        npx = (double)rpv.x + avx * dt; npy = (double)rpv.y + avy * dt; nvx = avx; nvy = avy;
+    } else {
+        double Rr;
+        if (fabs(act_r) < 0.0001) Rr = 0.0;
+        else { const double w = act_r / dt; Rr = act_v / w; }
+        const double th = rx.x;
+        npx = (double)rpv.x - Rr * sin(th) + Rr * sin(th + act_r);
+        npy = (double)rpv.y + Rr * cos(th) - Rr * cos(th + act_r);
+        nth = fmod(th + act_r, 2.0 * CN_PI);
+        if (nth < 0.0) nth += 2.0 * CN_PI;
+        nvx = act_v * cos(nth); nvy = act_v * sin(nth);
+    }
+
+    // ---- step_info (crowd_sim.py:973-1030)
+    float side_left = 0.f, side_right = 0.f, separation = 0.f;
+    if (cfg.side_preference) {
+        const float4 h0 = s_pv[0];
+        const float4 g0 = s_gr[0];
+        if (npy <= (double)h0.y + (double)g0.z && npy >= (double)h0.y - (double)g0.z) {
+            if (npx < (double)h0.x) side_left = 1.f; else side_right = 1.f;
+        }
+        separation = (float)norm2d((double)h0.x - (double)rpv.x, (double)h0.y - (double)rpv.y);
+    }
+    const double ax = avx - (double)rpv.z, ay = avy - (double)rpv.w;
+    const double dax = ax - (double)racc.x, day = ay - (double)racc.y;
+    const float jerk = (float)(dax * dax + day * day);
+    racc.x = (float)ax; racc.y = (float)ay;
+    const bool inside = inside_world_d(rpv.x, rpv.y, rgr.z, cfg.square_width / 2.0);
+    const float speed_viol = (sqrt(avx * avx + avy * avy) > cfg.max_walking_speed) ? 1.f : 0.f;
+
+    // ---- reward / done / event (crowd_sim.py:1032-1092)
+    double reward;
+    int done, event;
+    const int s = ctr.x;
+    if (s >= cfg.timeout_step) { reward = 0.0; done = 1; event = CN_EV_TIMEOUT; }
+    else if (collision || !inside) { reward = cfg.collision_penalty; done = 1; event = CN_EV_COLLISION; }
+    else if (reaching_goal) {
+        reward = cfg.success_reward;
+        if (cfg.time_factor) reward *= (cfg.time_limit - (double)s * dt) / cfg.time_limit;
+        done = 1; event = CN_EV_REACH_GOAL;
+    } else if (dmin < cfg.discomfort_dist) {
+        reward = (dmin - cfg.discomfort_dist) * cfg.discomfort_penalty_factor; done = 0; event = CN_EV_DANGER;
+    } else {
+        reward = 0.0;
+        if (cfg.potential_based) {
+            reward = cfg.potential_factor * (-fabs(dgoal) - (double)rx.z);
+            rx.z = (float)(-fabs(dgoal));
+        } else if (cfg.exponential) {
+            reward = cfg.exp_factor * (1.0 - pow(dgoal / cfg.exp_denom, 0.4));
+        }
+        done = 0; event = CN_EV_NOTHING;
+    }
+    if (cfg.kinematics == CN_UNICYCLE) {
+        const double r_spin = -2.0 * act_r * act_r;
+        const double r_back = (act_v < 0.0) ? -2.0 * fabs(act_v) : 0.0;
+        reward = reward + r_spin + r_back;
+    }
+
+    // ---- apply the actions; the state holds float32
+    rpv = make_float4((float)npx, (float)npy, (float)nvx, (float)nvy);
+    rx.x = (float)nth;
+    float4 npv = hpv;
+    if (act) {
+        const float2 nv = s_nv[lane];
+        npv = make_float4((float)((double)hpv.x + (double)nv.x * dt), (float)((double)hpv.y + (double)nv.y * dt), nv.x, nv.y);
+        s_pv[lane] = npv;
+        P.a.hum_pv[(size_t)e * H + lane] = npv;
+    }
+    ctr.x = s + 1;
+    __syncwarp();
+
+    // ---- generate_ob: FOV mask, belief, observation (crowd_sim_dict.py:72-103)
+    bool vis = false;
+    if (act) {
+        if (cfg.robot_fov >= 2.0 * CN_PI) vis = !((double)npv.x - (double)rpv.x == 0.0 && (double)npv.y - (double)rpv.y == 0.0);
+        else vis = detect_visible_d(cfg.kinematics, rpv.x, rpv.y, rpv.z, rpv.w, rx.x, npv.x, npv.y, cfg.robot_fov);
+        const size_t hi = (size_t)e * H + lane;
+        float4 bel;
+        if (vis) { bel = npv; P.a.hum_br[hi] = hgr.z; }
+        else {
+            bel = P.a.hum_bel[hi];
+            bel.x = (float)((double)bel.x + (double)bel.z * dt);
+            bel.y = (float)((double)bel.y + (double)bel.w * dt);
+        }
+        P.a.hum_bel[hi] = bel;
+        reinterpret_cast<float2 *>(out.obs.spatial_edges)[hi] =
+            make_float2((float)((double)bel.x - (double)rpv.x), (float)((double)bel.y - (double)rpv.y));
+    }
+    const unsigned vis_bits = __ballot_sync(FULL, vis);
+    if (lane < 7) {
+        const float v = lane == 0 ? rpv.x : lane == 1 ? rpv.y : lane == 2 ? rgr.z : lane == 3 ? rgr.x
+                      : lane == 4 ? rgr.y : lane == 5 ? rgr.w : rx.x;
+        out.obs.robot_node[(size_t)e * 7 + lane] = v;
+    } else if (lane < 9) {
+        out.obs.temporal_edges[(size_t)e * 2 + (lane - 7)] = lane == 7 ? rpv.z : rpv.w;
+    }
+
+    // ---- goal re-sampling (crowd_sim_dict.py:261-269; crowd_sim.py:724-811), bounded tries, lane t <-> try t
+    unsigned changed = 0u;
+    const uint32_t su = (uint32_t)ctr.x;
+    const uint64_t key = step_key(cfg, ctr.y, e);
+    if (cfg.random_goal_changing && su < 32u * CN_STEP_TABLE_WORDS && ((cfg.goal_change_steps[su >> 5] >> (su & 31)) & 1u)) {
+        for (int i = 0; i < H; ++i) {
+            const float4 gi = s_gr[i];
+            if (gi.w == 0.0f) continue;
+            const uint4 dec = philox4x32(key, RNG_DECISION, (uint32_t)i, su, RNG_GOAL_RANDOM);
+            if (!(u01(dec.x) <= cfg.goal_change_chance)) continue;
+            for (int t0 = 0; t0 < cfg.max_goal_tries; t0 += 32) {
+                const int t = t0 + lane;
+                const uint4 x = philox4x32(key, (uint32_t)t, (uint32_t)i, su, RNG_GOAL_RANDOM);
+                const double angle = u01(x.x) * CN_PI * 2.0;
+                const double vp = (double)gi.w;
+                const double gx = cfg.circle_radius * cos(angle) + (u01(x.y) - 0.5) * vp;
+                const double gy = cfg.circle_radius * sin(angle) + (u01(x.z) - 0.5) * vp;
+                const bool ok = t < cfg.max_goal_tries && !goal_collides(cfg, H, i, gx, gy, s_pv, s_gr, rpv, rgr);
+                const unsigned okb = __ballot_sync(FULL, ok);
+                if (okb) {
+                    const int src = __ffs(okb) - 1;
+                    const float ngx = (float)shfl_d(FULL, gx, src), ngy = (float)shfl_d(FULL, gy, src);
+                    if (lane == 0) {
+                        s_gr[i] = make_float4(ngx, ngy, gi.z, gi.w);
+                        P.a.hum_gr[(size_t)e * H + i] = make_float4(ngx, ngy, gi.z, gi.w);
+                    }
+                    changed |= 1u << i;
+                    break;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (cfg.end_goal_changing) {
+        for (int i = 0; i < H; ++i) {
+            const float4 pi_ = s_pv[i];
+            const float4 gi = s_gr[i];
+            if (!(norm2d((double)gi.x - (double)pi_.x, (double)gi.y - (double)pi_.y) < (double)gi.z)) continue;
+            const uint4 dec = philox4x32(key, RNG_DECISION, (uint32_t)i, su, RNG_GOAL_END);
+            if (!(u01(dec.x) <= cfg.end_goal_change_chance)) continue;
+            for (int t0 = 0; t0 < cfg.max_goal_tries; t0 += 32) {
+                const int t = t0 + lane;
+                const uint4 xa = philox4x32(key, (uint32_t)(2 * t), (uint32_t)i, su, RNG_GOAL_END);
+                const uint4 xb = philox4x32(key, (uint32_t)(2 * t + 1), (uint32_t)i, su, RNG_GOAL_END);
+                const double u6[6] = {u01(xa.x), u01(xa.y), u01(xa.z), u01(xa.w), u01(xb.x), u01(xb.y)};
+                const SpawnCand c = agent_attributes(cfg, ctr.w, (double)gi.z, (double)gi.w, (double)rgr.z, u6);
+                const bool ok = t < cfg.max_goal_tries && !goal_collides(cfg, H, i, c.gx, c.gy, s_pv, s_gr, rpv, rgr);
+                const unsigned okb = __ballot_sync(FULL, ok);
+                if (okb) {
+                    const int src = __ffs(okb) - 1;
+                    const float ngx = (float)shfl_d(FULL, c.gx, src), ngy = (float)shfl_d(FULL, c.gy, src);
+                    if (lane == 0) {
+                        s_gr[i] = make_float4(ngx, ngy, gi.z, gi.w);
+                        P.a.hum_gr[(size_t)e * H + i] = make_float4(ngx, ngy, gi.z, gi.w);
+                    }
+                    changed |= 1u << i;
+                    break;
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- per-env scalars
+    rx.w = (float)((double)rx.w + reward);
+    if (lane == 0) {
+        P.a.rob_pv[e] = rpv;
+        P.a.rob_x[e] = rx;
+        P.a.rob_acc[e] = racc;
+        P.a.ctr[e] = ctr;
+        out.reward[e] = (float)reward;
+        out.done[e] = (uint8_t)done;
+        out.event[e] = event;
+        if (out.scenario) out.scenario[e] = ctr.w;
+        if (out.episode_return) out.episode_return[e] = rx.w;
+        if (out.episode_length) out.episode_length[e] = ctr.x;
+        if (out.obs.visible_mask) out.obs.visible_mask[e] = vis_bits;
+        if (out.goal_changed) out.goal_changed[e] = changed;
+    }
+    if (out.info && lane < CN_INFO_DIM) {
+        float v = 0.f;
+        switch (lane) {
+        case CN_INFO_DMIN: v = (float)dmin; break;
+        case CN_INFO_AGGREGATE_NAV_TIME: v = (float)agg_nav; break;
+        case CN_INFO_PATH_VIOLATION: v = (float)vec_viol; break;
+        case CN_INFO_PERSONAL_VIOLATION: v = (dmin < cfg.min_personal_space) ? 1.f : 0.f; break;
+        case CN_INFO_JERK_COST: v = jerk; break;
+        case CN_INFO_DIST_TO_GOAL: v = (float)dgoal; break;
+        case CN_INFO_SPEED_VIOLATION: v = speed_viol; break;
+        case CN_INFO_SIDE_LEFT: v = side_left; break;
+        case CN_INFO_SIDE_RIGHT: v = side_right; break;
+        case CN_INFO_SEPARATION: v = separation; break;
+        default: break;
+        }
+        out.info[(size_t)e * CN_INFO_DIM + lane] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+// grid: ceil(N / E) CTAs of 256 threads, each owning E consecutive envs.
+// dynamic smem: E*H*(float4 pv + float4 gr + float2 nv + float th) + 256 float4 sort scratch
+template <int G>
+__global__ void __launch_bounds__(STEP_THREADS)
+crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnStepOut out,
+                  const float *__restrict__ action, int E)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const CnConfig &cfg = P.cfg;
+    const int H = cfg.human_num;
+    const int e0 = blockIdx.x * E;
+    const int ne = min(E, P.n_envs - e0);
+    const int EH = E * H;
+    float4 *s_pv = reinterpret_cast<float4 *>(smem_raw);
+    float4 *s_gr = s_pv + EH;
+    float4 *s_scr = s_gr + EH;
+    float2 *s_nv = reinterpret_cast<float2 *>(s_scr + STEP_THREADS);
+    float *s_th = reinterpret_cast<float *>(s_nv + EH);
+    __shared__ float4 s_rob_pv[64];
+    __shared__ float2 s_rob_rt[64];   // radius, theta
+
+    // stage: coalesced float4 loads of ne*H consecutive humans
+    const size_t base = (size_t)e0 * H;
+    const bool need_th = cfg.human_fov < 2.0 * CN_PI && cfg.kinematics != CN_HOLONOMIC;
+    for (int k = threadIdx.x; k < ne * H; k += STEP_THREADS) {
+        s_pv[k] = P.a.hum_pv[base + k];
+        s_gr[k] = P.a.hum_gr[base + k];
+        if (need_th) s_th[k] = P.a.hum_th[base + k];
+    }
+    if (cfg.robot_visible) {
+        for (int k = threadIdx.x; k < ne; k += STEP_THREADS) {
+            s_rob_pv[k] = P.a.rob_pv[e0 + k];
+            s_rob_rt[k] = make_float2(P.a.rob_gr[e0 + k].z, P.a.rob_x[e0 + k].x);
+        }
+    }
+    __syncthreads();
+
+    // phase A: ORCA, one G-lane group per (env, human) task
+    {
+        GroupOps<G> g;
+        const int lane = threadIdx.x & 31;
+        g.gl = lane % G;
+        g.gbase = lane - g.gl;
+        g.gmask = (G == 32) ? 0xffffffffu : (GroupOps<G>::kLow << g.gbase);
+        const int group = threadIdx.x / G;
+        constexpr int kGroups = STEP_THREADS / G;
+        float4 *scratch = s_scr + group * G;
+        for (int task = group; task < ne * H; task += kGroups) {
+            const int el = task / H, i = task - el * H;
+            const float4 rob = cfg.robot_visible ? s_rob_pv[el] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float2 rrt = cfg.robot_visible ? s_rob_rt[el] : make_float2(0.f, 0.f);
+            const float2 nv = orca_group<G>(cfg, g, i, H, s_pv + el * H, s_gr + el * H, s_th + el * H, rob, rrt.x, rrt.y, scratch);
+            if (g.gl == 0) s_nv[task] = nv;
+        }
+    }
+    __syncthreads();
+
+    // phase B: one warp per env
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int el = warp; el < ne; el += STEP_THREADS / 32)
+            env_tail(P, out, action, e0 + el, lane, s_pv + el * H, s_gr + el * H, s_nv + el * H);
+    }
+}
+
+static inline int pick_group(int M)
+{
+    return M <= 4 ? 4 : (M <= 8 ? 8 : (M <= 16 ? 16 : 32));
+}
+
+// host launcher (called from c_abi.cu)
+extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, cudaStream_t stream)
+{
+    const int H = P->cfg.human_num;
+    const int M = H - 1 + (P->cfg.robot_visible ? 1 : 0);
+    const int G = pick_group(M < 1 ? 1 : M);
+    // envs per CTA: ~2 rounds of ORCA groups per CTA, at most 64 (s_rob_* capacity), at least 8 (one tail warp each)
+    int E = (2 * (STEP_THREADS / G) + H - 1) / H;
+    E = E < 8 ? 8 : (E > 64 ? 64 : E);
+    const size_t smem = (size_t)E * H * (16 + 16 + 8 + 4) + STEP_THREADS * 16;
+    const int grid = (P->n_envs + E - 1) / E;
+    switch (G) {
+    case 4: crowd_step_kernel<4><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E); break;
+    case 8: crowd_step_kernel<8><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E); break;
+    case 16: crowd_step_kernel<16><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E); break;
+    default: crowd_step_kernel<32><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E); break;
+    }
+    return (int)cudaGetLastError();
+}

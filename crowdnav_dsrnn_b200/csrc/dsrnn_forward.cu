@@ -1,0 +1,430 @@
+// dsrnn_forward.cu -- K3: DS-RNN policy forward for one rollout step (sm_100a).
+//
+// SRNN.forward(infer=True) + DiagGaussian.fc_mean
+// (pytorchBaselines/a2c_ppo_acktr/srnn_model.py:409-504, distributions.py:85-94):
+//   stage 1  edge GRUs: rows = N temporal edges + N*H spatial edges, per row
+//            e = ReLU(W_enc x + b), GRU(64 -> 256) on the masked hidden state        (srnn_model.py:201-215, 37-50)
+//   stage 2  attention: q = W_t o_t, k_i = W_s o_i, softmax_i(q.k_i * H/sqrt(64)), c = sum a_i o_i   (:256-339)
+//   stage 3  node: x = [ReLU(W_ne (W_r robot + b) + b) | ReLU(W_na [o_t|c] + b)], GRU(128 -> 128), y = W_out h  (:149-173)
+//   stage 4  heads: actor / critic tanh MLPs, critic_linear, fc_mean                 (:378-395, 487-495)
+//
+// This file holds the fp32 CUDA-core implementation (precision CN_PREC_FP32: the exact mode and the
+// in-library reference for the tensor-core edge stage in dsrnn_edge_tc.cu) and the stage 2-4 kernels
+// every precision shares.
+#include <cstdio>
+#include <new>
+#include "dsrnn.cuh"
+
+struct CnDsrnn {
+    CnDsrnnWeights w;
+    int device;
+    int last_launches;
+    void *tc_state;   // packed bf16 weights of the tensor-core edge stage (dsrnn_edge_tc.cu)
+};
+
+// implemented in dsrnn_edge_tc.cu
+const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void **state);
+void dsrnn_tc_destroy(void *state);
+const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *w, int n_envs, int H, const CnDsrnnIO *io,
+                                  int precision, cudaStream_t stream, int *launches);
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+
+// ---------------------------------------------------------------------------------------------- generic linear
+struct LinArgs {
+    const float *X; int ldx;
+    int rows_per_env, env_stride_rows, first_row;   // memory row of logical row m: (m / rpe) * stride + first + m % rpe
+    const float *rowscale;                          // optional [M / rows_per_env] multiplier of the input rows (the mask)
+    const float *W; const float *b;                 // W [N, K] row-major
+    int M, N, K;
+    float *Y; int ldy; int ycol0;
+    int act;
+};
+
+#define LBM 64
+#define LBN 64
+#define LBK 16
+
+// Y[m, ycol0 + n] = act(sum_k X[row(m), k] * W[n, k] + b[n]); K % 16 == 0, 16-byte aligned rows
+__global__ void __launch_bounds__(256) linear_simt_kernel(const LinArgs a)
+{
+    __shared__ float As[LBK][LBM + 4];
+    __shared__ float Bs[LBK][LBN + 4];
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * LBN;
+    const int lr = t >> 2, lk = (t & 3) * 4;
+    const int tx = t & 15, ty = t >> 4;
+    float acc[4][4] = {};
+    const int am = m0 + lr;
+    const bool a_ok = am < a.M;
+    size_t a_row = 0;
+    float a_scale = 1.0f;
+    if (a_ok) {
+        const int env = am / a.rows_per_env;
+        a_row = (size_t)env * a.env_stride_rows + a.first_row + (am - env * a.rows_per_env);
+        if (a.rowscale) a_scale = a.rowscale[env];
+    }
+    const int bn = n0 + lr;
+    const bool b_ok = bn < a.N;
+    for (int k0 = 0; k0 < a.K; k0 += LBK) {
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+        if (a_ok) av = *reinterpret_cast<const float4 *>(a.X + a_row * a.ldx + k0 + lk);
+        if (b_ok) bv = *reinterpret_cast<const float4 *>(a.W + (size_t)bn * a.K + k0 + lk);
+        As[lk + 0][lr] = av.x * a_scale; As[lk + 1][lr] = av.y * a_scale;
+        As[lk + 2][lr] = av.z * a_scale; As[lk + 3][lr] = av.w * a_scale;
+        Bs[lk + 0][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LBK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float ar[4] = {a4.x, a4.y, a4.z, a4.w}, br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= a.N) continue;
+            float v = acc[i][j] + (a.b ? a.b[n] : 0.0f);
+            if (a.act == ACT_RELU) v = fmaxf(v, 0.0f);
+            else if (a.act == ACT_TANH) v = tanhf(v);
+            a.Y[(size_t)m * a.ldy + a.ycol0 + n] = v;
+        }
+    }
+}
+
+static void launch_linear(const LinArgs &a, cudaStream_t s, int *launches)
+{
+    dim3 grid((a.M + LBM - 1) / LBM, (a.N + LBN - 1) / LBN);
+    linear_simt_kernel<<<grid, 256, 0, s>>>(a);
+    ++*launches;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------- stage 1 (fp32)
+// Edge GRU for one weight set.  Logical row m -> (env = m / rpe, memory row env*(H+1) + first + m % rpe).
+struct EdgeArgs {
+    const float *x_in;      // [rows, 2] edge features (temporal_edges or spatial_edges, contiguous)
+    const float *h_in;      // [N, H+1, 256]
+    const float *masks;     // [N]
+    const float *enc_w, *enc_b, *w_ih, *w_hh, *b_ih, *b_hh;
+    float *h_out;           // [N, H+1, 256]
+    int M, rpe, stride, first;
+};
+
+// tile: 64 rows x 64 hidden units (x3 gates), K = 64 (encoded input) + 256 (hidden)
+__global__ void __launch_bounds__(256) edge_gru_simt_kernel(const EdgeArgs a)
+{
+    __shared__ float As[LBK][LBM + 4];
+    __shared__ float Ws[3][LBK][LBN + 4];
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * LBN;
+    const int lr = t >> 2, lk = (t & 3) * 4;
+    const int tx = t & 15, ty = t >> 4;
+    float acc_r[4][4] = {}, acc_z[4][4] = {}, acc_ni[4][4] = {}, acc_nh[4][4] = {};
+    const int am = m0 + lr;
+    const bool a_ok = am < a.M;
+    size_t a_row = 0;
+    float mask = 0.0f, x0 = 0.0f, x1 = 0.0f;
+    if (a_ok) {
+        const int env = am / a.rpe;
+        a_row = (size_t)env * a.stride + a.first + (am - env * a.rpe);
+        mask = a.masks[env];
+        x0 = a.x_in[2 * (size_t)am]; x1 = a.x_in[2 * (size_t)am + 1];
+    }
+    for (int k0 = 0; k0 < 320; k0 += LBK) {
+        const bool xr = k0 < 64;
+        float av[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a_ok) {
+            if (xr) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = k0 + lk + i;
+                    av[i] = fmaxf(fmaf(a.enc_w[2 * k + 1], x1, fmaf(a.enc_w[2 * k], x0, 0.0f)) + a.enc_b[k], 0.0f);
+                }
+            } else {
+                const float4 h4 = *reinterpret_cast<const float4 *>(a.h_in + a_row * 256 + (k0 - 64) + lk);
+                av[0] = h4.x * mask; av[1] = h4.y * mask; av[2] = h4.z * mask; av[3] = h4.w * mask;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) As[lk + i][lr] = av[i];
+#pragma unroll
+        for (int gate = 0; gate < 3; ++gate) {
+            const int wrow = gate * 256 + n0 + lr;
+            const float4 w4 = xr ? *reinterpret_cast<const float4 *>(a.w_ih + (size_t)wrow * 64 + k0 + lk)
+                                 : *reinterpret_cast<const float4 *>(a.w_hh + (size_t)wrow * 256 + (k0 - 64) + lk);
+            Ws[gate][lk + 0][lr] = w4.x; Ws[gate][lk + 1][lr] = w4.y; Ws[gate][lk + 2][lr] = w4.z; Ws[gate][lk + 3][lr] = w4.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LBK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 r4 = *reinterpret_cast<const float4 *>(&Ws[0][k][tx * 4]);
+            const float4 z4 = *reinterpret_cast<const float4 *>(&Ws[1][k][tx * 4]);
+            const float4 n4 = *reinterpret_cast<const float4 *>(&Ws[2][k][tx * 4]);
+            const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float wr[4] = {r4.x, r4.y, r4.z, r4.w}, wz[4] = {z4.x, z4.y, z4.z, z4.w}, wn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc_r[i][j] = fmaf(ar[i], wr[j], acc_r[i][j]);
+                    acc_z[i][j] = fmaf(ar[i], wz[j], acc_z[i][j]);
+                    if (xr) acc_ni[i][j] = fmaf(ar[i], wn[j], acc_ni[i][j]);
+                    else acc_nh[i][j] = fmaf(ar[i], wn[j], acc_nh[i][j]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= a.M) continue;
+        const int env = m / a.rpe;
+        const size_t row = (size_t)env * a.stride + a.first + (m - env * a.rpe);
+        const float mk = a.masks[env];
+        const int c0 = n0 + tx * 4;
+        const float4 hp4 = *reinterpret_cast<const float4 *>(a.h_in + row * 256 + c0);
+        const float hp[4] = {hp4.x * mk, hp4.y * mk, hp4.z * mk, hp4.w * mk};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            const float r = sigmoidf_(acc_r[i][j] + a.b_ih[c] + a.b_hh[c]);
+            const float z = sigmoidf_(acc_z[i][j] + a.b_ih[256 + c] + a.b_hh[256 + c]);
+            const float n = tanhf(acc_ni[i][j] + a.b_ih[512 + c] + r * (acc_nh[i][j] + a.b_hh[512 + c]));
+            o[j] = (1.0f - z) * n + z * hp[j];
+        }
+        *reinterpret_cast<float4 *>(a.h_out + row * 256 + c0) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- stage 2
+// one warp per env: scores, softmax over the H humans, weighted sum; writes cat = [o_t | c]  (N x 512)
+__global__ void __launch_bounds__(128) attention_kernel(const float *__restrict__ h_edge, const float *__restrict__ Q,
+                                                        const float *__restrict__ Kp, float *__restrict__ cat, int N, int H)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 4 + warp;
+    if (e >= N) return;
+    const float q0 = Q[(size_t)e * 64 + lane], q1 = Q[(size_t)e * 64 + 32 + lane];
+    float my_score = -INFINITY;
+    for (int i = 0; i < H; ++i) {
+        const float *k = Kp + ((size_t)e * H + i) * 64;
+        float s = q0 * k[lane] + q1 * k[32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == i) my_score = s * ((float)H / 8.0f);      // temperature = num_edges / sqrt(attention_size)
+    }
+    float mx = my_score;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float ex = lane < H ? expf(my_score - mx) : 0.0f;
+    float sum = ex;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float alpha = ex / sum;
+    const float *ot = h_edge + (size_t)e * (H + 1) * 256;
+    float c[8] = {};
+    for (int i = 0; i < H; ++i) {
+        const float ai = __shfl_sync(0xffffffffu, alpha, i);
+        const float *os = ot + (size_t)(1 + i) * 256;
+        const float4 v0 = *reinterpret_cast<const float4 *>(os + lane * 8);
+        const float4 v1 = *reinterpret_cast<const float4 *>(os + lane * 8 + 4);
+        c[0] = fmaf(ai, v0.x, c[0]); c[1] = fmaf(ai, v0.y, c[1]); c[2] = fmaf(ai, v0.z, c[2]); c[3] = fmaf(ai, v0.w, c[3]);
+        c[4] = fmaf(ai, v1.x, c[4]); c[5] = fmaf(ai, v1.y, c[5]); c[6] = fmaf(ai, v1.z, c[6]); c[7] = fmaf(ai, v1.w, c[7]);
+    }
+    float *dst = cat + (size_t)e * 512;
+    *reinterpret_cast<float4 *>(dst + lane * 8) = *reinterpret_cast<const float4 *>(ot + lane * 8);
+    *reinterpret_cast<float4 *>(dst + lane * 8 + 4) = *reinterpret_cast<const float4 *>(ot + lane * 8 + 4);
+    *reinterpret_cast<float4 *>(dst + 256 + lane * 8) = make_float4(c[0], c[1], c[2], c[3]);
+    *reinterpret_cast<float4 *>(dst + 256 + lane * 8 + 4) = make_float4(c[4], c[5], c[6], c[7]);
+}
+
+// ---------------------------------------------------------------------------------------------- stage 3 helpers
+// x[:, 0:64] = ReLU(W_ne (W_r robot_node + b_r) + b_ne)     (robot_linear 7->3, encoder_linear 3->64)
+__global__ void node_encode_kernel(const float *__restrict__ robot_node, const float *__restrict__ rw, const float *__restrict__ rb,
+                                   const float *__restrict__ ew, const float *__restrict__ eb, float *__restrict__ x, int N)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)N * 64) return;
+    const int e = (int)(idx >> 6), k = (int)(idx & 63);
+    const float *rn = robot_node + (size_t)e * 7;
+    float r3[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) s = fmaf(rw[j * 7 + i], rn[i], s);
+        r3[j] = s + rb[j];
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s = fmaf(ew[k * 3 + j], r3[j], s);
+    x[(size_t)e * 128 + k] = fmaxf(s + eb[k], 0.0f);
+}
+
+// node GRU gates: gi, gh [N,384] (biases already added), h_prev [N,128] masked -> h_out [N,128]
+__global__ void node_gru_gate_kernel(const float *__restrict__ gi, const float *__restrict__ gh, const float *__restrict__ h_prev,
+                                     const float *__restrict__ masks, float *__restrict__ h_out, int N)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)N * 128) return;
+    const int e = (int)(idx >> 7), c = (int)(idx & 127);
+    const float *i3 = gi + (size_t)e * 384, *h3 = gh + (size_t)e * 384;
+    const float r = sigmoidf_(i3[c] + h3[c]);
+    const float z = sigmoidf_(i3[128 + c] + h3[128 + c]);
+    const float n = tanhf(i3[256 + c] + r * h3[256 + c]);
+    h_out[idx] = (1.0f - z) * n + z * (h_prev[idx] * masks[e]);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+struct Workspace {
+    float *Kp, *Q, *cat, *x, *gi, *gh, *y, *a1, *a2, *c1, *c2;
+};
+
+static size_t carve_ws(Workspace *w, void *base, int N, int H)
+{
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](float **p, size_t count) {
+        if (w) *p = (float *)(b ? b + off : nullptr);
+        off = (off + count * sizeof(float) + 255) & ~(size_t)255;
+    };
+    Workspace tmp;
+    Workspace *q = w ? w : &tmp;
+    take(&q->Kp, (size_t)N * H * 64);
+    take(&q->Q, (size_t)N * 64);
+    take(&q->cat, (size_t)N * 512);
+    take(&q->x, (size_t)N * 128);
+    take(&q->gi, (size_t)N * 384);
+    take(&q->gh, (size_t)N * 384);
+    take(&q->y, (size_t)N * 256);
+    take(&q->a1, (size_t)N * 256);
+    take(&q->a2, (size_t)N * 256);
+    take(&q->c1, (size_t)N * 256);
+    take(&q->c2, (size_t)N * 256);
+    return off;
+}
+
+size_t dsrnn_workspace_bytes(int n_envs, int human_num) { return carve_ws(nullptr, nullptr, n_envs, human_num); }
+
+const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t stream, CnDsrnn **out)
+{
+    CnDsrnn *m = new (std::nothrow) CnDsrnn();
+    if (!m) return "out of host memory";
+    m->w = *w;
+    m->device = device;
+    m->last_launches = 0;
+    m->tc_state = nullptr;
+    const char *msg = dsrnn_tc_create(w, stream, &m->tc_state);
+    if (msg) { delete m; return msg; }
+    *out = m;
+    return nullptr;
+}
+
+void dsrnn_destroy(CnDsrnn *m)
+{
+    if (m->tc_state) dsrnn_tc_destroy(m->tc_state);
+    delete m;
+}
+
+const char *dsrnn_update_weights(CnDsrnn *m, const CnDsrnnWeights *w, cudaStream_t stream)
+{
+    m->w = *w;
+    if (m->tc_state) dsrnn_tc_destroy(m->tc_state);
+    m->tc_state = nullptr;
+    return dsrnn_tc_create(w, stream, &m->tc_state);
+}
+
+int dsrnn_last_launches(const CnDsrnn *m) { return m->last_launches; }
+
+static LinArgs lin(const float *X, int ldx, const float *W, const float *b, int M, int N, int K, float *Y, int ldy, int act)
+{
+    LinArgs a;
+    a.X = X; a.ldx = ldx; a.rows_per_env = 1; a.env_stride_rows = 1; a.first_row = 0; a.rowscale = nullptr;
+    a.W = W; a.b = b; a.M = M; a.N = N; a.K = K; a.Y = Y; a.ldy = ldy; a.ycol0 = 0; a.act = act;
+    return a;
+}
+
+const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int precision, void *workspace, cudaStream_t s)
+{
+    if (cudaSetDevice(m->device) != cudaSuccess) return "cudaSetDevice failed";
+    const CnDsrnnWeights &w = m->w;
+    Workspace ws;
+    carve_ws(&ws, workspace, N, H);
+    int launches = 0;
+
+    // ---- stage 1: edge GRUs -> io->h_edge_out
+    if (precision == CN_PREC_FP32) {
+        EdgeArgs t;
+        t.x_in = io->temporal_edges; t.h_in = io->h_edge_in; t.masks = io->masks;
+        t.enc_w = w.t_enc_w; t.enc_b = w.t_enc_b; t.w_ih = w.t_w_ih; t.w_hh = w.t_w_hh; t.b_ih = w.t_b_ih; t.b_hh = w.t_b_hh;
+        t.h_out = io->h_edge_out; t.M = N; t.rpe = 1; t.stride = H + 1; t.first = 0;
+        edge_gru_simt_kernel<<<dim3((t.M + LBM - 1) / LBM, 256 / LBN), 256, 0, s>>>(t);
+        EdgeArgs sp = t;
+        sp.x_in = io->spatial_edges;
+        sp.enc_w = w.s_enc_w; sp.enc_b = w.s_enc_b; sp.w_ih = w.s_w_ih; sp.w_hh = w.s_w_hh; sp.b_ih = w.s_b_ih; sp.b_hh = w.s_b_hh;
+        sp.M = N * H; sp.rpe = H; sp.first = 1;
+        edge_gru_simt_kernel<<<dim3((sp.M + LBM - 1) / LBM, 256 / LBN), 256, 0, s>>>(sp);
+        launches += 2;
+    } else {
+        const char *msg = dsrnn_tc_edge_forward(m->tc_state, &w, N, H, io, precision, s, &launches);
+        if (msg) return msg;
+    }
+
+    // ---- stage 2: attention projections, softmax, weighted sum
+    {
+        LinArgs q = lin(io->h_edge_out, 256, w.att_t_w, w.att_t_b, N, 64, 256, ws.Q, 64, ACT_NONE);
+        q.rows_per_env = 1; q.env_stride_rows = H + 1; q.first_row = 0;
+        launch_linear(q, s, &launches);
+        LinArgs k = lin(io->h_edge_out, 256, w.att_s_w, w.att_s_b, N * H, 64, 256, ws.Kp, 64, ACT_NONE);
+        k.rows_per_env = H; k.env_stride_rows = H + 1; k.first_row = 1;
+        launch_linear(k, s, &launches);
+        attention_kernel<<<(N + 3) / 4, 128, 0, s>>>(io->h_edge_out, ws.Q, ws.Kp, ws.cat, N, H);
+        ++launches;
+    }
+
+    // ---- stage 3: node RNN
+    {
+        node_encode_kernel<<<(unsigned)(((size_t)N * 64 + 255) / 256), 256, 0, s>>>(io->robot_node, w.robot_w, w.robot_b,
+                                                                                  w.n_enc_w, w.n_enc_b, ws.x, N);
+        ++launches;
+        LinArgs emb = lin(ws.cat, 512, w.n_att_w, w.n_att_b, N, 64, 512, ws.x, 128, ACT_RELU);
+        emb.ycol0 = 64;
+        launch_linear(emb, s, &launches);
+        launch_linear(lin(ws.x, 128, w.n_w_ih, w.n_b_ih, N, 384, 128, ws.gi, 384, ACT_NONE), s, &launches);
+        LinArgs gh = lin(io->h_node_in, 128, w.n_w_hh, w.n_b_hh, N, 384, 128, ws.gh, 384, ACT_NONE);
+        gh.rowscale = io->masks;
+        launch_linear(gh, s, &launches);
+        node_gru_gate_kernel<<<(unsigned)(((size_t)N * 128 + 255) / 256), 256, 0, s>>>(ws.gi, ws.gh, io->h_node_in, io->masks,
+                                                                                    io->h_node_out, N);
+        ++launches;
+        launch_linear(lin(io->h_node_out, 128, w.n_out_w, w.n_out_b, N, 256, 128, ws.y, 256, ACT_NONE), s, &launches);
+    }
+
+    // ---- stage 4: heads
+    {
+        float *feat = io->actor_features ? io->actor_features : ws.a2;
+        launch_linear(lin(ws.y, 256, w.actor0_w, w.actor0_b, N, 256, 256, ws.a1, 256, ACT_TANH), s, &launches);
+        launch_linear(lin(ws.a1, 256, w.actor2_w, w.actor2_b, N, 256, 256, feat, 256, ACT_TANH), s, &launches);
+        launch_linear(lin(ws.y, 256, w.critic0_w, w.critic0_b, N, 256, 256, ws.c1, 256, ACT_TANH), s, &launches);
+        launch_linear(lin(ws.c1, 256, w.critic2_w, w.critic2_b, N, 256, 256, ws.c2, 256, ACT_TANH), s, &launches);
+        launch_linear(lin(ws.c2, 256, w.critic_lin_w, w.critic_lin_b, N, 1, 256, io->value, 1, ACT_NONE), s, &launches);
+        launch_linear(lin(feat, 256, w.mean_w, w.mean_b, N, 2, 256, io->action_mean, 2, ACT_NONE), s, &launches);
+    }
+    m->last_launches = launches;
+    const cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}

@@ -1,0 +1,172 @@
+// env_common.cuh -- device-side state layout, RNG and small helpers shared by the
+// crowd-step (K1) and reset (K2) kernels.  sm_100a only.
+//
+// HBM layout (SoA, one blob owned by the caller, carved by cn_env_create):
+//   hum_pv  float4[N*H]  px,py,vx,vy          (read+written every step)
+//   hum_gr  float4[N*H]  gx,gy,radius,v_pref  (read every step, written on goal change / reset)
+//   hum_bel float4[N*H]  belief px,py,vx,vy   (last_human_states, crowd_sim.py:199,429-455)
+//   hum_br  float [N*H]  belief radius
+//   hum_th  float [N*H]  spawn heading (only read when a human FOV < 2*pi with a unicycle robot)
+//   rob_pv  float4[N]    px,py,vx,vy
+//   rob_gr  float4[N]    gx,gy,radius,v_pref
+//   rob_x   float4[N]    theta, desiredVelocity[0], potential, episode_return
+//   rob_acc float2[N]    last_acceleration
+//   ctr     int4  [N]    step_count, scenario_counter, case_counter, current_scenario
+// Humans of one env are contiguous, envs are contiguous: a CTA that owns E
+// consecutive envs reads E*H consecutive float4 (fully coalesced 16 B accesses).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/crowdnav_b200.h"
+
+#define CN_PI 3.141592653589793
+
+struct EnvArrays {
+    float4 *hum_pv, *hum_gr, *hum_bel;
+    float *hum_br, *hum_th;
+    float4 *rob_pv, *rob_gr, *rob_x;
+    float2 *rob_acc;
+    int4 *ctr;
+};
+
+struct EnvParams {
+    CnConfig cfg;
+    EnvArrays a;
+    int n_envs;
+};
+
+static inline size_t cn_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// carve the caller's blob; returns total bytes (base may be NULL to only size it)
+static inline size_t cn_carve(EnvArrays *a, void *base, int n, int H)
+{
+    size_t off = 0;
+    char *b = (char *)base;
+    const size_t nh = (size_t)n * H;
+#define CN_TAKE(field, type, count)                                    \
+    do {                                                               \
+        if (a) a->field = (type *)(b ? b + off : nullptr);             \
+        off = cn_align256(off + sizeof(type) * (count));               \
+    } while (0)
+    CN_TAKE(hum_pv, float4, nh);
+    CN_TAKE(hum_gr, float4, nh);
+    CN_TAKE(hum_bel, float4, nh);
+    CN_TAKE(hum_br, float, nh);
+    CN_TAKE(hum_th, float, nh);
+    CN_TAKE(rob_pv, float4, n);
+    CN_TAKE(rob_gr, float4, n);
+    CN_TAKE(rob_x, float4, n);
+    CN_TAKE(rob_acc, float2, n);
+    CN_TAKE(ctr, int4, n);
+#undef CN_TAKE
+    return off;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 (counter-based RNG contract)
+enum { RNG_RESET = 0, RNG_ATTR = 1, RNG_SPAWN = 2, RNG_GOAL_RANDOM = 3, RNG_GOAL_END = 4 };
+#define RNG_DECISION 0xFFFFFFFFu
+
+__device__ __forceinline__ uint4 philox4x32(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
+{
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double u01(uint32_t x) { return (double)x * (1.0 / 4294967296.0); }
+
+__device__ __forceinline__ uint64_t episode_key(const CnConfig &cfg, int case_counter, int env_local)
+{
+    return cfg.seed_offset + (uint64_t)(uint32_t)case_counter + cfg.base_seed +
+           (uint64_t)(uint32_t)(cfg.env_id_offset + env_local);
+}
+
+__device__ __forceinline__ uint64_t step_key(const CnConfig &cfg, int scenario_counter, int env_local)
+{
+    return (cfg.base_seed + (uint64_t)(uint32_t)(cfg.env_id_offset + env_local)) ^
+           ((uint64_t)(uint32_t)scenario_counter << 32) ^ 0x5EEDC0DE00000000ull;
+}
+
+__device__ __forceinline__ double norm2d(double x, double y) { return sqrt(x * x + y * y); }
+
+__device__ __forceinline__ double shfl_d(unsigned mask, double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(mask, lo, src);
+    hi = __shfl_sync(mask, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
+// detect_visible (crowd_sim/envs/crowd_sim.py:820-847): is (p2) inside the FOV of agent 1.
+// heading_src: atan2(vy,vx) for a holonomic-robot config, the agent's theta otherwise.
+__device__ __forceinline__ bool detect_visible_d(int kinematics, double p1x, double p1y, double v1x, double v1y,
+                                                 double th1, double p2x, double p2y, double fov)
+{
+    const double theta = (kinematics == CN_HOLONOMIC) ? atan2(v1y, v1x) : th1;
+    double fx = cos(theta), fy = sin(theta);
+    double dx = p2x - p1x, dy = p2y - p1y;
+    const double nf = norm2d(fx, fy);
+    fx = fx / nf; fy = fy / nf;
+    const double nd = norm2d(dx, dy);
+    dx = dx / nd; dy = dy / nd;
+    double d = fx * dx + fy * dy;
+    if (d != d) return false;
+    d = d < -1.0 ? -1.0 : (d > 1.0 ? 1.0 : d);
+    return fabs(acos(d)) <= fov / 2.0;
+}
+
+// create_agent_attributes (crowd_sim/envs/crowd_sim.py:296-357) from 6 uniforms
+struct SpawnCand { double px, py, gx, gy, heading, v_pref; };
+
+__device__ __forceinline__ SpawnCand agent_attributes(const CnConfig &cfg, int scenario, double h_radius, double h_vpref,
+                                                      double robot_radius, const double u[6])
+{
+    SpawnCand c;
+    double v_pref = (h_vpref == 0.0) ? 1.0 : h_vpref;
+    const double nx = (u[0] - 0.5) * v_pref, ny = (u[1] - 0.5) * v_pref;
+    const double R = cfg.circle_radius, sw = cfg.square_width;
+    c.heading = 0.0; c.px = c.py = c.gx = c.gy = 0.0;
+#define CN_WORLD(uu) (((uu) - 0.5) * sw / 2.0)
+    switch (scenario) {
+    case CN_SCN_CIRCLE_CROSSING: {
+        const double angle = u[2] * CN_PI * 2.0;
+        c.px = R * cos(angle) + nx; c.py = R * sin(angle) + ny; c.gx = -c.px; c.gy = -c.py;
+    } break;
+    case CN_SCN_SQUARE_CROSSING:
+        c.px = CN_WORLD(u[2]) * 0.4 + nx; c.py = CN_WORLD(u[3]) * 0.4 + ny;
+        c.gx = CN_WORLD(u[4]) * 0.4 + nx; c.gy = CN_WORLD(u[5]) * 0.4 + ny;
+        break;
+    case CN_SCN_PARALLEL_TRAFFIC: {
+        const double sign = (u[2] >= 0.5) ? 1.0 : -1.0;
+        c.px = CN_WORLD(u[3]) * 0.4 + nx; c.py = sign * (u[4] * 3.0 + 1.0 + ny); c.gx = c.px; c.gy = -c.py;
+    } break;
+    case CN_SCN_PERPENDICULAR_TRAFFIC: {
+        const double sign = (u[2] >= 0.5) ? 1.0 : -1.0;
+        c.px = sign * (u[3] * 3.0 + 1.0 + nx); c.gx = -c.px; c.py = CN_WORLD(u[4]) * 0.4 + ny; c.gy = c.py;
+    } break;
+    case CN_SCN_SIDE_PREF_PASSING:
+    case CN_SCN_SIDE_PREF_OVERTAKING: {
+        const double min_x = -(robot_radius + h_radius), max_x = -min_x;
+        const double hx = (max_x - min_x) * u[2] + min_x;
+        c.px = hx; c.gx = hx;
+        if (scenario == CN_SCN_SIDE_PREF_PASSING) { c.py = R; c.gy = -R; c.heading = -CN_PI / 2.0; }
+        else { c.py = -R + 2.0; c.gy = R + 2.0; c.heading = CN_PI / 2.0; v_pref = 0.3; }
+    } break;
+    case CN_SCN_SIDE_PREF_CROSSING: {
+        const double min_x = -(R + robot_radius + h_radius), max_x = -(R - robot_radius - h_radius);
+        const double hx = (max_x - min_x) * u[2] + min_x;
+        c.px = hx; c.gx = -hx; c.py = 0.0; c.gy = 0.0;
+    } break;
+    default: break;
+    }
+#undef CN_WORLD
+    c.v_pref = v_pref;
+    return c;
+}

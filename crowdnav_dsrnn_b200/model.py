@@ -1,0 +1,293 @@
+"""`Policy`: the DS-RNN actor-critic behind the reference's interface
+(pytorchBaselines/a2c_ppo_acktr/model.py:17-104): same constructor, `act`,
+`get_value`, `evaluate_actions`, `.base.nenv`, `.base.human_num`,
+`.is_recurrent` and the same 45 `state_dict()` keys, so either side's
+checkpoints load on the other.
+
+Rollout path (`act`, `get_value`): one call into the CUDA forward
+(`cn_dsrnn_forward`, csrc/dsrnn_forward.cu + dsrnn_edge_tc.cu) -- no CPU
+fallback; tensors must live on a B200.  Batch size and human count are read
+from the tensor shapes (the reference bakes them from config,
+srnn_model.py:361-363,410-418).
+
+Training path (`evaluate_actions`): the same math written
+with differentiable torch ops over the T x N rollout chunk.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, abi
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _orthogonal(module, gain=1.0):
+    nn.init.orthogonal_(module.weight.data, gain=gain)
+    nn.init.constant_(module.bias.data, 0)
+    return module
+
+
+class _EdgeRNN(nn.Module):
+    """Parameter holder of HumanHumanEdgeRNN (srnn_model.py:176-215): Linear(2,64) + GRU(64,256)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.gru = nn.GRU(cfg.human_human_edge_embedding_size, cfg.human_human_edge_rnn_size)
+        self.encoder_linear = nn.Linear(cfg.human_human_edge_input_size, cfg.human_human_edge_embedding_size)
+        _init_gru(self.gru)
+
+
+class _NodeRNN(nn.Module):
+    """Parameter holder of HumanNodeRNN (srnn_model.py:109-173)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.gru = nn.GRU(cfg.human_node_embedding_size * 2, cfg.human_node_rnn_size)
+        self.encoder_linear = nn.Linear(cfg.human_node_input_size, cfg.human_node_embedding_size)
+        self.edge_embed = nn.Linear(cfg.human_human_edge_rnn_size, cfg.human_node_embedding_size)  # unused, kept for state_dict
+        self.edge_attention_embed = nn.Linear(cfg.human_human_edge_rnn_size * 2, cfg.human_node_embedding_size)
+        self.output_linear = nn.Linear(cfg.human_node_rnn_size, cfg.human_node_output_size)
+        _init_gru(self.gru)
+
+
+class _Attention(nn.Module):
+    """Parameter holder of EdgeAttention (srnn_model.py:218-339)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.temporal_edge_layer = nn.ModuleList([nn.Linear(cfg.human_human_edge_rnn_size, cfg.attention_size)])
+        self.spatial_edge_layer = nn.ModuleList([nn.Linear(cfg.human_human_edge_rnn_size, cfg.attention_size)])
+
+
+def _init_gru(gru):
+    for name, param in gru.named_parameters():
+        if "bias" in name:
+            nn.init.constant_(param, 0)
+        elif "weight" in name:
+            nn.init.orthogonal_(param)
+
+
+class SRNN(nn.Module):
+    """Module tree (names = state_dict keys) of srnn_model.py:342-407."""
+
+    def __init__(self, obs_space_dict, config, infer=False):
+        super().__init__()
+        self.infer = infer
+        self.is_recurrent = True
+        self.config = config
+        self.human_num = config.sim.human_num
+        self.seq_length = config.ppo.num_steps
+        self.nenv = config.training.num_processes
+        self.nminibatch = config.ppo.num_mini_batch
+        c = config.SRNN
+        if (c.human_node_rnn_size, c.human_human_edge_rnn_size, c.human_node_output_size, c.human_node_embedding_size,
+                c.human_human_edge_embedding_size, c.attention_size, c.human_node_input_size,
+                c.human_human_edge_input_size) != (128, 256, 256, 64, 64, 64, 3, 2):
+            raise NotImplementedError("the CUDA forward is specialised for the reference's SRNN sizes (config.py:178-193)")
+        self.human_node_rnn_size = c.human_node_rnn_size
+        self.human_human_edge_rnn_size = c.human_human_edge_rnn_size
+        self.output_size = c.human_node_output_size
+        self.humanNodeRNN = _NodeRNN(c)
+        self.humanhumanEdgeRNN_spatial = _EdgeRNN(c)
+        self.humanhumanEdgeRNN_temporal = _EdgeRNN(c)
+        self.attn = _Attention(c)
+        g = math.sqrt(2)
+        hid = self.output_size
+        self.actor = nn.Sequential(_orthogonal(nn.Linear(hid, hid), g), nn.Tanh(), _orthogonal(nn.Linear(hid, hid), g), nn.Tanh())
+        self.critic = nn.Sequential(_orthogonal(nn.Linear(hid, hid), g), nn.Tanh(), _orthogonal(nn.Linear(hid, hid), g), nn.Tanh())
+        self.critic_linear = _orthogonal(nn.Linear(hid, 1), g)
+        self.robot_linear = _orthogonal(nn.Linear(7, 3), g)
+        self.human_node_final_linear = _orthogonal(nn.Linear(hid, 2), g)  # unused, kept for state_dict
+        self.num_edges = self.human_num + 1
+
+
+class _AddBias(nn.Module):
+    def __init__(self, bias):
+        super().__init__()
+        self._bias = nn.Parameter(bias.unsqueeze(1))
+
+
+class DiagGaussian(nn.Module):
+    """distributions.py:74-94: fc_mean + state-independent logstd."""
+
+    def __init__(self, num_inputs, num_outputs):
+        super().__init__()
+        self.fc_mean = _orthogonal(nn.Linear(num_inputs, num_outputs))
+        self.logstd = _AddBias(torch.zeros(num_outputs))
+
+    def std(self):
+        return self.logstd._bias.t().view(1, -1).exp()
+
+
+def _normal_log_prob(action, mean, std):
+    var = std * std
+    return (-((action - mean) ** 2) / (2 * var) - std.log() - math.log(math.sqrt(2 * math.pi))).sum(-1, keepdim=True)
+
+
+class Policy(nn.Module):
+    def __init__(self, obs_shape, action_space, base=None, base_kwargs=None):
+        super().__init__()
+        if base != "srnn":
+            raise NotImplementedError("only base='srnn' is on the hot path (convgru is out of scope, SURVEY section 2 row 18)")
+        self.base = SRNN(obs_shape, base_kwargs)
+        self.srnn = True
+        if action_space.__class__.__name__ != "Box":
+            raise NotImplementedError("only Box action spaces are supported")
+        self.dist = DiagGaussian(self.base.output_size, action_space.shape[0])
+        self.precision = "fp32"   # contraction precision of the CUDA forward: "fp32" | "bf16x3" | "bf16"
+        self._handle = None
+        self._weights_key = None
+        self._workspace = None
+        self.gpu_launches = 0
+
+    @property
+    def is_recurrent(self):
+        return self.base.is_recurrent
+
+    def forward(self, inputs, rnn_hxs, masks):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ CUDA forward plumbing
+    def _weight_tensors(self):
+        sd = dict(self.named_parameters())
+        return [sd[abi.DSRNN_STATE_DICT_KEYS[f]] for f in abi.DSRNN_WEIGHT_FIELDS]
+
+    def _ensure_handle(self, device):
+        tensors = self._weight_tensors()
+        for t in tensors:
+            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise _lib.CrowdNavLibraryError("Policy parameters must be contiguous float32 on %s (call .to(device))" % device)
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        lib = _lib.load()
+        if self._handle is not None and key == self._weights_key:
+            return lib
+        w = abi.CnDsrnnWeights(*[_ptr(t) for t in tensors])
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        if self._handle is None:
+            handle = C.c_void_p()
+            _lib.check(lib.cn_dsrnn_create(C.byref(w), index, stream, C.byref(handle)), "cn_dsrnn_create")
+            self._handle = handle
+        else:
+            _lib.check(lib.cn_dsrnn_update_weights(self._handle, C.byref(w), stream), "cn_dsrnn_update_weights")
+        self._weights_key = key
+        return lib
+
+    def __del__(self):
+        if getattr(self, "_handle", None) is not None:
+            try:
+                _lib.load().cn_dsrnn_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def cuda_forward(self, inputs, rnn_hxs, masks, need_features=True):
+        """One rollout-step forward on the GPU. Returns (value[N,1], mean[N,2], features[N,256]|None, h_node, h_edge)."""
+        rn, te, se = inputs["robot_node"], inputs["temporal_edges"], inputs["spatial_edges"]
+        device = se.device
+        if device.type != "cuda":
+            raise _lib.CrowdNavLibraryError("Policy.act/get_value run on a B200 only; inputs are on %s (no CPU fallback)" % device)
+        lib = self._ensure_handle(device)
+        N, H = se.shape[0], se.shape[1]
+        f = lambda t: t.detach().to(dtype=torch.float32).contiguous()
+        rn, te, se = f(rn), f(te), f(se)
+        hn, he, mk = f(rnn_hxs["human_node_rnn"]), f(rnn_hxs["human_human_edge_rnn"]), f(masks)
+        if hn.numel() != N * 128 or he.numel() != N * (H + 1) * 256 or mk.numel() != N or rn.numel() != N * 7:
+            raise ValueError("inconsistent batch shapes for the DS-RNN forward")
+        opts = dict(dtype=torch.float32, device=device)
+        hn_out = torch.empty(N, 1, 128, **opts)
+        he_out = torch.empty(N, H + 1, 256, **opts)
+        value = torch.empty(N, 1, **opts)
+        mean = torch.empty(N, 2, **opts)
+        feat = torch.empty(N, 256, **opts) if need_features else None
+        nbytes = lib.cn_dsrnn_workspace_bytes(N, H)
+        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        io = abi.CnDsrnnIO(_ptr(rn), _ptr(te), _ptr(se), _ptr(hn), _ptr(he), _ptr(mk), _ptr(hn_out), _ptr(he_out),
+                           _ptr(value), _ptr(mean), _ptr(feat))
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.cn_dsrnn_forward(self._handle, N, H, C.byref(io), abi.PRECISIONS[self.precision],
+                                        _ptr(self._workspace), self._workspace.numel(), stream), "cn_dsrnn_forward")
+        self.gpu_launches += lib.cn_dsrnn_last_launches(self._handle)
+        return value, mean, feat, hn_out, he_out
+
+    # ------------------------------------------------------------------ reference API
+    def act(self, inputs, rnn_hxs, masks, deterministic=False):
+        with torch.no_grad():
+            value, mean, _, hn, he = self.cuda_forward(inputs, rnn_hxs, masks, need_features=False)
+            std = self.dist.std().expand_as(mean)
+            action = mean if deterministic else torch.normal(mean, std)
+            log_probs = _normal_log_prob(action, mean, std)
+        rnn_hxs["human_node_rnn"] = hn            # the reference mutates the dict it was given (srnn_model.py:481-491)
+        rnn_hxs["human_human_edge_rnn"] = he
+        return value, action, log_probs, rnn_hxs
+
+    def get_value(self, inputs, rnn_hxs, masks):
+        with torch.no_grad():
+            value, _, _, hn, he = self.cuda_forward(inputs, rnn_hxs, masks, need_features=False)
+        rnn_hxs["human_node_rnn"] = hn
+        rnn_hxs["human_human_edge_rnn"] = he
+        return value
+
+    def evaluate_actions(self, inputs, rnn_hxs, masks, action):
+        """Training-time evaluation over a [T*N, ...] rollout chunk (model.py:96-104; srnn_model.py:53-104)."""
+        value, feat, rnn_hxs = self._torch_sequence_forward(inputs, rnn_hxs, masks)
+        mean = self.dist.fc_mean(feat)
+        std = self.dist.std().expand_as(mean)
+        log_probs = _normal_log_prob(action, mean, std)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + std.log()).sum(-1).mean()
+        return value, log_probs, entropy, rnn_hxs
+
+    # ------------------------------------------------------------------ differentiable torch restatement (training)
+    def _torch_step(self, rn, te, se, h_node, h_edge, m):
+        b = self.base
+        N, H = se.shape[0], se.shape[1]
+
+        def gru(mod, x, h):
+            gi = x @ mod.weight_ih_l0.t() + mod.bias_ih_l0
+            gh = h @ mod.weight_hh_l0.t() + mod.bias_hh_l0
+            i_r, i_z, i_n = gi.chunk(3, -1)
+            h_r, h_z, h_n = gh.chunk(3, -1)
+            r, z = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
+            n = torch.tanh(i_n + r * h_n)
+            return (1.0 - z) * n + z * h
+
+        h_edge = h_edge * m.view(N, 1, 1)
+        h_node = h_node * m.view(N, 1)
+        o_t = gru(b.humanhumanEdgeRNN_temporal.gru, torch.relu(b.humanhumanEdgeRNN_temporal.encoder_linear(te)), h_edge[:, 0])
+        o_s = gru(b.humanhumanEdgeRNN_spatial.gru, torch.relu(b.humanhumanEdgeRNN_spatial.encoder_linear(se.reshape(N * H, 2))),
+                  h_edge[:, 1:].reshape(N * H, 256)).view(N, H, 256)
+        q = b.attn.temporal_edge_layer[0](o_t)
+        k = b.attn.spatial_edge_layer[0](o_s)
+        alpha = torch.softmax((q.unsqueeze(1) * k).sum(-1) * (H / math.sqrt(64.0)), dim=-1)
+        c = (alpha.unsqueeze(-1) * o_s).sum(1)
+        enc = torch.relu(b.humanNodeRNN.encoder_linear(b.robot_linear(rn)))
+        emb = torch.relu(b.humanNodeRNN.edge_attention_embed(torch.cat([o_t, c], -1)))
+        h_n = gru(b.humanNodeRNN.gru, torch.cat([enc, emb], -1), h_node)
+        y = b.humanNodeRNN.output_linear(h_n)
+        return b.critic_linear(b.critic(y)), b.actor(y), h_n, torch.cat([o_t.unsqueeze(1), o_s], 1)
+
+    def _torch_sequence_forward(self, inputs, rnn_hxs, masks):
+        se = inputs["spatial_edges"]
+        H = se.shape[1]
+        N = rnn_hxs["human_node_rnn"].shape[0]
+        T = se.shape[0] // N
+        rn = inputs["robot_node"].reshape(T, N, 7)
+        te = inputs["temporal_edges"].reshape(T, N, 2)
+        se = se.reshape(T, N, H, 2)
+        mk = masks.reshape(T, N)
+        h_node = rnn_hxs["human_node_rnn"].reshape(N, 128)
+        h_edge = rnn_hxs["human_human_edge_rnn"].reshape(N, H + 1, 256)
+        values, feats = [], []
+        for t in range(T):
+            v, f, h_node, h_edge = self._torch_step(rn[t], te[t], se[t], h_node, h_edge, mk[t])
+            values.append(v)
+            feats.append(f)
+        rnn_hxs["human_node_rnn"] = h_node.unsqueeze(1)
+        rnn_hxs["human_human_edge_rnn"] = h_edge
+        return torch.cat(values, 0).view(-1, 1), torch.cat(feats, 0).view(-1, self.base.output_size), rnn_hxs
