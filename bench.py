@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the rollout hot path (crowd step + DS-RNN forward) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--precision fp32|bf16x3|bf16]
+    python bench.py --impl reference ...      # the CPU arm: the oracle port on the box's host cores
+
+One "step" = Policy.act (DS-RNN forward, deterministic) + CrowdSimDict.step for every env of the batch
+(+ the device-side reset of finished episodes).  Workload (BASELINE.json):
+  c3 (default, the config the metric's 1e7 env-steps/s target is quoted on): 20 humans, robot FOV 90 deg,
+     16384 envs per GPU, inference-only rollout, weights of the shipped holonomic checkpoint (27776.pt);
+  c2: unicycle robot, 10 humans, mixed scenarios, dt 0.1, 1024 envs;  c1: reference defaults, 5 humans, 16 envs.
+Prints ONE JSON line (see the task contract): value = whole-job env-steps/s with everything resident in HBM,
+e2e = the same metric through the reference-facing API with host buffers (actions, masks, rewards, dones cross
+PCIe every step, as in train.py:243-292), roofline for the dominant kernel, cpu_baseline for the oracle port.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c3": dict(human_num=20, envs_per_gpu=16384, kinematics="holonomic", over={"robot.FOV": 0.5},
+               weights="holonomic_27776", label="c3: 20 humans, robot FOV 0.5*pi, 16384 envs/GPU, inference rollout"),
+    "c2": dict(human_num=10, envs_per_gpu=1024, kinematics="unicycle",
+               over={"env.time_step": 0.1, "reward.discomfort_penalty_factor": 1.0},
+               weights="unicycle_55554", label="c2: unicycle, 10 humans, mixed scenarios, dt 0.1, 1024 envs"),
+    "c1": dict(human_num=5, envs_per_gpu=16, kinematics="holonomic", over={"sim.train_val_sim": ["circle_crossing"]},
+               weights="holonomic_27776", label="c1: reference defaults, 5 humans circle_crossing, 16 envs"),
+}
+
+
+def step_bytes(H):          # algorithmic HBM bytes of the step kernel per env-step
+    return 96 * H + 188
+
+
+def forward_flops(H):       # algorithmic FLOPs of the DS-RNN forward per env-step
+    return 2 * ((H + 1) * 262272 + 320 * H + 426965)
+
+
+def edge_stage_flops(H):    # encoder + GRU(64->256) per edge row: 2*(2*64 + 768*64 + 768*256) FLOP
+    return 2 * (H + 1) * (2 * 64 + 768 * 64 + 768 * 256)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def make_config(wl):
+    from crowdnav_dsrnn_b200 import Config
+
+    cfg = Config(kinematics=wl["kinematics"], human_num=wl["human_num"])
+    for k, v in wl["over"].items():
+        sec, _, attr = k.partition(".")
+        setattr(getattr(cfg, sec), attr, v)
+    return cfg
+
+
+def load_weights(name):
+    path = os.path.join(ROOT, "tests", "golden", "weights_%s.npz" % name)
+    w = np.load(path)
+    return {k: w[k] for k in w.files}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:  # noqa: BLE001 - nvidia-smi missing: report no clocks rather than fail the bench
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rate(wl, n_envs, steps, warmup, threads):
+    """env-steps/s of the ORACLE PORT on the host cores: C crowd step (pthreads over envs) + torch fp32 forward."""
+    import torch
+
+    from crowdnav_dsrnn_b200 import abi
+    from oracle import crowd_oracle, dsrnn_oracle
+
+    torch.set_num_threads(threads)
+    cfg_obj = make_config(wl)
+    cfg = abi.flatten_config(cfg_obj, n_envs, phase="train")
+    H = cfg.human_num
+    sd = {k: torch.from_numpy(v) for k, v in load_weights(wl["weights"]).items()}
+    st = crowd_oracle.OracleState(n_envs, H)
+    out = crowd_oracle.reset(cfg, st, n_threads=threads)
+    hn, he = torch.zeros(n_envs, 1, 128), torch.zeros(n_envs, H + 1, 256)
+    masks = torch.ones(n_envs, 1)
+    t0 = None
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            if it == warmup:
+                t0 = time.perf_counter()
+            r = dsrnn_oracle.forward(sd, torch.from_numpy(out.robot_node), torch.from_numpy(out.temporal_edges),
+                                     torch.from_numpy(out.spatial_edges), hn, he, masks)
+            hn, he = r["h_node"], r["h_edge"]
+            out = crowd_oracle.step(cfg, st, r["action_mean"].numpy(), auto_reset=True, n_threads=threads)
+            masks = torch.from_numpy(1.0 - out.done.astype(np.float32)).unsqueeze(1)
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_cpu = max(64, min(wl["envs_per_gpu"], 32 * threads))
+    rate, dt = cpu_port_rate(wl, n_cpu, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec_incl_dsrnn_forward", "value": rate, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["label"], "human_num": wl["human_num"], "envs_per_step": n_cpu},
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                         "sample": "%d envs x %d steps of the same workload (oracle C crowd step on %d pthreads + torch fp32 "
+                                   "DS-RNN forward on %d threads)" % (n_cpu, args.steps, threads, threads)},
+        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    from crowdnav_dsrnn_b200 import _lib
+    from crowdnav_dsrnn_b200.envs import CrowdVecEnv
+    from crowdnav_dsrnn_b200.model import Policy
+    from crowdnav_dsrnn_b200.spaces import crowd_spaces
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    N = args.envs_per_gpu or wl["envs_per_gpu"]
+    H = wl["human_num"]
+    cfg_obj = make_config(wl)
+    cfg_obj.training.num_processes = N * world
+    # envs shard by global id: rank r owns [r*N, (r+1)*N); RNG is keyed by global env id, no data-path collective
+    venv = CrowdVecEnv(cfg_obj, N, dev, seed=0, phase="train", env_id_offset=rank * N, nenv=N * world)
+    obs_space, act_space = crowd_spaces(H)
+    policy = Policy(obs_space.spaces, act_space, base="srnn", base_kwargs=cfg_obj)
+    policy.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights(wl["weights"]).items()})
+    policy = policy.to(dev)
+    policy.precision = args.precision
+    eng = venv.engine
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident rollout (value)
+    def rollout(steps, obs, hx, masks):
+        for _ in range(steps):
+            _, action, _, hx = policy.act(obs, hx, masks, deterministic=True)
+            obs, _, done, _ = venv.step_device(action)
+            masks = (1.0 - done.to(torch.float32)).unsqueeze(1)
+        return obs, hx, masks
+
+    obs = venv.reset()
+    hx = {"human_node_rnn": torch.zeros(N, 1, 128, device=dev), "human_human_edge_rnn": torch.zeros(N, H + 1, 256, device=dev)}
+    masks = torch.zeros(N, 1, device=dev)
+    obs, hx, masks = rollout(args.prime, obs, hx, masks)      # de-phase the episodes (untimed)
+    obs, hx, masks = rollout(args.warmup, obs, hx, masks)     # warm-up (untimed)
+    policy.act(obs, dict(hx), masks, deterministic=True)
+    lib.cn_dsrnn_enable_timing(policy._handle, 1)
+    lib.cn_env_enable_timing(eng.handle, 1)
+    launches0 = eng.launches + policy.gpu_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    obs, hx, masks = rollout(args.steps, obs, hx, masks)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launches + policy.gpu_launches - launches0
+    import ctypes as C
+    edge_ms, n_fw, step_ms, n_st = C.c_float(), C.c_int(), C.c_float(), C.c_int()
+    lib.cn_dsrnn_time_ms(policy._handle, C.byref(edge_ms), C.byref(n_fw))
+    lib.cn_env_time_ms(eng.handle, C.byref(step_ms), C.byref(n_st))
+    lib.cn_dsrnn_enable_timing(policy._handle, 0)
+    lib.cn_env_enable_timing(eng.handle, 0)
+    resets = float(eng.get_state()["counters"][:, 1].float().mean().item())
+
+    # ---------------- end-to-end through the reference-facing API with HOST buffers (e2e)
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    pin_action = torch.empty(N, 2, dtype=torch.float32).pin_memory()
+    pin_masks = torch.empty(N, 1, dtype=torch.float32).pin_memory()
+
+    def e2e_rollout(steps, obs, hx, masks):
+        for _ in range(steps):
+            _, action, _, hx = policy.act(obs, hx, masks, deterministic=True)
+            pin_action.copy_(action, non_blocking=True)            # action.cpu() of VecPyTorch.step_async (envs.py:224-229)
+            torch.cuda.current_stream().synchronize()
+            host_action = pin_action                                # the host buffer the env API is driven from
+            obs, reward, done, infos = venv.step(host_action.to(dev, non_blocking=True))   # reward CPU tensor, done numpy
+            pin_masks.copy_(torch.from_numpy(1.0 - done.astype(np.float32)).unsqueeze(1))  # train.py:279
+            masks = pin_masks.to(dev, non_blocking=True)
+        return obs, hx, masks
+
+    obs, hx, masks = e2e_rollout(3, obs, hx, masks)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    obs, hx, masks = e2e_rollout(e2e_steps, obs, hx, masks)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    h2d = N * 2 * 4 + N * 4                 # actions + masks
+    d2h = N * 2 * 4 + N * 4 + N             # actions + reward + done
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([float(launches)], device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    value = N * world * args.steps / (ms * 1e-3)
+    e2e_value = N * world * e2e_steps / (e2e_ms * 1e-3)
+    edge_avg_ms = edge_ms.value / max(1, n_fw.value)
+    step_avg_ms = step_ms.value / max(1, n_st.value)
+    roof_step = {"bound": "hbm", "achieved": N * step_bytes(H) / (step_avg_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                 "unit": "GB/s", "kernel": "crowd_step_kernel", "ms_per_launch": step_avg_ms, "traffic": None,
+                 "algorithmic_bytes_per_env_step": step_bytes(H), "share_of_step": step_avg_ms / (ms / args.steps)}
+    roof_step["frac"] = roof_step["achieved"] / roof_step["peak"]
+    edge_kernel = "edge_gru_simt_kernel" if args.precision == "fp32" else "edge_gru_tc_kernel"
+    passes = 3 if args.precision == "bf16x3" else 1
+    roof_edge = {"bound": "tensor", "achieved": N * edge_stage_flops(H) / (edge_avg_ms * 1e-3) / 1e12,
+                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "kernel": edge_kernel,
+                 "ms_per_launch": edge_avg_ms, "traffic": None, "algorithmic_flops_per_env_step": edge_stage_flops(H),
+                 "tensor_passes": passes, "share_of_step": edge_avg_ms / (ms / args.steps)}
+    roof_edge["frac"] = roof_edge["achieved"] / roof_edge["peak"]
+    dominant = roof_edge if edge_avg_ms >= step_avg_ms else roof_step
+    other = roof_step if dominant is roof_edge else roof_edge
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_cpu = max(64, min(N, 32 * threads))
+        _, probe = cpu_port_rate(wl, n_cpu, 2, 1, threads)                 # size the sample for ~args.cpu_seconds of CPU work
+        cpu_steps = int(max(3, min(2000, args.cpu_seconds / max(probe / 2, 1e-4))))
+        rate, dt = cpu_port_rate(wl, n_cpu, cpu_steps, 2, threads)
+        cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+               "sample": "%d envs x %d steps of the same workload in %.1f s (oracle C crowd step on %d pthreads + torch fp32 "
+                         "DS-RNN forward)" % (n_cpu, cpu_steps, dt, threads)}
+
+    line = {
+        "metric": "env_steps_per_sec_incl_dsrnn_forward", "value": value, "unit": "env-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (3-pass split bf16, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+        "data": "synthetic scenarios (device reset, counter-based RNG); weights of the shipped checkpoint %s" % wl["weights"],
+        "config": {"workload": wl["label"], "human_num": H, "envs_per_gpu": N, "global_envs": N * world,
+                   "parallelism": "env-sharded x%d, no data-path collective" % world, "precision": args.precision,
+                   "l2": "inputs larger than L2 (hidden state %.0f MB + env state %.0f MB per step vs 126 MB L2)" % (
+                       N * (H + 1) * 256 * 4 * 2 / 1e6, N * step_bytes(H) / 1e6),
+                   "prime_steps": args.prime, "resets_per_env_total": resets, "peaks": peaks["source"]},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": dominant, "roofline_other": other, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
+    ap.add_argument("--prime", type=int, default=150, help="untimed steps before warm-up so episodes are de-phased")
+    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,10 @@ SYMBOLS = {
     "cn_dsrnn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cn_dsrnn_forward": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(abi.CnDsrnnIO), C.c_int, _P, C.c_size_t, _P]),
     "cn_dsrnn_last_launches": (C.c_int, [_P]),
+    "cn_dsrnn_enable_timing": (C.c_int, [_P, C.c_int]),
+    "cn_dsrnn_time_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "cn_env_enable_timing": (C.c_int, [_P, C.c_int]),
+    "cn_env_time_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }
 
 _LIB = None

@@ -29,10 +29,44 @@ extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, co
 extern "C" int cn_launch_crowd_observe(const EnvParams *P, const CnObsOut *obs, cudaStream_t stream);
 extern "C" int cn_launch_state_convert(const EnvParams *P, const CnStateView *v, int dir, cudaStream_t stream);
 
+#include <vector>
+// pairs of events recorded around a kernel on the caller's stream; drained by *_time_ms()
+struct EventTimer {
+    bool enabled = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;
+    void begin(cudaStream_t s) {
+        if (!enabled) return;
+        std::pair<cudaEvent_t, cudaEvent_t> p;
+        if (!pool.empty()) { p = pool.back(); pool.pop_back(); }
+        else { cudaEventCreate(&p.first); cudaEventCreate(&p.second); }
+        cudaEventRecord(p.first, s);
+        pending.push_back(p);
+    }
+    void end(cudaStream_t s) { if (enabled && !pending.empty()) cudaEventRecord(pending.back().second, s); }
+    float drain(int *count) {
+        float total = 0.f;
+        for (auto &p : pending) {
+            cudaEventSynchronize(p.second);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, p.first, p.second);
+            total += ms;
+            pool.push_back(p);
+        }
+        if (count) *count = (int)pending.size();
+        pending.clear();
+        return total;
+    }
+    ~EventTimer() {
+        for (auto &p : pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        for (auto &p : pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    }
+};
+
 struct CnEnv {
     EnvParams p;
     int device;
     int last_launches;
+    EventTimer timer;
 };
 
 extern "C" const char *cn_last_error(void) { return g_err; }
@@ -121,7 +155,9 @@ extern "C" int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut 
     if (rc != CN_OK) return rc;
     if (!out->reward || !out->done || !out->event) return fail(CN_ERR_ARG, "CnStepOut needs reward, done and event");
     CN_CUDA(cudaSetDevice(env->device));
+    env->timer.begin((cudaStream_t)stream);
     CN_CUDA((cudaError_t)cn_launch_crowd_step(&env->p, out, action_dev, (cudaStream_t)stream));
+    env->timer.end((cudaStream_t)stream);
     env->last_launches = 1;
     if (auto_reset) {
         CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, &out->obs, out->done, (cudaStream_t)stream));
@@ -153,6 +189,19 @@ static int convert(CnEnv *env, const CnStateView *view, int dir, void *stream)
 extern "C" int cn_env_set_state(CnEnv *env, const CnStateView *view, void *stream) { return convert(env, view, 0, stream); }
 extern "C" int cn_env_get_state(CnEnv *env, const CnStateView *view, void *stream) { return convert(env, view, 1, stream); }
 extern "C" int cn_env_last_launches(const CnEnv *env) { return env ? env->last_launches : 0; }
+extern "C" int cn_env_enable_timing(CnEnv *env, int enable)
+{
+    if (!env) return fail(CN_ERR_ARG, "env is NULL");
+    env->timer.drain(nullptr);
+    env->timer.enabled = enable != 0;
+    return CN_OK;
+}
+extern "C" int cn_env_time_ms(CnEnv *env, float *step_kernel_ms, int *n_steps)
+{
+    if (!env || !step_kernel_ms) return fail(CN_ERR_ARG, "env/out is NULL");
+    *step_kernel_ms = env->timer.drain(n_steps);
+    return CN_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ DS-RNN
 extern "C" int cn_dsrnn_create(const CnDsrnnWeights *w, int device, void *stream, CnDsrnn **out)
@@ -215,3 +264,15 @@ extern "C" int cn_dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnD
 }
 
 extern "C" int cn_dsrnn_last_launches(const CnDsrnn *m) { return m ? dsrnn_last_launches(m) : 0; }
+extern "C" int cn_dsrnn_enable_timing(CnDsrnn *m, int enable)
+{
+    if (!m) return fail(CN_ERR_ARG, "model is NULL");
+    dsrnn_enable_timing(m, enable);
+    return CN_OK;
+}
+extern "C" int cn_dsrnn_time_ms(CnDsrnn *m, float *edge_stage_ms, int *n_forwards)
+{
+    if (!m || !edge_stage_ms) return fail(CN_ERR_ARG, "model/out is NULL");
+    *edge_stage_ms = dsrnn_time_ms(m, n_forwards);
+    return CN_OK;
+}

@@ -12,3 +12,5 @@ size_t dsrnn_workspace_bytes(int n_envs, int human_num);
 const char *dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnDsrnnIO *io, int precision,
                           void *workspace, cudaStream_t stream);
 int dsrnn_last_launches(const CnDsrnn *m);
+void dsrnn_enable_timing(CnDsrnn *m, int enable);
+float dsrnn_time_ms(CnDsrnn *m, int *count);

@@ -1,10 +1,471 @@
-// dsrnn_edge_tc.cu -- tensor-core (tcgen05) edge-GRU stage of the DS-RNN forward.  PLACEHOLDER until the
-// tcgen05 kernel lands: create/destroy are no-ops and the forward reports that the precision is unavailable.
+// dsrnn_edge_tc.cu -- K3 stage 1 on the 5th-gen tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+// The edge GRUs of the DS-RNN (HumanHumanEdgeRNN.forward, srnn_model.py:201-215; one GRU(64->256) step on
+// N temporal + N*H spatial edge rows) are one tall GEMM per weight set:
+//     [e | m*h]  (rows x 320)   x   [W_ih | W_hh]^T  (320 x 768)      e = ReLU(W_enc x + b)  (K = 2, computed in place)
+// followed by the gate non-linearities.  One persistent CTA per SM walks 128-row tiles:
+//   warps 0-3  stage the tile's A operand straight from the fp32 hidden state in HBM (masking, fp32 -> split bf16
+//              hi/lo, 128B-swizzled K-major smem image), then act as the epilogue: tcgen05.ld the accumulators of a
+//              64-hidden-unit column tile (n_i | r | z | n_h, 256 TMEM columns), apply sigmoid/tanh/blend and store h'.
+//   warp 4     streams the pre-swizzled bf16 weight images (24 KB chunks) with cp.async.bulk into a 2-slot smem ring.
+//   warp 5     owns TMEM (512 columns = 2 accumulator buffers) and issues tcgen05.mma.kind::f16 (M=128, N=192, K=16).
+// Precision: CN_PREC_BF16X3 runs A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (fp32 accumulate in TMEM, ~2^-16 relative operand
+// error); CN_PREC_BF16 runs the first pass only.
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <new>
 #include "dsrnn.cuh"
 
-const char *dsrnn_tc_create(const CnDsrnnWeights *, cudaStream_t, void **state) { *state = nullptr; return nullptr; }
-void dsrnn_tc_destroy(void *) {}
-const char *dsrnn_tc_edge_forward(void *, const CnDsrnnWeights *, int, int, const CnDsrnnIO *, int, cudaStream_t, int *)
+namespace {
+
+constexpr int kRows = 128;                 // UMMA M
+constexpr int kKBlocks = 5;                // 64-wide k-blocks: 1 encoded-input block + 4 hidden blocks
+constexpr int kColTiles = 4;               // 64 hidden units per column tile
+constexpr int kABlockBytes = kRows * 128;  // 128 rows x 64 bf16
+constexpr int kBChunkRows = 192;
+constexpr int kBChunkBytes = kBChunkRows * 128;
+constexpr int kThreads = 192;
+
+constexpr int kOffAHi = 0;
+constexpr int kOffALo = kOffAHi + kKBlocks * kABlockBytes;        //  81920
+constexpr int kOffB = kOffALo + kKBlocks * kABlockBytes;          // 163840
+constexpr int kOffBias = kOffB + 2 * kBChunkBytes;                // 212992  float[2][4][256]
+constexpr int kOffEnc = kOffBias + 2 * 4 * 256 * 4;               // 221184  float[2][192]: w0[64] w1[64] b[64]
+constexpr int kOffBar = kOffEnc + 2 * 192 * 4;                    // 222720  mbarriers
+constexpr int kSmemBytes = kOffBar + 128;                         // 222848 (+1024 alignment slack at launch)
+
+struct TcState {
+    __nv_bfloat16 *wimg;   // [2 problems][4 ct][5 kb][2 parts] x 24 KB swizzled images
+    float *bias4;          // [2][4][256]: b_in | b_ir+b_hr | b_iz+b_hz | b_hn
+    float *enc;            // [2][192]
+    int num_sms;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    return "tensor-core edge stage not built yet: use precision fp32";
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v)
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024>>4 |
+// version=1 (bits 46-47) | layout_type=2 (bits 61-63).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
+{
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, BF16 x BF16, both K-major, M=128
+__host__ __device__ constexpr uint32_t idesc_bf16(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+// byte offset of element (row, k) inside a [rows x 64] bf16 block in the canonical K-major SW128 layout
+__host__ __device__ __forceinline__ int sw128_offset(int row, int k)
+{
+    return (row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2;
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+// ---------------------------------------------------------------------------------------------- weight packing
+struct PackArgs {
+    const float *w_ih[2], *w_hh[2], *b_ih[2], *b_hh[2], *enc_w[2], *enc_b[2];   // [0] spatial, [1] temporal
+    __nv_bfloat16 *wimg;
+    float *bias4, *enc;
+};
+
+__global__ void pack_edge_weights_kernel(const PackArgs a)
+{
+    const int total = 2 * kColTiles * kKBlocks * kBChunkRows * 64;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int t = idx;
+        const int k = t & 63; t >>= 6;
+        const int q = t % kBChunkRows; t /= kBChunkRows;
+        const int kb = t % kKBlocks; t /= kKBlocks;
+        const int ct = t % kColTiles; t /= kColTiles;
+        const int p = t;
+        const int j = ct * 64 + (q & 63);
+        const int blk = q >> 6;                      // 0,1,2 within the 192-row chunk
+        float w;
+        if (kb == 0) {                               // rows [n_i ; r ; z] of W_ih
+            const int gate_row = (blk == 0 ? 512 : blk == 1 ? 0 : 256) + j;
+            w = a.w_ih[p][(size_t)gate_row * 64 + k];
+        } else {                                     // rows [r ; z ; n_h] of W_hh
+            const int gate_row = (blk == 0 ? 0 : blk == 1 ? 256 : 512) + j;
+            w = a.w_hh[p][(size_t)gate_row * 256 + (kb - 1) * 64 + k];
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        const size_t chunk = ((size_t)(p * kColTiles + ct) * kKBlocks + kb) * 2;
+        char *base = reinterpret_cast<char *>(a.wimg);
+        *reinterpret_cast<__nv_bfloat16 *>(base + (chunk + 0) * kBChunkBytes + sw128_offset(q, k)) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(base + (chunk + 1) * kBChunkBytes + sw128_offset(q, k)) = lo;
+    }
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * 256; idx += gridDim.x * blockDim.x) {
+        const int p = idx >> 8, c = idx & 255;
+        float *b = a.bias4 + (size_t)p * 4 * 256;
+        b[0 * 256 + c] = a.b_ih[p][512 + c];
+        b[1 * 256 + c] = a.b_ih[p][c] + a.b_hh[p][c];
+        b[2 * 256 + c] = a.b_ih[p][256 + c] + a.b_hh[p][256 + c];
+        b[3 * 256 + c] = a.b_hh[p][512 + c];
+    }
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * 64; idx += gridDim.x * blockDim.x) {
+        const int p = idx >> 6, k = idx & 63;
+        float *e = a.enc + (size_t)p * 192;
+        e[k] = a.enc_w[p][2 * k];
+        e[64 + k] = a.enc_w[p][2 * k + 1];
+        e[128 + k] = a.enc_b[p][k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+struct EdgeTcArgs {
+    const float *temporal_edges, *spatial_edges, *h_in, *masks;
+    float *h_out;
+    const __nv_bfloat16 *wimg;
+    const float *bias4, *enc;
+    int N, H;
+    int tiles_spatial, tiles_total;
+    int three_pass;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = smem_u32(smem);
+    float *s_bias = reinterpret_cast<float *>(smem + kOffBias);
+    float *s_enc = reinterpret_cast<float *>(smem + kOffEnc);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 96);
+    // barrier map: 0,1 full_b | 2,3 empty_b | 4 a_ready | 5,6 tmem_full | 7,8 tmem_empty
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = a.H, stride = a.H + 1;
+
+    for (int i = threadIdx.x; i < 2 * 4 * 256; i += kThreads) s_bias[i] = a.bias4[i];
+    for (int i = threadIdx.x; i < 2 * 192; i += kThreads) s_enc[i] = a.enc[i];
+    if (threadIdx.x == 0) {
+        mbar_init(bar(0), 1); mbar_init(bar(1), 1);
+        mbar_init(bar(2), 1); mbar_init(bar(3), 1);
+        mbar_init(bar(4), 128);
+        mbar_init(bar(5), 1); mbar_init(bar(6), 1);
+        mbar_init(bar(7), 128); mbar_init(bar(8), 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp < 4) {
+        // =============================================================== staging + epilogue warps
+        const int tid = threadIdx.x;          // 0..127 = row of the tile in the epilogue
+        uint32_t ctg = 0;                     // column tiles consumed so far (selects the TMEM buffer / parity)
+        for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+            const bool spatial = tile < a.tiles_spatial;
+            const int p = spatial ? 0 : 1;
+            const int row0 = (spatial ? tile : tile - a.tiles_spatial) * kRows;
+            const int M = spatial ? a.N * H : a.N;
+            const float *enc = s_enc + p * 192;
+            // ---- stage A: warp w converts rows w*32 .. w*32+31; a warp reads one row (1 KB) per two float4 loads
+            for (int rr = 0; rr < 32; ++rr) {
+                const int r = warp * 32 + rr;
+                const int m = row0 + r;
+                const bool ok = m < M;
+                size_t mem_row = 0;
+                float mk = 0.f, x0 = 0.f, x1 = 0.f;
+                if (ok) {
+                    const int env = spatial ? m / H : m;
+                    mem_row = spatial ? (size_t)env * stride + 1 + (m - env * H) : (size_t)env * stride;
+                    mk = a.masks[env];
+                    const float *x = spatial ? a.spatial_edges + 2 * (size_t)m : a.temporal_edges + 2 * (size_t)m;
+                    x0 = x[0]; x1 = x[1];
+                }
+                {   // encoded input block (k-block 0): lane owns k = 2*lane, 2*lane+1
+                    float e[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int k = 2 * lane + i;
+                        e[i] = ok ? fmaxf(fmaf(enc[64 + k], x1, enc[k] * x0) + enc[128 + k], 0.f) : 0.f;
+                    }
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(e[0], e[1]);
+                    const int off = sw128_offset(r, 2 * lane);
+                    *reinterpret_cast<__nv_bfloat162 *>(smem + kOffAHi + off) = hi;
+                    if (a.three_pass) {
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(e[0] - __low2float(hi), e[1] - __high2float(hi));
+                        *reinterpret_cast<__nv_bfloat162 *>(smem + kOffALo + off) = lo;
+                    }
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {   // hidden blocks: elements half*128 + lane*4 .. +3
+                    const int e0 = half * 128 + lane * 4;
+                    float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) h4 = *reinterpret_cast<const float4 *>(a.h_in + mem_row * 256 + e0);
+                    h4.x *= mk; h4.y *= mk; h4.z *= mk; h4.w *= mk;
+                    const int kb = 1 + (e0 >> 6);
+                    const int off = kb * kABlockBytes + sw128_offset(r, e0 & 63);
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(h4.x, h4.y), h23 = __floats2bfloat162_rn(h4.z, h4.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t *>(&h01); pk.y = *reinterpret_cast<const uint32_t *>(&h23);
+                    *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = pk;
+                    if (a.three_pass) {
+                        const __nv_bfloat162 l01 = __floats2bfloat162_rn(h4.x - __low2float(h01), h4.y - __high2float(h01));
+                        const __nv_bfloat162 l23 = __floats2bfloat162_rn(h4.z - __low2float(h23), h4.w - __high2float(h23));
+                        pk.x = *reinterpret_cast<const uint32_t *>(&l01); pk.y = *reinterpret_cast<const uint32_t *>(&l23);
+                        *reinterpret_cast<uint2 *>(smem + kOffALo + off) = pk;
+                    }
+                }
+            }
+            fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            mbar_arrive(bar(4));
+
+            // ---- epilogue: thread tid owns row tid of the tile (TMEM lane tid)
+            const int m = row0 + tid;
+            const bool ok = m < M;
+            size_t mem_row = 0;
+            float mk = 0.f;
+            if (ok) {
+                const int env = spatial ? m / H : m;
+                mem_row = spatial ? (size_t)env * stride + 1 + (m - env * H) : (size_t)env * stride;
+                mk = a.masks[env];
+            }
+            const float *bias = s_bias + p * 4 * 256;
+            for (int ct = 0; ct < kColTiles; ++ct, ++ctg) {
+                const uint32_t buf = ctg & 1u;
+                mbar_wait(bar(5 + buf), (ctg >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256u;
+#pragma unroll 1
+                for (int c16 = 0; c16 < 4; ++c16) {
+                    float ni[16], rg[16], zg[16], nh[16];
+                    tmem_ld16(t0 + 0 * 64 + c16 * 16, ni);
+                    tmem_ld16(t0 + 1 * 64 + c16 * 16, rg);
+                    tmem_ld16(t0 + 2 * 64 + c16 * 16, zg);
+                    tmem_ld16(t0 + 3 * 64 + c16 * 16, nh);
+                    tmem_ld_wait();
+                    const int c0 = ct * 64 + c16 * 16;
+                    if (ok) {
+                        const float4 *hp = reinterpret_cast<const float4 *>(a.h_in + mem_row * 256 + c0);
+                        float4 *ho = reinterpret_cast<float4 *>(a.h_out + mem_row * 256 + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 h4 = hp[q];
+                            const float hprev[4] = {h4.x * mk, h4.y * mk, h4.z * mk, h4.w * mk};
+                            float o[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int c = c0 + q * 4 + i, j = q * 4 + i;
+                                const float r = fast_sigmoid(rg[j] + bias[256 + c]);
+                                const float z = fast_sigmoid(zg[j] + bias[512 + c]);
+                                const float n = fast_tanh(ni[j] + bias[c] + r * (nh[j] + bias[768 + c]));
+                                o[i] = (1.0f - z) * n + z * hprev[i];
+                            }
+                            ho[q] = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar(7 + buf));
+            }
+        }
+    } else if (warp == 4) {
+        // =============================================================== weight producer (one lane)
+        if (lane == 0) {
+            uint32_t chunk = 0;
+            const int parts = a.three_pass ? 2 : 1;
+            for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+                const int p = tile < a.tiles_spatial ? 0 : 1;
+                const char *img = reinterpret_cast<const char *>(a.wimg) + (size_t)p * kColTiles * kKBlocks * 2 * kBChunkBytes;
+                for (int ct = 0; ct < kColTiles; ++ct)
+                    for (int kb = 0; kb < kKBlocks; ++kb)
+                        for (int part = 0; part < parts; ++part, ++chunk) {
+                            const uint32_t slot = chunk & 1u;
+                            mbar_wait(bar(2 + slot), ((chunk >> 1) & 1u) ^ 1u);
+                            mbar_expect_tx(bar(0 + slot), kBChunkBytes);
+                            bulk_g2s(s_base + kOffB + slot * kBChunkBytes,
+                                     img + ((size_t)(ct * kKBlocks + kb) * 2 + part) * kBChunkBytes, kBChunkBytes, bar(0 + slot));
+                        }
+            }
+        }
+    } else {
+        // =============================================================== MMA issuer (one lane)
+        if (lane == 0) {
+            uint32_t chunk = 0, ctg = 0, tile_iter = 0;
+            constexpr uint32_t id192 = idesc_bf16(192), id128 = idesc_bf16(128), id64 = idesc_bf16(64);
+            for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++tile_iter) {
+                mbar_wait(bar(4), tile_iter & 1u);
+                tc_fence_after();
+                for (int ct = 0; ct < kColTiles; ++ct, ++ctg) {
+                    const uint32_t buf = ctg & 1u;
+                    mbar_wait(bar(7 + buf), ((ctg >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d0 = tmem_base + buf * 256u;
+                    for (int kb = 0; kb < kKBlocks; ++kb) {
+                        const uint32_t dcol = d0 + (kb == 0 ? 0u : 64u);
+                        // ---- chunk B_hi: passes A_hi*B_hi and (3-pass) A_lo*B_hi
+                        {
+                            const uint32_t slot = chunk & 1u;
+                            mbar_wait(bar(0 + slot), (chunk >> 1) & 1u);
+                            tc_fence_after();
+                            const uint32_t b_addr = s_base + kOffB + slot * kBChunkBytes;
+                            const int passes = a.three_pass ? 2 : 1;
+                            for (int ps = 0; ps < passes; ++ps) {
+                                const uint32_t a_addr = s_base + (ps == 0 ? kOffAHi : kOffALo) + kb * kABlockBytes;
+#pragma unroll
+                                for (int k16 = 0; k16 < 4; ++k16) {
+                                    const uint64_t ad = smem_desc_sw128(a_addr + k16 * 32);
+                                    const uint64_t bd = smem_desc_sw128(b_addr + k16 * 32);
+                                    const bool first = ps == 0 && k16 == 0;
+                                    if (first && kb == 0) umma_bf16(dcol, ad, bd, id192, 0u);          // overwrite n_i | r | z
+                                    else if (first && kb == 1) {                                        // r | z accumulate, n_h starts
+                                        umma_bf16(dcol, ad, bd, id128, 1u);
+                                        umma_bf16(dcol + 128u, ad, smem_desc_sw128(b_addr + 128 * 128 + k16 * 32), id64, 0u);
+                                    } else umma_bf16(dcol, ad, bd, id192, 1u);
+                                }
+                            }
+                            umma_commit(bar(2 + slot));
+                            ++chunk;
+                        }
+                        // ---- chunk B_lo: pass A_hi*B_lo
+                        if (a.three_pass) {
+                            const uint32_t slot = chunk & 1u;
+                            mbar_wait(bar(0 + slot), (chunk >> 1) & 1u);
+                            tc_fence_after();
+                            const uint32_t b_addr = s_base + kOffB + slot * kBChunkBytes;
+                            const uint32_t a_addr = s_base + kOffAHi + kb * kABlockBytes;
+#pragma unroll
+                            for (int k16 = 0; k16 < 4; ++k16)
+                                umma_bf16(dcol, smem_desc_sw128(a_addr + k16 * 32), smem_desc_sw128(b_addr + k16 * 32), id192, 1u);
+                            umma_commit(bar(2 + slot));
+                            ++chunk;
+                        }
+                    }
+                    umma_commit(bar(5 + buf));       // accumulators of this column tile are complete
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- host side
+void dsrnn_tc_destroy(void *state);
+
+const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void **state)
+{
+    *state = nullptr;
+    TcState *st = new (std::nothrow) TcState();
+    if (!st) return "out of host memory";
+    const size_t img_bytes = (size_t)2 * kColTiles * kKBlocks * 2 * kBChunkBytes;
+    if (cudaMalloc(&st->wimg, img_bytes) != cudaSuccess || cudaMalloc(&st->bias4, 2 * 4 * 256 * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&st->enc, 2 * 192 * sizeof(float)) != cudaSuccess) {
+        delete st;
+        return "cudaMalloc of the packed edge weights failed";
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    PackArgs pa;
+    pa.w_ih[0] = w->s_w_ih; pa.w_hh[0] = w->s_w_hh; pa.b_ih[0] = w->s_b_ih; pa.b_hh[0] = w->s_b_hh; pa.enc_w[0] = w->s_enc_w; pa.enc_b[0] = w->s_enc_b;
+    pa.w_ih[1] = w->t_w_ih; pa.w_hh[1] = w->t_w_hh; pa.b_ih[1] = w->t_b_ih; pa.b_hh[1] = w->t_b_hh; pa.enc_w[1] = w->t_enc_w; pa.enc_b[1] = w->t_enc_b;
+    pa.wimg = st->wimg; pa.bias4 = st->bias4; pa.enc = st->enc;
+    pack_edge_weights_kernel<<<256, 256, 0, stream>>>(pa);
+    if (cudaGetLastError() != cudaSuccess) { dsrnn_tc_destroy(st); return "pack_edge_weights_kernel launch failed"; }
+    if (cudaFuncSetAttribute(edge_gru_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess) {
+        dsrnn_tc_destroy(st);
+        return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+    }
+    *state = st;
+    return nullptr;
+}
+
+void dsrnn_tc_destroy(void *state)
+{
+    TcState *st = static_cast<TcState *>(state);
+    if (!st) return;
+    cudaFree(st->wimg);
+    cudaFree(st->bias4);
+    cudaFree(st->enc);
+    delete st;
+}
+
+const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *, int n_envs, int H, const CnDsrnnIO *io, int precision,
+                                  cudaStream_t stream, int *launches)
+{
+    TcState *st = static_cast<TcState *>(state);
+    if (!st) return "tensor-core edge stage was not initialised";
+    EdgeTcArgs a;
+    a.temporal_edges = io->temporal_edges; a.spatial_edges = io->spatial_edges; a.h_in = io->h_edge_in; a.masks = io->masks;
+    a.h_out = io->h_edge_out; a.wimg = st->wimg; a.bias4 = st->bias4; a.enc = st->enc;
+    a.N = n_envs; a.H = H;
+    a.tiles_spatial = (int)(((size_t)n_envs * H + kRows - 1) / kRows);
+    a.tiles_total = a.tiles_spatial + (n_envs + kRows - 1) / kRows;
+    a.three_pass = precision == CN_PREC_BF16X3 ? 1 : 0;
+    const int grid = a.tiles_total < st->num_sms ? a.tiles_total : st->num_sms;
+    edge_gru_tc_kernel<<<grid, kThreads, kSmemBytes + 1024, stream>>>(a);
+    ++*launches;
+    const cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }

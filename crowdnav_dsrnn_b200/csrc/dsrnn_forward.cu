@@ -15,12 +15,32 @@
 #include <new>
 #include "dsrnn.cuh"
 
+#include <vector>
 struct CnDsrnn {
     CnDsrnnWeights w;
     int device;
     int last_launches;
     void *tc_state;   // packed bf16 weights of the tensor-core edge stage (dsrnn_edge_tc.cu)
+    bool timing;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;   // events around the edge stage
 };
+
+void dsrnn_enable_timing(CnDsrnn *m, int enable) { dsrnn_time_ms(m, nullptr); m->timing = enable != 0; }
+
+float dsrnn_time_ms(CnDsrnn *m, int *count)
+{
+    float total = 0.f;
+    for (auto &p : m->pending) {
+        cudaEventSynchronize(p.second);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.first, p.second);
+        total += ms;
+        m->pool.push_back(p);
+    }
+    if (count) *count = (int)m->pending.size();
+    m->pending.clear();
+    return total;
+}
 
 // implemented in dsrnn_edge_tc.cu
 const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void **state);
@@ -328,6 +348,7 @@ const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t strea
     m->device = device;
     m->last_launches = 0;
     m->tc_state = nullptr;
+    m->timing = false;
     const char *msg = dsrnn_tc_create(w, stream, &m->tc_state);
     if (msg) { delete m; return msg; }
     *out = m;
@@ -337,6 +358,8 @@ const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t strea
 void dsrnn_destroy(CnDsrnn *m)
 {
     if (m->tc_state) dsrnn_tc_destroy(m->tc_state);
+    dsrnn_time_ms(m, nullptr);
+    for (auto &p : m->pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete m;
 }
 
@@ -367,6 +390,13 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
     int launches = 0;
 
     // ---- stage 1: edge GRUs -> io->h_edge_out
+    if (m->timing) {
+        std::pair<cudaEvent_t, cudaEvent_t> p;
+        if (!m->pool.empty()) { p = m->pool.back(); m->pool.pop_back(); }
+        else { cudaEventCreate(&p.first); cudaEventCreate(&p.second); }
+        cudaEventRecord(p.first, s);
+        m->pending.push_back(p);
+    }
     if (precision == CN_PREC_FP32) {
         EdgeArgs t;
         t.x_in = io->temporal_edges; t.h_in = io->h_edge_in; t.masks = io->masks;
@@ -383,6 +413,8 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
         const char *msg = dsrnn_tc_edge_forward(m->tc_state, &w, N, H, io, precision, s, &launches);
         if (msg) return msg;
     }
+
+    if (m->timing) cudaEventRecord(m->pending.back().second, s);
 
     // ---- stage 2: attention projections, softmax, weighted sum
     {

@@ -139,7 +139,7 @@ class Policy(nn.Module):
         if action_space.__class__.__name__ != "Box":
             raise NotImplementedError("only Box action spaces are supported")
         self.dist = DiagGaussian(self.base.output_size, action_space.shape[0])
-        self.precision = "fp32"   # contraction precision of the CUDA forward: "fp32" | "bf16x3" | "bf16"
+        self.precision = "bf16x3"   # contraction precision of the CUDA forward: "fp32" | "bf16x3" | "bf16"
         self._handle = None
         self._weights_key = None
         self._workspace = None

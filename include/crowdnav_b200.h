@@ -222,6 +222,14 @@ int cn_dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnDsrnnIO *io,
 /* number of kernels the last forward / step call launched (bench.py's gpu_launches claim) */
 int cn_dsrnn_last_launches(const CnDsrnn *m);
 int cn_env_last_launches(const CnEnv *env);
+/* Optional device timing of the dominant kernels (bench.py's roofline): when enabled the library brackets the
+ * edge-GRU stage of every forward / the step kernel of every cn_env_step with CUDA events on the launching
+ * stream.  *_time_ms() synchronises those events and returns the accumulated milliseconds and launch count
+ * since the last call (and resets both). */
+int cn_dsrnn_enable_timing(CnDsrnn *m, int enable);
+int cn_dsrnn_time_ms(CnDsrnn *m, float *edge_stage_ms, int *n_forwards);
+int cn_env_enable_timing(CnEnv *env, int enable);
+int cn_env_time_ms(CnEnv *env, float *step_kernel_ms, int *n_steps);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ from oracle import dsrnn_oracle
 from helpers import DSRNN_CASES, GOLDEN, TOL_NET_REL
 
 pytestmark = pytest.mark.gpu
-PRECISIONS = ["fp32"]
+PRECISIONS = ["fp32", "bf16x3"]
 
 
 def _policy(H, weights):
