@@ -221,52 +221,66 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
             const int row0 = (spatial ? tile : tile - a.tiles_spatial) * kRows;
             const int M = spatial ? a.N * H : a.N;
             const float *enc = s_enc + p * 192;
-            // ---- stage A: warp w converts rows w*32 .. w*32+31; a warp reads one row (1 KB) per two float4 loads
-            for (int rr = 0; rr < 32; ++rr) {
-                const int r = warp * 32 + rr;
-                const int m = row0 + r;
-                const bool ok = m < M;
-                size_t mem_row = 0;
-                float mk = 0.f, x0 = 0.f, x1 = 0.f;
-                if (ok) {
-                    const int env = spatial ? m / H : m;
-                    mem_row = spatial ? (size_t)env * stride + 1 + (m - env * H) : (size_t)env * stride;
-                    mk = a.masks[env];
-                    const float *x = spatial ? a.spatial_edges + 2 * (size_t)m : a.temporal_edges + 2 * (size_t)m;
-                    x0 = x[0]; x1 = x[1];
-                }
-                {   // encoded input block (k-block 0): lane owns k = 2*lane, 2*lane+1
-                    float e[2];
+            // ---- stage A: warp w converts rows w*32 .. w*32+31, 8 rows per batch so 16 x 16 B loads per lane are in
+            //      flight before the first conversion (a warp reads one 1 KB row with two float4 loads per lane)
+#pragma unroll 1
+            for (int rb = 0; rb < 32; rb += 8) {
+                float4 hv[8][2];
+                float xs[8][2], mks[8];
+                bool oks[8];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int k = 2 * lane + i;
-                        e[i] = ok ? fmaxf(fmaf(enc[64 + k], x1, enc[k] * x0) + enc[128 + k], 0.f) : 0.f;
-                    }
-                    const __nv_bfloat162 hi = __floats2bfloat162_rn(e[0], e[1]);
-                    const int off = sw128_offset(r, 2 * lane);
-                    *reinterpret_cast<__nv_bfloat162 *>(smem + kOffAHi + off) = hi;
-                    if (a.three_pass) {
-                        const __nv_bfloat162 lo = __floats2bfloat162_rn(e[0] - __low2float(hi), e[1] - __high2float(hi));
-                        *reinterpret_cast<__nv_bfloat162 *>(smem + kOffALo + off) = lo;
+                for (int b = 0; b < 8; ++b) {
+                    const int m = row0 + warp * 32 + rb + b;
+                    oks[b] = m < M;
+                    hv[b][0] = hv[b][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    xs[b][0] = xs[b][1] = mks[b] = 0.f;
+                    if (oks[b]) {
+                        const int env = spatial ? m / H : m;
+                        const size_t mem_row = spatial ? (size_t)env * stride + 1 + (m - env * H) : (size_t)env * stride;
+                        const float *hrow = a.h_in + mem_row * 256 + lane * 4;
+                        hv[b][0] = *reinterpret_cast<const float4 *>(hrow);
+                        hv[b][1] = *reinterpret_cast<const float4 *>(hrow + 128);
+                        mks[b] = a.masks[env];
+                        const float *x = spatial ? a.spatial_edges + 2 * (size_t)m : a.temporal_edges + 2 * (size_t)m;
+                        xs[b][0] = x[0]; xs[b][1] = x[1];
                     }
                 }
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {   // hidden blocks: elements half*128 + lane*4 .. +3
-                    const int e0 = half * 128 + lane * 4;
-                    float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) h4 = *reinterpret_cast<const float4 *>(a.h_in + mem_row * 256 + e0);
-                    h4.x *= mk; h4.y *= mk; h4.z *= mk; h4.w *= mk;
-                    const int kb = 1 + (e0 >> 6);
-                    const int off = kb * kABlockBytes + sw128_offset(r, e0 & 63);
-                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(h4.x, h4.y), h23 = __floats2bfloat162_rn(h4.z, h4.w);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<const uint32_t *>(&h01); pk.y = *reinterpret_cast<const uint32_t *>(&h23);
-                    *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = pk;
-                    if (a.three_pass) {
-                        const __nv_bfloat162 l01 = __floats2bfloat162_rn(h4.x - __low2float(h01), h4.y - __high2float(h01));
-                        const __nv_bfloat162 l23 = __floats2bfloat162_rn(h4.z - __low2float(h23), h4.w - __high2float(h23));
-                        pk.x = *reinterpret_cast<const uint32_t *>(&l01); pk.y = *reinterpret_cast<const uint32_t *>(&l23);
-                        *reinterpret_cast<uint2 *>(smem + kOffALo + off) = pk;
+                for (int b = 0; b < 8; ++b) {
+                    const int r = warp * 32 + rb + b;
+                    {   // encoded input block (k-block 0): lane owns k = 2*lane, 2*lane+1
+                        float e[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int k = 2 * lane + i;
+                            e[i] = oks[b] ? fmaxf(fmaf(enc[64 + k], xs[b][1], enc[k] * xs[b][0]) + enc[128 + k], 0.f) : 0.f;
+                        }
+                        const __nv_bfloat162 hi = __floats2bfloat162_rn(e[0], e[1]);
+                        const int off = sw128_offset(r, 2 * lane);
+                        *reinterpret_cast<__nv_bfloat162 *>(smem + kOffAHi + off) = hi;
+                        if (a.three_pass) {
+                            const __nv_bfloat162 lo = __floats2bfloat162_rn(e[0] - __low2float(hi), e[1] - __high2float(hi));
+                            *reinterpret_cast<__nv_bfloat162 *>(smem + kOffALo + off) = lo;
+                        }
+                    }
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {   // hidden blocks: elements half*128 + lane*4 .. +3
+                        const int e0 = half * 128 + lane * 4;
+                        float4 h4 = hv[b][half];
+                        const float mk = mks[b];
+                        h4.x *= mk; h4.y *= mk; h4.z *= mk; h4.w *= mk;
+                        const int kb = 1 + (e0 >> 6);
+                        const int off = kb * kABlockBytes + sw128_offset(r, e0 & 63);
+                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(h4.x, h4.y), h23 = __floats2bfloat162_rn(h4.z, h4.w);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<const uint32_t *>(&h01); pk.y = *reinterpret_cast<const uint32_t *>(&h23);
+                        *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = pk;
+                        if (a.three_pass) {
+                            const __nv_bfloat162 l01 = __floats2bfloat162_rn(h4.x - __low2float(h01), h4.y - __high2float(h01));
+                            const __nv_bfloat162 l23 = __floats2bfloat162_rn(h4.z - __low2float(h23), h4.w - __high2float(h23));
+                            pk.x = *reinterpret_cast<const uint32_t *>(&l01); pk.y = *reinterpret_cast<const uint32_t *>(&l23);
+                            *reinterpret_cast<uint2 *>(smem + kOffALo + off) = pk;
+                        }
                     }
                 }
             }
@@ -286,10 +300,15 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
             const float *bias = s_bias + p * 4 * 256;
             for (int ct = 0; ct < kColTiles; ++ct, ++ctg) {
                 const uint32_t buf = ctg & 1u;
+                // h_prev of this row's 64 hidden units (just staged, so L2-resident) is fetched BEFORE the accumulator wait
+                float4 hprev4[16];
+                const float4 *hp = reinterpret_cast<const float4 *>(a.h_in + mem_row * 256 + ct * 64);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) hprev4[q] = ok ? hp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                 mbar_wait(bar(5 + buf), (ctg >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256u;
-#pragma unroll 1
+#pragma unroll
                 for (int c16 = 0; c16 < 4; ++c16) {
                     float ni[16], rg[16], zg[16], nh[16];
                     tmem_ld16(t0 + 0 * 64 + c16 * 16, ni);
@@ -299,11 +318,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                     tmem_ld_wait();
                     const int c0 = ct * 64 + c16 * 16;
                     if (ok) {
-                        const float4 *hp = reinterpret_cast<const float4 *>(a.h_in + mem_row * 256 + c0);
                         float4 *ho = reinterpret_cast<float4 *>(a.h_out + mem_row * 256 + c0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 h4 = hp[q];
+                            const float4 h4 = hprev4[c16 * 4 + q];
                             const float hprev[4] = {h4.x * mk, h4.y * mk, h4.z * mk, h4.w * mk};
                             float o[4];
 #pragma unroll
