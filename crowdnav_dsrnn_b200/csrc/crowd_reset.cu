@@ -4,8 +4,8 @@
 // CrowdSimDict.reset (crowd_sim/envs/crowd_sim_dict.py:105-203): scenario choice, robot spawn
 // (crowd_sim.py:626-660), per-human attributes (agent.py:44-50) and spawn/goal by scenario
 // (crowd_sim.py:296-393) with the min-distance rejection rule, belief initialisation
-// (crowd_sim.py:443-445), potential, counters.  One warp per env; lane t evaluates try t of the
-// (bounded) rejection loops, the first accepted lane wins -- identical to the sequential loop
+// (crowd_sim.py:443-445), potential, counters.  One CTA per resetting env; thread t evaluates try t of the
+// (bounded) rejection loops, the first accepted thread wins -- identical to the sequential loop
 // because every candidate is a pure function of (episode key, human, try) under the counter-based
 // Philox4x32-10 contract (oracle/crowd_oracle.c restates the same contract sequentially).
 #include "env_common.cuh"
@@ -47,19 +47,35 @@ __device__ __forceinline__ void write_reset_obs(const EnvParams &P, const CnObsO
     if (lane == 0 && obs.visible_mask) obs.visible_mask[e] = vis_bits;
 }
 
-// grid: ceil(N / 4) CTAs of 4 warps, one warp per env; envs whose mask byte is 0 return immediately.
+// first thread (in try order) whose candidate is acceptable, over the whole CTA; -1 if none.  s_vote: 4 ints.
+__device__ __forceinline__ int cta_first_ok(bool ok, int *s_vote)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    __syncthreads();                       // previous round's readers are done with s_vote
+    if (lane == 0) s_vote[warp] = b ? warp * 32 + (__ffs(b) - 1) : 0x7fffffff;
+    __syncthreads();
+    int first = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < RESET_THREADS / 32; ++w) first = min(first, s_vote[w]);
+    return first == 0x7fffffff ? -1 : first;
+}
+
+// grid: one CTA of 128 threads per env (envs whose mask byte is 0 exit at once); thread t evaluates try
+// t, t+128, ... of each bounded rejection loop, so a typical spawn needs a single round per human.
 __global__ void __launch_bounds__(RESET_THREADS)
 crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnObsOut obs,
                    const uint8_t *__restrict__ mask)
 {
-    __shared__ float4 s_h[RESET_THREADS / 32][CN_MAX_HUMANS];   // px, py, radius of the humans spawned so far
+    __shared__ float4 s_h[CN_MAX_HUMANS];   // px, py, radius of the humans spawned so far
+    __shared__ int s_vote[RESET_THREADS / 32];
+    __shared__ double s_pick[6];
     const CnConfig &cfg = P.cfg;
     const int H = cfg.human_num;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (RESET_THREADS / 32) + warp;
+    const int tid = threadIdx.x, lane = threadIdx.x & 31;
+    const int e = blockIdx.x;
     if (e >= P.n_envs) return;
     if (mask && !mask[e]) return;
-    const unsigned FULL = 0xffffffffu;
     int4 ctr = P.a.ctr[e];
     const uint64_t key = episode_key(cfg, ctr.z, e);
     const uint4 g0 = philox4x32(key, 0, 0, 0, RNG_RESET);
@@ -75,24 +91,24 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
         const bool uni = cfg.kinematics == CN_UNICYCLE;
         const double angle = u01(g0.y) * CN_PI * 2.0;
         double cpx = R * cos(angle), cpy = R * sin(angle), cgx = 0.0, cgy = 0.0;
-        bool found = false;
-        for (int t0 = 0; t0 < cfg.max_robot_tries && !found; t0 += 32) {
-            const int t = t0 + lane;
+        for (int t0 = 0; t0 < cfg.max_robot_tries; t0 += RESET_THREADS) {
+            const int t = t0 + tid;
             const uint4 x = philox4x32(key, (uint32_t)t, 1, 0, RNG_RESET);
             if (uni) { cgx = -R + 2.0 * R * u01(x.x); cgy = -R + 2.0 * R * u01(x.y); }
             else {
                 cpx = -R + 2.0 * R * u01(x.x); cpy = -R + 2.0 * R * u01(x.y);
                 cgx = -R + 2.0 * R * u01(x.z); cgy = -R + 2.0 * R * u01(x.w);
             }
-            const bool in_range = t < cfg.max_robot_tries;
-            const bool ok = in_range && norm2d(cpx - cgx, cpy - cgy) >= 6.0;
-            const unsigned okb = __ballot_sync(FULL, ok);
-            int src;
-            if (okb) { src = __ffs(okb) - 1; found = true; }
-            else if (t0 + 32 >= cfg.max_robot_tries) { src = (cfg.max_robot_tries - 1) & 31; found = true; }  // keep the last try
-            else continue;
-            cpx = shfl_d(FULL, cpx, src); cpy = shfl_d(FULL, cpy, src);
-            cgx = shfl_d(FULL, cgx, src); cgy = shfl_d(FULL, cgy, src);
+            const bool ok = t < cfg.max_robot_tries && norm2d(cpx - cgx, cpy - cgy) >= 6.0;
+            int src = cta_first_ok(ok, s_vote);
+            const bool last_round = t0 + RESET_THREADS >= cfg.max_robot_tries;
+            if (src < 0 && last_round) src = (cfg.max_robot_tries - 1) - t0;        // keep the last try
+            if (src >= 0) {
+                if (tid == src) { s_pick[0] = cpx; s_pick[1] = cpy; s_pick[2] = cgx; s_pick[3] = cgy; }
+                __syncthreads();
+                cpx = s_pick[0]; cpy = s_pick[1]; cgx = s_pick[2]; cgy = s_pick[3];
+                break;
+            }
         }
         rpx = cpx; rpy = cpy; rgx = cgx; rgy = cgy;
         rth = uni ? u01(g0.z) * 2.0 * CN_PI : CN_PI / 2.0;
@@ -112,9 +128,9 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
         }
         const float radius_f = (float)radius;
         SpawnCand c;
-        bool found = false;
-        for (int t0 = 0; t0 < cfg.max_spawn_tries && !found; t0 += 32) {
-            const int t = t0 + lane;
+        c.px = c.py = c.gx = c.gy = c.heading = c.v_pref = 0.0;
+        for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += RESET_THREADS) {
+            const int t = t0 + tid;
             const uint4 xa = philox4x32(key, (uint32_t)t, (uint32_t)i, 0, RNG_SPAWN);
             const uint4 xb = philox4x32(key, (uint32_t)t, (uint32_t)i, 1, RNG_SPAWN);
             const double u6[6] = {u01(xa.x), u01(xa.y), u01(xa.z), u01(xa.w), u01(xb.x), u01(xb.y)};
@@ -125,33 +141,36 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
                 collide = norm2d(c.px - (double)rpv.x, c.py - (double)rpv.y) < md;
             }
             for (int k = 0; k < i && !collide; ++k) {
-                const float4 a = s_h[warp][k];
+                const float4 a = s_h[k];
                 const double md = (double)radius_f + (double)a.z + cfg.discomfort_dist;
                 if (norm2d(c.px - (double)a.x, c.py - (double)a.y) < md) collide = true;
             }
             const bool ok = t < cfg.max_spawn_tries && !collide;
-            const unsigned okb = __ballot_sync(FULL, ok);
-            int src;
-            if (okb) { src = __ffs(okb) - 1; found = true; }
-            else if (t0 + 32 >= cfg.max_spawn_tries) { src = (cfg.max_spawn_tries - 1) & 31; found = true; }
-            else continue;
-            c.px = shfl_d(FULL, c.px, src); c.py = shfl_d(FULL, c.py, src);
-            c.gx = shfl_d(FULL, c.gx, src); c.gy = shfl_d(FULL, c.gy, src);
-            c.heading = shfl_d(FULL, c.heading, src); c.v_pref = shfl_d(FULL, c.v_pref, src);
+            int src = cta_first_ok(ok, s_vote);
+            const bool last_round = t0 + RESET_THREADS >= cfg.max_spawn_tries;
+            if (src < 0 && last_round) src = (cfg.max_spawn_tries - 1) - t0;        // keep the last try
+            if (src >= 0) {
+                if (tid == src) { s_pick[0] = c.px; s_pick[1] = c.py; s_pick[2] = c.gx; s_pick[3] = c.gy; s_pick[4] = c.heading; s_pick[5] = c.v_pref; }
+                __syncthreads();
+                c.px = s_pick[0]; c.py = s_pick[1]; c.gx = s_pick[2]; c.gy = s_pick[3]; c.heading = s_pick[4]; c.v_pref = s_pick[5];
+                break;
+            }
         }
         const float4 pv = make_float4((float)c.px, (float)c.py, 0.0f, 0.0f);
         const float4 gr = make_float4((float)c.gx, (float)c.gy, radius_f, (float)c.v_pref);
-        if (lane == 0) {
+        __syncthreads();                    // everyone has read s_pick / the old s_h before they change
+        if (tid == 0) {
             const size_t hi = (size_t)e * H + i;
-            s_h[warp][i] = make_float4(pv.x, pv.y, radius_f, 0.0f);
+            s_h[i] = make_float4(pv.x, pv.y, radius_f, 0.0f);
             P.a.hum_pv[hi] = pv;
             P.a.hum_gr[hi] = gr;
             P.a.hum_th[hi] = (float)c.heading;
         }
-        __syncwarp();
+        __syncthreads();
     }
 
-    // ---- counters, potential, observation
+    // ---- counters, potential, observation (warp 0 only; its lane 0 wrote the humans above)
+    if (tid >= 32) return;
     ctr.x = 0;
     ctr.z = (int)(uint32_t)(((uint64_t)(uint32_t)ctr.z + (uint64_t)cfg.nenv) % cfg.case_size);
     ctr.w = scenario;
@@ -237,8 +256,7 @@ __global__ void state_convert_kernel(const __grid_constant__ EnvParams P, const 
 
 extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, cudaStream_t stream)
 {
-    const int per = RESET_THREADS / 32;
-    crowd_reset_kernel<<<(P->n_envs + per - 1) / per, RESET_THREADS, 0, stream>>>(*P, *obs, mask);
+    crowd_reset_kernel<<<P->n_envs, RESET_THREADS, 0, stream>>>(*P, *obs, mask);
     return (int)cudaGetLastError();
 }
 

@@ -22,6 +22,9 @@
 
 #define ORCA_EPS 0.00001f
 #define STEP_THREADS 256
+#ifndef STEP_MIN_BLOCKS
+#define STEP_MIN_BLOCKS 4
+#endif
 
 template <int G> struct GroupOps {
     static constexpr unsigned kLow = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
@@ -30,16 +33,12 @@ template <int G> struct GroupOps {
     int gl;          // lane index inside the group
     __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(gmask, v, src, G); }
     __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(gmask, p) >> gbase) & kLow; }
-    __device__ __forceinline__ float rmax(float v) const {
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(gmask, v, o, G));
-        return v;
-    }
-    __device__ __forceinline__ float rmin(float v) const {
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gmask, v, o, G));
-        return v;
-    }
+    // min/max over the group in ONE redux.sync each: floats are mapped to integers with the same total order
+    // (exact: a reduction only selects one of its inputs; the LP never feeds NaNs here)
+    static __device__ __forceinline__ int ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+    static __device__ __forceinline__ float unord(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+    __device__ __forceinline__ float rmax(float v) const { return unord(__reduce_max_sync(gmask, ord(v))); }
+    __device__ __forceinline__ float rmin(float v) const { return unord(__reduce_min_sync(gmask, ord(v))); }
 };
 
 struct Line { float px, py, dx, dy; };
@@ -187,8 +186,8 @@ __device__ __forceinline__ float2 orca_group(const CnConfig &cfg, const GroupOps
     const unsigned in_bits = g.ballot(in);
     const int n = __popc(in_bits);
     int rank = 0;
-#pragma unroll
-    for (int k = 0; k < G; ++k) {
+#pragma unroll 4
+    for (int k = 0; k < M; ++k) {   // slots >= M are never in range
         const float dk = g.shfl(dist_sq, k);
         if (((in_bits >> k) & 1u) && (dk < dist_sq || (dk == dist_sq && k < g.gl))) ++rank;
     }
@@ -594,7 +593,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
 // grid: ceil(N / E) CTAs of 256 threads, each owning E consecutive envs.
 // dynamic smem: E*H*(float4 pv + float4 gr + float2 nv + float th) + 256 float4 sort scratch
 template <int G>
-__global__ void __launch_bounds__(STEP_THREADS)
+__global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS)
 crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnStepOut out,
                   const float *__restrict__ action, int E)
 {

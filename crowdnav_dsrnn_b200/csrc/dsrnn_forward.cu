@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <new>
 #include "dsrnn.cuh"
+#include "dsrnn_tc_linear.cuh"
 
 #include <vector>
 struct CnDsrnn {
@@ -23,6 +24,10 @@ struct CnDsrnn {
     void *tc_state;   // packed bf16 weights of the tensor-core edge stage (dsrnn_edge_tc.cu)
     bool timing;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;   // events around the edge stage
+    int num_sms;
+    // tensor-core images of the stage 2-4 linears (dsrnn_tc_linear.cu)
+    TcLinear att_qt, emb, gi, gh, out, ac0, actor2, critic2, value, mean;
+    float *att_wc = nullptr, *att_bc = nullptr;   // folded attention projection (W_s^T W_t, W_s^T b_t)
 };
 
 void dsrnn_enable_timing(CnDsrnn *m, int enable) { dsrnn_time_ms(m, nullptr); m->timing = enable != 0; }
@@ -231,18 +236,39 @@ __global__ void __launch_bounds__(256) edge_gru_simt_kernel(const EdgeArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------- stage 2
-// one warp per env: scores, softmax over the H humans, weighted sum; writes cat = [o_t | c]  (N x 512)
-__global__ void __launch_bounds__(128) attention_kernel(const float *__restrict__ h_edge, const float *__restrict__ Q,
-                                                        const float *__restrict__ Kp, float *__restrict__ cat, int N, int H)
+// EdgeAttention (srnn_model.py:256-339) scores are q.k_i with q = W_t o_t + b_t and k_i = W_s o_i + b_s.  Since
+//   q.(W_s o_i + b_s) = (W_s^T q).o_i + q.b_s   and the softmax over i ignores the per-env constant q.b_s,
+// the N*H x 64 key projection is replaced by ONE per-env projection qt = (W_s^T W_t) o_t + W_s^T b_t (256 values)
+// and the scores are taken against the edge outputs o_i that the weighted sum reads anyway.
+__global__ void fold_attention_kernel(const float *__restrict__ wt, const float *__restrict__ bt, const float *__restrict__ wsp,
+                                      float *__restrict__ wc, float *__restrict__ bc)
+{
+    const int a = blockIdx.x, b = threadIdx.x;       // wc[a][b] = sum_d wsp[d][a] * wt[d][b]; grid 256 x 256 threads
+    double acc = 0.0;
+    for (int d = 0; d < 64; ++d) acc += (double)wsp[d * 256 + a] * (double)wt[d * 256 + b];
+    wc[a * 256 + b] = (float)acc;
+    if (b == 0) {
+        double s = 0.0;
+        for (int d = 0; d < 64; ++d) s += (double)wsp[d * 256 + a] * (double)bt[d];
+        bc[a] = (float)s;
+    }
+}
+
+// one warp per env: scores against qt, softmax over the H humans, weighted sum; writes cat = [o_t | c]  (N x 512)
+__global__ void __launch_bounds__(128) attention_kernel(const float *__restrict__ h_edge, const float *__restrict__ qt,
+                                                        float *__restrict__ cat, int N, int H)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * 4 + warp;
     if (e >= N) return;
-    const float q0 = Q[(size_t)e * 64 + lane], q1 = Q[(size_t)e * 64 + 32 + lane];
+    const float4 qa = *reinterpret_cast<const float4 *>(qt + (size_t)e * 256 + lane * 8);
+    const float4 qb = *reinterpret_cast<const float4 *>(qt + (size_t)e * 256 + lane * 8 + 4);
+    const float *ot = h_edge + (size_t)e * (H + 1) * 256;
     float my_score = -INFINITY;
     for (int i = 0; i < H; ++i) {
-        const float *k = Kp + ((size_t)e * H + i) * 64;
-        float s = q0 * k[lane] + q1 * k[32 + lane];
+        const float *os = ot + (size_t)(1 + i) * 256 + lane * 8;
+        const float4 v0 = *reinterpret_cast<const float4 *>(os), v1 = *reinterpret_cast<const float4 *>(os + 4);
+        float s = qa.x * v0.x + qa.y * v0.y + qa.z * v0.z + qa.w * v0.w + qb.x * v1.x + qb.y * v1.y + qb.z * v1.z + qb.w * v1.w;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == i) my_score = s * ((float)H / 8.0f);      // temperature = num_edges / sqrt(attention_size)
@@ -255,7 +281,6 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float alpha = ex / sum;
-    const float *ot = h_edge + (size_t)e * (H + 1) * 256;
     float c[8] = {};
     for (int i = 0; i < H; ++i) {
         const float ai = __shfl_sync(0xffffffffu, alpha, i);
@@ -311,7 +336,7 @@ __global__ void node_gru_gate_kernel(const float *__restrict__ gi, const float *
 
 // ---------------------------------------------------------------------------------------------- host side
 struct Workspace {
-    float *Kp, *Q, *cat, *x, *gi, *gh, *y, *a1, *a2, *c1, *c2;
+    float *qt, *cat, *x, *gi, *gh, *y, *ac1, *a2, *c2;
 };
 
 static size_t carve_ws(Workspace *w, void *base, int N, int H)
@@ -324,21 +349,51 @@ static size_t carve_ws(Workspace *w, void *base, int N, int H)
     };
     Workspace tmp;
     Workspace *q = w ? w : &tmp;
-    take(&q->Kp, (size_t)N * H * 64);
-    take(&q->Q, (size_t)N * 64);
+    (void)H;
+    take(&q->qt, (size_t)N * 256);
     take(&q->cat, (size_t)N * 512);
     take(&q->x, (size_t)N * 128);
     take(&q->gi, (size_t)N * 384);
     take(&q->gh, (size_t)N * 384);
     take(&q->y, (size_t)N * 256);
-    take(&q->a1, (size_t)N * 256);
+    take(&q->ac1, (size_t)N * 512);     // [tanh(actor.0 y) | tanh(critic.0 y)]
     take(&q->a2, (size_t)N * 256);
-    take(&q->c1, (size_t)N * 256);
     take(&q->c2, (size_t)N * 256);
     return off;
 }
 
 size_t dsrnn_workspace_bytes(int n_envs, int human_num) { return carve_ws(nullptr, nullptr, n_envs, human_num); }
+
+static void destroy_tc_linears(CnDsrnn *m)
+{
+    TcLinear *all[] = {&m->att_qt, &m->emb, &m->gi, &m->gh, &m->out, &m->ac0, &m->actor2, &m->critic2, &m->value, &m->mean};
+    for (TcLinear *L : all) tc_linear_destroy(L);
+    if (m->att_wc) cudaFree(m->att_wc);
+    if (m->att_bc) cudaFree(m->att_bc);
+    m->att_wc = m->att_bc = nullptr;
+}
+
+static const char *create_tc_linears(CnDsrnn *m, cudaStream_t s)
+{
+    const CnDsrnnWeights &w = m->w;
+    const char *msg;
+#define CN_TCL(L, W0, B0, N0, W1, B1, N1, K, NT) if ((msg = tc_linear_create(&m->L, W0, B0, N0, W1, B1, N1, K, NT, s))) return msg
+    if (cudaMalloc(&m->att_wc, 256 * 256 * sizeof(float)) != cudaSuccess || cudaMalloc(&m->att_bc, 256 * sizeof(float)) != cudaSuccess)
+        return "cudaMalloc of the folded attention projection failed";
+    fold_attention_kernel<<<256, 256, 0, s>>>(w.att_t_w, w.att_t_b, w.att_s_w, m->att_wc, m->att_bc);
+    CN_TCL(att_qt, m->att_wc, m->att_bc, 256, nullptr, nullptr, 0, 256, 256);
+    CN_TCL(emb, w.n_att_w, w.n_att_b, 64, nullptr, nullptr, 0, 512, 64);
+    CN_TCL(gi, w.n_w_ih, w.n_b_ih, 384, nullptr, nullptr, 0, 128, 192);
+    CN_TCL(gh, w.n_w_hh, w.n_b_hh, 384, nullptr, nullptr, 0, 128, 192);
+    CN_TCL(out, w.n_out_w, w.n_out_b, 256, nullptr, nullptr, 0, 128, 256);
+    CN_TCL(ac0, w.actor0_w, w.actor0_b, 256, w.critic0_w, w.critic0_b, 256, 256, 256);
+    CN_TCL(actor2, w.actor2_w, w.actor2_b, 256, nullptr, nullptr, 0, 256, 256);
+    CN_TCL(critic2, w.critic2_w, w.critic2_b, 256, nullptr, nullptr, 0, 256, 256);
+    CN_TCL(value, w.critic_lin_w, w.critic_lin_b, 1, nullptr, nullptr, 0, 256, 16);
+    CN_TCL(mean, w.mean_w, w.mean_b, 2, nullptr, nullptr, 0, 256, 16);
+#undef CN_TCL
+    return nullptr;
+}
 
 const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t stream, CnDsrnn **out)
 {
@@ -349,8 +404,10 @@ const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t strea
     m->last_launches = 0;
     m->tc_state = nullptr;
     m->timing = false;
+    cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
     const char *msg = dsrnn_tc_create(w, stream, &m->tc_state);
-    if (msg) { delete m; return msg; }
+    if (!msg) msg = create_tc_linears(m, stream);
+    if (msg) { dsrnn_destroy(m); return msg; }
     *out = m;
     return nullptr;
 }
@@ -358,6 +415,7 @@ const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t strea
 void dsrnn_destroy(CnDsrnn *m)
 {
     if (m->tc_state) dsrnn_tc_destroy(m->tc_state);
+    destroy_tc_linears(m);
     dsrnn_time_ms(m, nullptr);
     for (auto &p : m->pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete m;
@@ -368,17 +426,37 @@ const char *dsrnn_update_weights(CnDsrnn *m, const CnDsrnnWeights *w, cudaStream
     m->w = *w;
     if (m->tc_state) dsrnn_tc_destroy(m->tc_state);
     m->tc_state = nullptr;
-    return dsrnn_tc_create(w, stream, &m->tc_state);
+    destroy_tc_linears(m);
+    const char *msg = dsrnn_tc_create(w, stream, &m->tc_state);
+    return msg ? msg : create_tc_linears(m, stream);
 }
 
 int dsrnn_last_launches(const CnDsrnn *m) { return m->last_launches; }
 
-static LinArgs lin(const float *X, int ldx, const float *W, const float *b, int M, int N, int K, float *Y, int ldy, int act)
+// one linear layer, on CUDA cores (fp32) or tensor cores (bf16x3 / bf16)
+struct LinearRun {
+    CnDsrnn *m; int precision; cudaStream_t s; int *launches; const char *err = nullptr;
+    void operator()(const TcLinear &tcl, const float *W, const float *b, TcLinearCall c, int N, int K)
+    {
+        if (err) return;
+        if (precision == CN_PREC_FP32) {
+            LinArgs a;
+            a.X = c.X; a.ldx = c.ldx; a.rows_per_env = c.rows_per_env; a.env_stride_rows = c.env_stride_rows; a.first_row = c.first_row;
+            a.rowscale = c.rowscale; a.W = W; a.b = b; a.M = c.M; a.N = N; a.K = K; a.Y = c.Y; a.ldy = c.ldy; a.ycol0 = c.ycol0; a.act = c.act;
+            launch_linear(a, s, launches);
+        } else {
+            c.three_pass = precision == CN_PREC_BF16X3 ? 1 : 0;
+            err = tc_linear_run(&tcl, c, m->num_sms, s);
+            ++*launches;
+        }
+    }
+};
+
+static TcLinearCall call(const float *X, int ldx, int M, float *Y, int ldy, int act, int ycol0 = 0)
 {
-    LinArgs a;
-    a.X = X; a.ldx = ldx; a.rows_per_env = 1; a.env_stride_rows = 1; a.first_row = 0; a.rowscale = nullptr;
-    a.W = W; a.b = b; a.M = M; a.N = N; a.K = K; a.Y = Y; a.ldy = ldy; a.ycol0 = 0; a.act = act;
-    return a;
+    TcLinearCall c;
+    c.X = X; c.ldx = ldx; c.M = M; c.Y = Y; c.ldy = ldy; c.act = act; c.ycol0 = ycol0;
+    return c;
 }
 
 const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int precision, void *workspace, cudaStream_t s)
@@ -413,18 +491,16 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
         const char *msg = dsrnn_tc_edge_forward(m->tc_state, &w, N, H, io, precision, s, &launches);
         if (msg) return msg;
     }
-
     if (m->timing) cudaEventRecord(m->pending.back().second, s);
+
+    LinearRun run{m, precision, s, &launches};
 
     // ---- stage 2: attention projections, softmax, weighted sum
     {
-        LinArgs q = lin(io->h_edge_out, 256, w.att_t_w, w.att_t_b, N, 64, 256, ws.Q, 64, ACT_NONE);
+        TcLinearCall q = call(io->h_edge_out, 256, N, ws.qt, 256, ACT_NONE);
         q.rows_per_env = 1; q.env_stride_rows = H + 1; q.first_row = 0;
-        launch_linear(q, s, &launches);
-        LinArgs k = lin(io->h_edge_out, 256, w.att_s_w, w.att_s_b, N * H, 64, 256, ws.Kp, 64, ACT_NONE);
-        k.rows_per_env = H; k.env_stride_rows = H + 1; k.first_row = 1;
-        launch_linear(k, s, &launches);
-        attention_kernel<<<(N + 3) / 4, 128, 0, s>>>(io->h_edge_out, ws.Q, ws.Kp, ws.cat, N, H);
+        run(m->att_qt, m->att_wc, m->att_bc, q, 256, 256);
+        attention_kernel<<<(N + 3) / 4, 128, 0, s>>>(io->h_edge_out, ws.qt, ws.cat, N, H);
         ++launches;
     }
 
@@ -433,29 +509,32 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
         node_encode_kernel<<<(unsigned)(((size_t)N * 64 + 255) / 256), 256, 0, s>>>(io->robot_node, w.robot_w, w.robot_b,
                                                                                   w.n_enc_w, w.n_enc_b, ws.x, N);
         ++launches;
-        LinArgs emb = lin(ws.cat, 512, w.n_att_w, w.n_att_b, N, 64, 512, ws.x, 128, ACT_RELU);
-        emb.ycol0 = 64;
-        launch_linear(emb, s, &launches);
-        launch_linear(lin(ws.x, 128, w.n_w_ih, w.n_b_ih, N, 384, 128, ws.gi, 384, ACT_NONE), s, &launches);
-        LinArgs gh = lin(io->h_node_in, 128, w.n_w_hh, w.n_b_hh, N, 384, 128, ws.gh, 384, ACT_NONE);
+        run(m->emb, w.n_att_w, w.n_att_b, call(ws.cat, 512, N, ws.x, 128, ACT_RELU, 64), 64, 512);
+        run(m->gi, w.n_w_ih, w.n_b_ih, call(ws.x, 128, N, ws.gi, 384, ACT_NONE), 384, 128);
+        TcLinearCall gh = call(io->h_node_in, 128, N, ws.gh, 384, ACT_NONE);
         gh.rowscale = io->masks;
-        launch_linear(gh, s, &launches);
+        run(m->gh, w.n_w_hh, w.n_b_hh, gh, 384, 128);
         node_gru_gate_kernel<<<(unsigned)(((size_t)N * 128 + 255) / 256), 256, 0, s>>>(ws.gi, ws.gh, io->h_node_in, io->masks,
                                                                                     io->h_node_out, N);
         ++launches;
-        launch_linear(lin(io->h_node_out, 128, w.n_out_w, w.n_out_b, N, 256, 128, ws.y, 256, ACT_NONE), s, &launches);
+        run(m->out, w.n_out_w, w.n_out_b, call(io->h_node_out, 128, N, ws.y, 256, ACT_NONE), 256, 128);
     }
 
     // ---- stage 4: heads
     {
         float *feat = io->actor_features ? io->actor_features : ws.a2;
-        launch_linear(lin(ws.y, 256, w.actor0_w, w.actor0_b, N, 256, 256, ws.a1, 256, ACT_TANH), s, &launches);
-        launch_linear(lin(ws.a1, 256, w.actor2_w, w.actor2_b, N, 256, 256, feat, 256, ACT_TANH), s, &launches);
-        launch_linear(lin(ws.y, 256, w.critic0_w, w.critic0_b, N, 256, 256, ws.c1, 256, ACT_TANH), s, &launches);
-        launch_linear(lin(ws.c1, 256, w.critic2_w, w.critic2_b, N, 256, 256, ws.c2, 256, ACT_TANH), s, &launches);
-        launch_linear(lin(ws.c2, 256, w.critic_lin_w, w.critic_lin_b, N, 1, 256, io->value, 1, ACT_NONE), s, &launches);
-        launch_linear(lin(feat, 256, w.mean_w, w.mean_b, N, 2, 256, io->action_mean, 2, ACT_NONE), s, &launches);
+        if (precision == CN_PREC_FP32) {
+            run(m->ac0, w.actor0_w, w.actor0_b, call(ws.y, 256, N, ws.ac1, 512, ACT_TANH, 0), 256, 256);
+            run(m->ac0, w.critic0_w, w.critic0_b, call(ws.y, 256, N, ws.ac1, 512, ACT_TANH, 256), 256, 256);
+        } else {
+            run(m->ac0, nullptr, nullptr, call(ws.y, 256, N, ws.ac1, 512, ACT_TANH, 0), 512, 256);   // actor.0 and critic.0 in one GEMM
+        }
+        run(m->actor2, w.actor2_w, w.actor2_b, call(ws.ac1, 512, N, feat, 256, ACT_TANH), 256, 256);
+        run(m->critic2, w.critic2_w, w.critic2_b, call(ws.ac1 + 256, 512, N, ws.c2, 256, ACT_TANH), 256, 256);
+        run(m->value, w.critic_lin_w, w.critic_lin_b, call(ws.c2, 256, N, io->value, 1, ACT_NONE), 1, 256);
+        run(m->mean, w.mean_w, w.mean_b, call(feat, 256, N, io->action_mean, 2, ACT_NONE), 2, 256);
     }
+    if (run.err) return run.err;
     m->last_launches = launches;
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

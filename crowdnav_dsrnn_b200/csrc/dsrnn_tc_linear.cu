@@ -1,0 +1,275 @@
+// dsrnn_tc_linear.cu -- tall-skinny linear layers of the DS-RNN forward on tcgen05 (sm_100a):
+//     Y[m, ycol0 + n] = act( sum_k X[row(m), k] * W[n, k] + b[n] ),   M up to N_envs*H rows, K in {128,256,512}, N <= 512
+// used for the attention projections (srnn_model.py:256-339), the node RNN (:149-173) and the actor/critic
+// heads (:378-395,487-495) when the precision is bf16x3 / bf16.
+//
+// One persistent CTA per SM walks (128-row tile, n_tile column block) work items.  Both operands stream through
+// 2-slot shared-memory rings, 64 k-columns at a time:
+//   warps 0-3  read the fp32 activations (row gather + optional per-env mask), split them into bf16 hi/lo and
+//              write the 128B-swizzled K-major A image of the k-block; after the last k-block they are the
+//              epilogue (tcgen05.ld -> bias -> ReLU/tanh -> fp32 store);
+//   warp 4     cp.async.bulk's the pre-swizzled weight image of the k-block (hi | lo, n_tile rows);
+//   warp 5     owns TMEM and issues tcgen05.mma (M=128, N=n_tile, K=16), 3 passes for bf16x3.
+#include <new>
+#include "dsrnn.cuh"
+#include "dsrnn_tc_linear.cuh"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kThreads = 192;
+constexpr int kASlotBytes = 2 * kRows * 128;          // hi | lo images of one 128 x 64 k-block
+constexpr int kMaxNTile = 256;
+constexpr int kBSlotBytes = 2 * kMaxNTile * 128;      // hi | lo images of n_tile x 64 weights
+constexpr int kOffA = 0;
+constexpr int kOffB = kOffA + 2 * kASlotBytes;        //  65536
+constexpr int kOffBias = kOffB + 2 * kBSlotBytes;     // 196608
+constexpr int kOffBar = kOffBias + kMaxNTile * 4;     // 197632
+constexpr int kSmemBytes = kOffBar + 128;
+
+struct LinTcArgs {
+    const float *X; int ldx;
+    int rows_per_env, env_stride_rows, first_row;
+    const float *rowscale;
+    const __nv_bfloat16 *wimg;     // [n_blocks][k_blocks] x (hi | lo) images of n_tile x 64
+    const float *bias;             // [n_blocks * n_tile] (zero padded) or NULL
+    int M, N, K, n_tile, n_blocks, m_tiles;
+    float *Y; int ldy, ycol0;
+    int act, three_pass;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_constant__ LinTcArgs a)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = smem_u32(smem);
+    float *s_bias = reinterpret_cast<float *>(smem + kOffBias);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 96);
+    // barrier map: 0,1 a_full | 2,3 a_empty | 4,5 b_full | 6,7 b_empty | 8 tmem_full | 9 tmem_empty
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = a.K >> 6;
+    const int items = a.m_tiles * a.n_blocks;
+    const uint32_t b_bytes = (uint32_t)(a.three_pass ? 2 : 1) * a.n_tile * 128;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar(0), 128); mbar_init(bar(1), 128);
+        mbar_init(bar(2), 1); mbar_init(bar(3), 1);
+        mbar_init(bar(4), 1); mbar_init(bar(5), 1);
+        mbar_init(bar(6), 1); mbar_init(bar(7), 1);
+        mbar_init(bar(8), 1); mbar_init(bar(9), 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp < 4) {
+        // =============================================================== A staging + epilogue
+        const int tid = threadIdx.x;
+        const int sub = lane >> 4, c4 = (lane & 15) * 4;     // two rows per warp instruction, 16 lanes x float4 each
+        uint32_t it = 0, item_iter = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_iter) {
+            const int mt = item % a.m_tiles, nb = item / a.m_tiles;
+            const int row0 = mt * kRows;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                const uint32_t slot = it & 1u;
+                mbar_wait(bar(2 + slot), ((it >> 1) & 1u) ^ 1u);
+                unsigned char *dst = smem + kOffA + slot * kASlotBytes;
+#pragma unroll 1
+                for (int rb = 0; rb < 16; rb += 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        const int m = row0 + warp * 32 + (rb + b) * 2 + sub;
+                        v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (m < a.M) {
+                            const int env = m / a.rows_per_env;
+                            const size_t mem_row = (size_t)env * a.env_stride_rows + a.first_row + (m - env * a.rows_per_env);
+                            v[b] = *reinterpret_cast<const float4 *>(a.X + mem_row * a.ldx + kb * 64 + c4);
+                            if (a.rowscale) { const float sc = a.rowscale[env]; v[b].x *= sc; v[b].y *= sc; v[b].z *= sc; v[b].w *= sc; }
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        const int r = warp * 32 + (rb + b) * 2 + sub;
+                        uint2 hi, lo;
+                        split_bf16x2(v[b].x, v[b].y, hi.x, lo.x);
+                        split_bf16x2(v[b].z, v[b].w, hi.y, lo.y);
+                        const int off = sw128_offset(r, c4);
+                        *reinterpret_cast<uint2 *>(dst + off) = hi;
+                        if (a.three_pass) *reinterpret_cast<uint2 *>(dst + kRows * 128 + off) = lo;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(bar(0 + slot));
+            }
+            // ---- epilogue: thread tid owns row tid
+            if (a.bias) for (int i = tid; i < a.n_tile; i += 128) s_bias[i] = a.bias[nb * a.n_tile + i];
+            asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
+            mbar_wait(bar(8), item_iter & 1u);
+            tc_fence_after();
+            const int m = row0 + tid;
+            const bool ok = m < a.M;
+            float *yrow = a.Y + (size_t)(ok ? m : 0) * a.ldy + a.ycol0 + nb * a.n_tile;
+            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+                float acc[16];
+                tmem_ld16(t0 + c0, acc);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v = acc[j] + (a.bias ? s_bias[c0 + j] : 0.f);
+                        if (a.act == 1) v = fmaxf(v, 0.f);
+                        else if (a.act == 2) v = fast_tanh(v);
+                        acc[j] = v;
+                    }
+                    const int ncol = nb * a.n_tile + c0;
+                    if (ncol + 16 <= a.N && ((a.ldy | a.ycol0) & 3) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            reinterpret_cast<float4 *>(yrow + c0)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (ncol + j < a.N) yrow[c0 + j] = acc[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(9));
+            asm volatile("bar.sync 1, 128;" ::: "memory");        // s_bias may be rewritten by the next item
+        }
+    } else if (warp == 4) {
+        // =============================================================== weight producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int nb = item / a.m_tiles;
+                const char *img = reinterpret_cast<const char *>(a.wimg) + (size_t)nb * kblocks * 2 * a.n_tile * 128;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t slot = it & 1u;
+                    mbar_wait(bar(6 + slot), ((it >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(bar(4 + slot), b_bytes);
+                    bulk_g2s(s_base + kOffB + slot * kBSlotBytes, img + (size_t)kb * 2 * a.n_tile * 128, b_bytes, bar(4 + slot));
+                }
+            }
+        }
+    } else {
+        // =============================================================== MMA issuer
+        if (lane == 0) {
+            uint32_t it = 0, item_iter = 0;
+            const uint32_t idesc = idesc_bf16(a.n_tile);
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_iter) {
+                mbar_wait(bar(9), (item_iter & 1u) ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t slot = it & 1u;
+                    mbar_wait(bar(0 + slot), (it >> 1) & 1u);
+                    mbar_wait(bar(4 + slot), (it >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_hi = s_base + kOffA + slot * kASlotBytes, a_lo = a_hi + kRows * 128;
+                    const uint32_t b_hi = s_base + kOffB + slot * kBSlotBytes, b_lo = b_hi + a.n_tile * 128;
+                    const int passes = a.three_pass ? 3 : 1;
+                    for (int ps = 0; ps < passes; ++ps) {
+                        const uint32_t aa = ps == 1 ? a_lo : a_hi, bb = ps == 2 ? b_lo : b_hi;
+#pragma unroll
+                        for (int k16 = 0; k16 < 4; ++k16)
+                            umma_bf16(tmem_base, smem_desc_sw128(aa + k16 * 32), smem_desc_sw128(bb + k16 * 32), idesc,
+                                      (kb | ps | k16) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(bar(2 + slot));
+                    umma_commit(bar(6 + slot));
+                }
+                umma_commit(bar(8));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
+// W = [W0 (n0 rows) ; W1 (n1 rows)] (row-major [*, K]) -> per (n block, k block): hi image | lo image, zero padded
+__global__ void pack_linear_kernel(const float *W0, int n0, const float *W1, int n1, const float *b0, const float *b1,
+                                   int K, int n_tile, int n_blocks, __nv_bfloat16 *wimg, float *bias)
+{
+    const int kblocks = K >> 6;
+    const long total = (long)n_blocks * kblocks * n_tile * 64;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long t = idx;
+        const int k = (int)(t & 63); t >>= 6;
+        const int q = (int)(t % n_tile); t /= n_tile;
+        const int kb = (int)(t % kblocks); t /= kblocks;
+        const int nb = (int)t;
+        const int n = nb * n_tile + q;
+        float w = 0.f;
+        if (n < n0) w = W0[(size_t)n * K + kb * 64 + k];
+        else if (n < n0 + n1) w = W1[(size_t)(n - n0) * K + kb * 64 + k];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        char *base = reinterpret_cast<char *>(wimg) + ((size_t)nb * kblocks + kb) * 2 * n_tile * 128;
+        *reinterpret_cast<__nv_bfloat16 *>(base + sw128_offset(q, k)) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(base + (size_t)n_tile * 128 + sw128_offset(q, k)) = lo;
+    }
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_blocks * n_tile; n += gridDim.x * blockDim.x)
+        bias[n] = n < n0 ? (b0 ? b0[n] : 0.f) : (n < n0 + n1 ? (b1 ? b1[n - n0] : 0.f) : 0.f);
+}
+
+}  // namespace
+
+const char *tc_linear_create(TcLinear *L, const float *W0, const float *b0, int n0, const float *W1, const float *b1, int n1,
+                             int K, int n_tile, cudaStream_t stream)
+{
+    if (K % 64 != 0 || n_tile % 16 != 0 || n_tile < 16 || n_tile > kMaxNTile) return "tc_linear_create: unsupported shape";
+    L->N = n0 + n1; L->K = K; L->n_tile = n_tile;
+    L->n_blocks = (L->N + n_tile - 1) / n_tile;
+    const size_t bytes = (size_t)L->n_blocks * (K / 64) * 2 * n_tile * 128;
+    if (cudaMalloc(&L->wimg, bytes) != cudaSuccess || cudaMalloc(&L->bias, (size_t)L->n_blocks * n_tile * sizeof(float)) != cudaSuccess)
+        return "tc_linear_create: cudaMalloc failed";
+    pack_linear_kernel<<<128, 256, 0, stream>>>(W0, n0, W1, n1, b0, b1, K, n_tile, L->n_blocks,
+                                                reinterpret_cast<__nv_bfloat16 *>(L->wimg), L->bias);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess)
+            return "tc_linear_create: cudaFuncSetAttribute failed";
+        attr_set = true;
+    }
+    return cudaGetLastError() == cudaSuccess ? nullptr : "pack_linear_kernel launch failed";
+}
+
+void tc_linear_destroy(TcLinear *L)
+{
+    if (L->wimg) cudaFree(L->wimg);
+    if (L->bias) cudaFree(L->bias);
+    L->wimg = nullptr; L->bias = nullptr;
+}
+
+const char *tc_linear_run(const TcLinear *L, const TcLinearCall &c, int num_sms, cudaStream_t stream)
+{
+    LinTcArgs a;
+    a.X = c.X; a.ldx = c.ldx; a.rows_per_env = c.rows_per_env; a.env_stride_rows = c.env_stride_rows; a.first_row = c.first_row;
+    a.rowscale = c.rowscale;
+    a.wimg = reinterpret_cast<const __nv_bfloat16 *>(L->wimg); a.bias = L->bias;
+    a.M = c.M; a.N = L->N; a.K = L->K; a.n_tile = L->n_tile; a.n_blocks = L->n_blocks;
+    a.m_tiles = (c.M + kRows - 1) / kRows;
+    a.Y = c.Y; a.ldy = c.ldy; a.ycol0 = c.ycol0; a.act = c.act; a.three_pass = c.three_pass;
+    const int items = a.m_tiles * a.n_blocks;
+    linear_tc_kernel<<<items < num_sms ? items : num_sms, kThreads, kSmemBytes + 1024, stream>>>(a);
+    const cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
