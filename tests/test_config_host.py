@@ -1,0 +1,118 @@
+"""CPU: host-side logic -- Config restatement, step tables, CnConfig flattening, lazy infos, Policy container."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from crowdnav_dsrnn_b200 import Config, _lib, abi
+from crowdnav_dsrnn_b200.envs import LazyInfos
+from crowdnav_dsrnn_b200.info import Collision, Danger, Nothing, ReachGoal, Timeout
+from crowdnav_dsrnn_b200.model import Policy
+from crowdnav_dsrnn_b200.spaces import crowd_spaces
+from helpers import GOLDEN, config_from_overrides
+from oracle import dsrnn_oracle, ref_import
+
+
+def test_config_defaults_and_derived_values():
+    c = Config()
+    assert (c.sim.human_num, c.sim.circle_radius, c.env.time_step, c.env.time_limit, c.env.test_size) == (5, 6, 0.25, 50, 500)
+    assert c.reward.discomfort_penalty_factor == 10 * 0.25 and c.reward.collision_penalty == -20
+    assert c.humans.random_goal_changing and c.humans.end_goal_changing and not c.robot.visible
+    s = Config(social_metrics=True)
+    assert (s.sim.circle_radius, s.env.test_size, s.test.side_preference) == (4, 2000, False)
+    p = Config(test_sim=["side_pref_passing"])
+    assert p.test.side_preference and p.sim.human_num == 1 and p.env.test_size == 200 and not p.humans.end_goal_changing
+
+
+def test_step_tables_replay_float64_accumulation():
+    t, words = abi.step_tables(0.25, 50)
+    assert t == 196                                           # Timeout is returned by the 197th step
+    steps = [s for s in range(300) if (words[s >> 5] >> (s & 31)) & 1]
+    assert steps == [20, 40, 60, 80, 100, 120, 140, 160, 180]
+    t, words = abi.step_tables(0.1, 50)
+    assert t == 490 and not any(words)                        # dt = 0.1: `global_time % 5 == 0` never fires
+
+
+def test_flatten_config_rejects_out_of_scope_flags():
+    c = Config()
+    c.humans.policy = "social_force"
+    with pytest.raises(NotImplementedError):
+        abi.flatten_config(c, 4)
+    c = Config()
+    c.sim.train_val_sim = "circle_crossing"
+    with pytest.raises(TypeError):                            # crowd_sim.py:138-142
+        abi.flatten_config(c, 4)
+    c = Config(human_num=33)
+    with pytest.raises(ValueError):
+        abi.flatten_config(c, 4)
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree only exists in the build container")
+def test_flatten_config_equals_reference_config():
+    import json
+    import glob
+    import os
+    from oracle import ref_harness
+
+    for path in glob.glob(os.path.join(GOLDEN, "step_*.npz")):
+        over = json.loads(str(np.load(path)["overrides"]))
+        mine = abi.flatten_config(config_from_overrides(over), 32, phase="train")
+        ref = abi.flatten_config(ref_harness.make_reference_config(**over), 32, phase="train")
+        assert bytes(mine) == bytes(ref), path
+    assert bytes(abi.flatten_config(Config(), 1)) == bytes(abi.flatten_config(ref_harness.make_reference_config(), 1))
+
+
+class _FakeBuf:
+    def __init__(self):
+        n = 3
+        self.event = torch.tensor([abi.EV_NOTHING, abi.EV_DANGER, abi.EV_COLLISION], dtype=torch.int32)
+        self.scenario = torch.tensor([0, 2, 3], dtype=torch.int32)
+        self.info = torch.zeros(n, abi.INFO_DIM)
+        self.info[1, abi.INFO_COLUMNS["dmin"]] = 0.125
+        self.info[:, abi.INFO_COLUMNS["aggregate_nav_time"]] = torch.tensor([6.0, 5.0, 4.0])
+        self.done = torch.tensor([0, 0, 1], dtype=torch.uint8)
+        self.episode_return = torch.tensor([0.0, 0.0, -17.5])
+        self.episode_length = torch.tensor([0, 0, 42], dtype=torch.int32)
+
+
+def test_lazy_infos_reference_shape():
+    infos = LazyInfos(_FakeBuf(), side_preference=False, t0=0.0)
+    assert len(infos) == 3
+    a, b, c = list(infos)
+    assert isinstance(a["info"]["event"], Nothing) and "episode" not in a
+    assert isinstance(b["info"]["event"], Danger) and b["info"]["event"].min_dist == pytest.approx(0.125)
+    assert b["info"]["scenario"] == "parallel_traffic" and b["info"]["aggregate_nav_time"] == 5
+    assert isinstance(c["info"]["event"], Collision) and c["episode"]["r"] == -17.5 and c["episode"]["l"] == 42
+    assert str(Timeout()) == "Timeout" and str(ReachGoal()) == "Reaching goal"
+    assert "bad_transition" not in c
+
+
+def test_policy_state_dict_is_checkpoint_compatible_and_cpu_act_fails_loudly():
+    obs, act = crowd_spaces(5)
+    p = Policy(obs.spaces, act, base="srnn", base_kwargs=Config())
+    w = np.load(GOLDEN + "/weights_holonomic_27776.npz")
+    assert sorted(p.state_dict().keys()) == sorted(w.files) and len(w.files) == 45
+    p.load_state_dict({k: torch.from_numpy(w[k]) for k in w.files})
+    assert sum(v.numel() for v in p.parameters()) == 973983
+    inputs = {"robot_node": torch.zeros(2, 1, 7), "temporal_edges": torch.zeros(2, 1, 2), "spatial_edges": torch.zeros(2, 5, 2)}
+    hx = {"human_node_rnn": torch.zeros(2, 1, 128), "human_human_edge_rnn": torch.zeros(2, 6, 256)}
+    with pytest.raises(_lib.CrowdNavLibraryError):
+        p.act(inputs, hx, torch.ones(2, 1))
+
+
+def test_evaluate_actions_matches_reference_forward_on_cpu():
+    """The differentiable training path restates the same math: T=1 chunk vs the golden reference outputs."""
+    d = np.load(GOLDEN + "/dsrnn_holonomic_27776_h5.npz")
+    w = np.load(GOLDEN + "/weights_holonomic_27776.npz")
+    obs, act = crowd_spaces(5)
+    p = Policy(obs.spaces, act, base="srnn", base_kwargs=Config())
+    p.load_state_dict({k: torch.from_numpy(w[k]) for k in w.files})
+    t = lambda k: torch.from_numpy(d[k])
+    inputs = {"robot_node": t("robot_node"), "temporal_edges": t("temporal_edges"), "spatial_edges": t("spatial_edges")}
+    hx = {"human_node_rnn": t("h_node"), "human_human_edge_rnn": t("h_edge")}
+    value, logp, ent, hx2 = p.evaluate_actions(inputs, hx, t("masks"), t("ref_action_mean"))
+    assert (value - t("ref_value")).abs().max() < 1e-4
+    assert (logp - t("ref_log_prob")).abs().max() < 1e-4
+    assert (hx2["human_human_edge_rnn"] - t("ref_h_edge")).abs().max() < 1e-5
+    assert value.requires_grad and math.isfinite(float(ent))
