@@ -4,11 +4,11 @@
 // N temporal + N*H spatial edge rows) are one tall GEMM per weight set:
 //     [e | m*h]  (rows x 320)   x   [W_ih | W_hh]^T  (320 x 768)      e = ReLU(W_enc x + b)  (K = 2, computed in place)
 // followed by the gate non-linearities.  One persistent CTA per SM walks 128-row tiles:
-//   warps 0-3  stage the tile's A operand straight from the fp32 hidden state in HBM (masking, fp32 -> split bf16
+//   warps 0-7  stage the tile's A operand straight from the fp32 hidden state in HBM (masking, fp32 -> split bf16
 //              hi/lo, 128B-swizzled K-major smem image), then act as the epilogue: tcgen05.ld the accumulators of a
 //              64-hidden-unit column tile (n_i | r | z | n_h, 256 TMEM columns), apply sigmoid/tanh/blend and store h'.
-//   warp 4     streams the pre-swizzled bf16 weight images (24 KB chunks) with cp.async.bulk into a 2-slot smem ring.
-//   warp 5     owns TMEM (512 columns = 2 accumulator buffers) and issues tcgen05.mma.kind::f16 (M=128, N=192, K=16).
+//   warp 8     streams the pre-swizzled bf16 weight images (24 KB chunks) with cp.async.bulk into a 2-slot smem ring.
+//   warp 9     owns TMEM (512 columns = 2 accumulator buffers) and issues tcgen05.mma.kind::f16 (M=128, N=192, K=16).
 // Precision: CN_PREC_BF16X3 runs A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (fp32 accumulate in TMEM, ~2^-16 relative operand
 // error); CN_PREC_BF16 runs the first pass only.
 #include <new>
@@ -23,7 +23,7 @@ constexpr int kColTiles = 4;               // 64 hidden units per column tile
 constexpr int kABlockBytes = kRows * 128;  // 128 rows x 64 bf16
 constexpr int kBChunkRows = 192;
 constexpr int kBChunkBytes = kBChunkRows * 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;              // 8 staging/epilogue warps + weight producer + MMA issuer
 
 constexpr int kOffAHi = 0;
 constexpr int kOffALo = kOffAHi + kKBlocks * kABlockBytes;        //  81920
@@ -125,12 +125,12 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
     if (threadIdx.x == 0) {
         mbar_init(bar(0), 1); mbar_init(bar(1), 1);
         mbar_init(bar(2), 1); mbar_init(bar(3), 1);
-        mbar_init(bar(4), 128);
+        mbar_init(bar(4), 256);
         mbar_init(bar(5), 1); mbar_init(bar(6), 1);
-        mbar_init(bar(7), 128); mbar_init(bar(8), 128);
+        mbar_init(bar(7), 256); mbar_init(bar(8), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -139,9 +139,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =============================================================== staging + epilogue warps
-        const int tid = threadIdx.x;          // 0..127 = row of the tile in the epilogue
+        const int tid = (warp & 3) * 32 + lane;   // row of the tile (TMEM lane) this thread owns in the epilogue
+        const int chalf = warp >> 2;              // warps 0-3: hidden units 0..31 of a column tile, warps 4-7: 32..63
         uint32_t ctg = 0;                     // column tiles consumed so far (selects the TMEM buffer / parity)
         for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
             const bool spatial = tile < a.tiles_spatial;
@@ -149,16 +150,16 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
             const int row0 = (spatial ? tile : tile - a.tiles_spatial) * kRows;
             const int M = spatial ? a.N * H : a.N;
             const float *enc = s_enc + p * 192;
-            // ---- stage A: warp w converts rows w*32 .. w*32+31, 8 rows per batch so 16 x 16 B loads per lane are in
+            // ---- stage A: warp w converts rows w*16 .. w*16+15, 8 rows per batch so 16 x 16 B loads per lane are in
             //      flight before the first conversion (a warp reads one 1 KB row with two float4 loads per lane)
 #pragma unroll 1
-            for (int rb = 0; rb < 32; rb += 8) {
+            for (int rb = 0; rb < 16; rb += 8) {
                 float4 hv[8][2];
                 float xs[8][2], mks[8];
                 bool oks[8];
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const int m = row0 + warp * 32 + rb + b;
+                    const int m = row0 + warp * 16 + rb + b;
                     oks[b] = m < M;
                     hv[b][0] = hv[b][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     xs[b][0] = xs[b][1] = mks[b] = 0.f;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                 }
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const int r = warp * 32 + rb + b;
+                    const int r = warp * 16 + rb + b;
                     {   // encoded input block (k-block 0): lane owns k = 2*lane, 2*lane+1
                         float e[2];
 #pragma unroll
@@ -229,15 +230,16 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
             for (int ct = 0; ct < kColTiles; ++ct, ++ctg) {
                 const uint32_t buf = ctg & 1u;
                 // h_prev of this row's 64 hidden units (just staged, so L2-resident) is fetched BEFORE the accumulator wait
-                float4 hprev4[16];
-                const float4 *hp = reinterpret_cast<const float4 *>(a.h_in + mem_row * 256 + ct * 64);
+                float4 hprev4[8];
+                const float4 *hp = reinterpret_cast<const float4 *>(a.h_in + mem_row * 256 + ct * 64 + chalf * 32);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) hprev4[q] = ok ? hp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 8; ++q) hprev4[q] = ok ? hp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                 mbar_wait(bar(5 + buf), (ctg >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256u;
+                const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256u;
 #pragma unroll
-                for (int c16 = 0; c16 < 4; ++c16) {
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c16 = chalf * 2 + cc;
                     float ni[16], rg[16], zg[16], nh[16];
                     tmem_ld16(t0 + 0 * 64 + c16 * 16, ni);
                     tmem_ld16(t0 + 1 * 64 + c16 * 16, rg);
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                         float4 *ho = reinterpret_cast<float4 *>(a.h_out + mem_row * 256 + c0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 h4 = hprev4[c16 * 4 + q];
+                            const float4 h4 = hprev4[cc * 4 + q];
                             const float hprev[4] = {h4.x * mk, h4.y * mk, h4.z * mk, h4.w * mk};
                             float o[4];
 #pragma unroll
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                 mbar_arrive(bar(7 + buf));
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // =============================================================== weight producer (one lane)
         if (lane == 0) {
             uint32_t chunk = 0;
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }

@@ -5,11 +5,11 @@
 //
 // One persistent CTA per SM walks (128-row tile, n_tile column block) work items.  Both operands stream through
 // 2-slot shared-memory rings, 64 k-columns at a time:
-//   warps 0-3  read the fp32 activations (row gather + optional per-env mask), split them into bf16 hi/lo and
+//   warps 0-7  read the fp32 activations (row gather + optional per-env mask), split them into bf16 hi/lo and
 //              write the 128B-swizzled K-major A image of the k-block; after the last k-block they are the
 //              epilogue (tcgen05.ld -> bias -> ReLU/tanh -> fp32 store);
-//   warp 4     cp.async.bulk's the pre-swizzled weight image of the k-block (hi | lo, n_tile rows);
-//   warp 5     owns TMEM and issues tcgen05.mma (M=128, N=n_tile, K=16), 3 passes for bf16x3.
+//   warp 8     cp.async.bulk's the pre-swizzled weight image of the k-block (hi | lo, n_tile rows);
+//   warp 9     owns TMEM and issues tcgen05.mma (M=128, N=n_tile, K=16), 3 passes for bf16x3.
 #include <new>
 #include "dsrnn.cuh"
 #include "dsrnn_tc_linear.cuh"
@@ -20,7 +20,7 @@ using namespace tc;
 namespace {
 
 constexpr int kRows = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;              // 8 staging/epilogue warps + weight producer + MMA issuer
 constexpr int kASlotBytes = 2 * kRows * 128;          // hi | lo images of one 128 x 64 k-block
 constexpr int kMaxNTile = 256;
 constexpr int kBSlotBytes = 2 * kMaxNTile * 128;      // hi | lo images of n_tile x 64 weights
@@ -58,14 +58,14 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
     const uint32_t b_bytes = (uint32_t)(a.three_pass ? 2 : 1) * a.n_tile * 128;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar(0), 128); mbar_init(bar(1), 128);
+        mbar_init(bar(0), 256); mbar_init(bar(1), 256);
         mbar_init(bar(2), 1); mbar_init(bar(3), 1);
         mbar_init(bar(4), 1); mbar_init(bar(5), 1);
         mbar_init(bar(6), 1); mbar_init(bar(7), 1);
-        mbar_init(bar(8), 1); mbar_init(bar(9), 128);
+        mbar_init(bar(8), 1); mbar_init(bar(9), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -74,9 +74,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =============================================================== A staging + epilogue
-        const int tid = threadIdx.x;
+        const int tid = (warp & 3) * 32 + lane;      // row of the tile (TMEM lane) owned in the epilogue
+        const int chalf = warp >> 2;                 // warps 0-3 take the even 16-column chunks, warps 4-7 the odd ones
         const int sub = lane >> 4, c4 = (lane & 15) * 4;     // two rows per warp instruction, 16 lanes x float4 each
         uint32_t it = 0, item_iter = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_iter) {
@@ -86,12 +87,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
                 const uint32_t slot = it & 1u;
                 mbar_wait(bar(2 + slot), ((it >> 1) & 1u) ^ 1u);
                 unsigned char *dst = smem + kOffA + slot * kASlotBytes;
-#pragma unroll 1
-                for (int rb = 0; rb < 16; rb += 8) {
+                {
+                    constexpr int rb = 0;
                     float4 v[8];
 #pragma unroll
                     for (int b = 0; b < 8; ++b) {
-                        const int m = row0 + warp * 32 + (rb + b) * 2 + sub;
+                        const int m = row0 + warp * 16 + (rb + b) * 2 + sub;
                         v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (m < a.M) {
                             const int env = m / a.rows_per_env;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
                     }
 #pragma unroll
                     for (int b = 0; b < 8; ++b) {
-                        const int r = warp * 32 + (rb + b) * 2 + sub;
+                        const int r = warp * 16 + (rb + b) * 2 + sub;
                         uint2 hi, lo;
                         split_bf16x2(v[b].x, v[b].y, hi.x, lo.x);
                         split_bf16x2(v[b].z, v[b].w, hi.y, lo.y);
@@ -115,15 +116,15 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
                 mbar_arrive(bar(0 + slot));
             }
             // ---- epilogue: thread tid owns row tid
-            if (a.bias) for (int i = tid; i < a.n_tile; i += 128) s_bias[i] = a.bias[nb * a.n_tile + i];
-            asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
+            if (a.bias) for (int i = threadIdx.x; i < a.n_tile; i += 256) s_bias[i] = a.bias[nb * a.n_tile + i];
+            asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 epilogue warps only
             mbar_wait(bar(8), item_iter & 1u);
             tc_fence_after();
             const int m = row0 + tid;
             const bool ok = m < a.M;
             float *yrow = a.Y + (size_t)(ok ? m : 0) * a.ldy + a.ycol0 + nb * a.n_tile;
-            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16);
-            for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+            const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            for (int c0 = chalf * 16; c0 < a.n_tile; c0 += 32) {
                 float acc[16];
                 tmem_ld16(t0 + c0, acc);
                 tmem_ld_wait();
@@ -148,9 +149,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
             }
             tc_fence_before();
             mbar_arrive(bar(9));
-            asm volatile("bar.sync 1, 128;" ::: "memory");        // s_bias may be rewritten by the next item
+            asm volatile("bar.sync 1, 256;" ::: "memory");        // s_bias may be rewritten by the next item
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // =============================================================== weight producer
         if (lane == 0) {
             uint32_t it = 0;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
     }
