@@ -21,14 +21,16 @@ constexpr int kRows = 128;                 // UMMA M
 constexpr int kKBlocks = 5;                // 64-wide k-blocks: 1 encoded-input block + 4 hidden blocks
 constexpr int kColTiles = 4;               // 64 hidden units per column tile
 constexpr int kABlockBytes = kRows * 128;  // 128 rows x 64 bf16
-constexpr int kBChunkRows = 192;
+constexpr int kBChunkRows = 192;                 // weight rows per (column tile, k-block, part): [n_i|r|z] or [r|z|n_h] x 64
 constexpr int kBChunkBytes = kBChunkRows * 128;
+constexpr int kBSlots = 2;
+constexpr int kBarAReady = 2 * kBSlots, kBarTmemFull = kBarAReady + 1, kBarTmemEmpty = kBarTmemFull + 2;
 constexpr int kThreads = 320;              // 8 staging/epilogue warps + weight producer + MMA issuer
 
 constexpr int kOffAHi = 0;
 constexpr int kOffALo = kOffAHi + kKBlocks * kABlockBytes;        //  81920
 constexpr int kOffB = kOffALo + kKBlocks * kABlockBytes;          // 163840
-constexpr int kOffBias = kOffB + 2 * kBChunkBytes;                // 212992  float[2][4][256]
+constexpr int kOffBias = kOffB + kBSlots * kBChunkBytes;                // 212992  float[2][4][256]
 constexpr int kOffEnc = kOffBias + 2 * 4 * 256 * 4;               // 221184  float[2][192]: w0[64] w1[64] b[64]
 constexpr int kOffBar = kOffEnc + 2 * 192 * 4;                    // 222720  mbarriers
 constexpr int kSmemBytes = kOffBar + 128;                         // 222848 (+1024 alignment slack at launch)
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
     float *s_bias = reinterpret_cast<float *>(smem + kOffBias);
     float *s_enc = reinterpret_cast<float *>(smem + kOffEnc);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 96);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 112);   // 13 mbarriers occupy the first 104 bytes
     // barrier map: 0,1 full_b | 2,3 empty_b | 4 a_ready | 5,6 tmem_full | 7,8 tmem_empty
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -123,11 +125,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
     for (int i = threadIdx.x; i < 2 * 4 * 256; i += kThreads) s_bias[i] = a.bias4[i];
     for (int i = threadIdx.x; i < 2 * 192; i += kThreads) s_enc[i] = a.enc[i];
     if (threadIdx.x == 0) {
-        mbar_init(bar(0), 1); mbar_init(bar(1), 1);
-        mbar_init(bar(2), 1); mbar_init(bar(3), 1);
-        mbar_init(bar(4), 256);
-        mbar_init(bar(5), 1); mbar_init(bar(6), 1);
-        mbar_init(bar(7), 256); mbar_init(bar(8), 256);
+        for (int i = 0; i < 2 * kBSlots; ++i) mbar_init(bar(i), 1);
+        mbar_init(bar(kBarAReady), 256);
+        mbar_init(bar(kBarTmemFull), 1); mbar_init(bar(kBarTmemFull + 1), 1);
+        mbar_init(bar(kBarTmemEmpty), 256); mbar_init(bar(kBarTmemEmpty + 1), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
@@ -143,15 +144,35 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
         // =============================================================== staging + epilogue warps
         const int tid = (warp & 3) * 32 + lane;   // row of the tile (TMEM lane) this thread owns in the epilogue
         const int chalf = warp >> 2;              // warps 0-3: hidden units 0..31 of a column tile, warps 4-7: 32..63
-        uint32_t ctg = 0;                     // column tiles consumed so far (selects the TMEM buffer / parity)
-        for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
-            const bool spatial = tile < a.tiles_spatial;
-            const int p = spatial ? 0 : 1;
-            const int row0 = (spatial ? tile : tile - a.tiles_spatial) * kRows;
-            const int M = spatial ? a.N * H : a.N;
-            const float *enc = s_enc + p * 192;
-            // ---- stage A: warp w converts rows w*16 .. w*16+15, 8 rows per batch so 16 x 16 B loads per lane are in
-            //      flight before the first conversion (a warp reads one 1 KB row with two float4 loads per lane)
+        uint32_t ctg = 0;                         // column tiles consumed so far (selects the TMEM buffer / parity)
+
+        struct TileInfo { bool spatial; int p, row0, M; };
+        auto tile_info = [&](int tile) {
+            TileInfo t;
+            t.spatial = tile < a.tiles_spatial;
+            t.p = t.spatial ? 0 : 1;
+            t.row0 = (t.spatial ? tile : tile - a.tiles_spatial) * kRows;
+            t.M = t.spatial ? a.N * H : a.N;
+            return t;
+        };
+        auto mem_row_of = [&](const TileInfo &t, int m, int &env) {
+            env = t.spatial ? m / H : m;
+            return t.spatial ? (size_t)env * stride + 1 + (m - env * H) : (size_t)env * stride;
+        };
+        // pull the NEXT tile's hidden-state rows into L2 while this tile is being computed (128 rows x 8 lines / 256 threads)
+        auto prefetch_tile = [&](const TileInfo &t) {
+            const int r = threadIdx.x >> 1, m = t.row0 + r;
+            if (m < t.M) {
+                int env;
+                const float *row = a.h_in + mem_row_of(t, m, env) * 256 + (threadIdx.x & 1) * 128;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + l * 32));
+            }
+        };
+        // stage A: warp w converts rows w*16 .. w*16+15, 8 rows per batch so 16 x 16 B loads per lane are in flight
+        // before the first conversion (a warp reads one 1 KB row with two float4 loads per lane)
+        auto stage_tile = [&](const TileInfo &t) {
+            const float *enc = s_enc + t.p * 192;
 #pragma unroll 1
             for (int rb = 0; rb < 16; rb += 8) {
                 float4 hv[8][2];
@@ -159,18 +180,17 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                 bool oks[8];
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const int m = row0 + warp * 16 + rb + b;
-                    oks[b] = m < M;
+                    const int m = t.row0 + warp * 16 + rb + b;
+                    oks[b] = m < t.M;
                     hv[b][0] = hv[b][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     xs[b][0] = xs[b][1] = mks[b] = 0.f;
                     if (oks[b]) {
-                        const int env = spatial ? m / H : m;
-                        const size_t mem_row = spatial ? (size_t)env * stride + 1 + (m - env * H) : (size_t)env * stride;
-                        const float *hrow = a.h_in + mem_row * 256 + lane * 4;
+                        int env;
+                        const float *hrow = a.h_in + mem_row_of(t, m, env) * 256 + lane * 4;
                         hv[b][0] = *reinterpret_cast<const float4 *>(hrow);
                         hv[b][1] = *reinterpret_cast<const float4 *>(hrow + 128);
                         mks[b] = a.masks[env];
-                        const float *x = spatial ? a.spatial_edges + 2 * (size_t)m : a.temporal_edges + 2 * (size_t)m;
+                        const float *x = t.spatial ? a.spatial_edges + 2 * (size_t)m : a.temporal_edges + 2 * (size_t)m;
                         xs[b][0] = x[0]; xs[b][1] = x[1];
                     }
                 }
@@ -184,13 +204,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                             const int k = 2 * lane + i;
                             e[i] = oks[b] ? fmaxf(fmaf(enc[64 + k], xs[b][1], enc[k] * xs[b][0]) + enc[128 + k], 0.f) : 0.f;
                         }
-                        const __nv_bfloat162 hi = __floats2bfloat162_rn(e[0], e[1]);
+                        uint32_t hi, lo;
+                        split_bf16x2(e[0], e[1], hi, lo);
                         const int off = sw128_offset(r, 2 * lane);
-                        *reinterpret_cast<__nv_bfloat162 *>(smem + kOffAHi + off) = hi;
-                        if (a.three_pass) {
-                            const __nv_bfloat162 lo = __floats2bfloat162_rn(e[0] - __low2float(hi), e[1] - __high2float(hi));
-                            *reinterpret_cast<__nv_bfloat162 *>(smem + kOffALo + off) = lo;
-                        }
+                        *reinterpret_cast<uint32_t *>(smem + kOffAHi + off) = hi;
+                        if (a.three_pass) *reinterpret_cast<uint32_t *>(smem + kOffALo + off) = lo;
                     }
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {   // hidden blocks: elements half*128 + lane*4 .. +3
@@ -198,44 +216,45 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                         float4 h4 = hv[b][half];
                         const float mk = mks[b];
                         h4.x *= mk; h4.y *= mk; h4.z *= mk; h4.w *= mk;
-                        const int kb = 1 + (e0 >> 6);
-                        const int off = kb * kABlockBytes + sw128_offset(r, e0 & 63);
-                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(h4.x, h4.y), h23 = __floats2bfloat162_rn(h4.z, h4.w);
-                        uint2 pk;
-                        pk.x = *reinterpret_cast<const uint32_t *>(&h01); pk.y = *reinterpret_cast<const uint32_t *>(&h23);
-                        *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = pk;
-                        if (a.three_pass) {
-                            const __nv_bfloat162 l01 = __floats2bfloat162_rn(h4.x - __low2float(h01), h4.y - __high2float(h01));
-                            const __nv_bfloat162 l23 = __floats2bfloat162_rn(h4.z - __low2float(h23), h4.w - __high2float(h23));
-                            pk.x = *reinterpret_cast<const uint32_t *>(&l01); pk.y = *reinterpret_cast<const uint32_t *>(&l23);
-                            *reinterpret_cast<uint2 *>(smem + kOffALo + off) = pk;
-                        }
+                        const int off = (1 + (e0 >> 6)) * kABlockBytes + sw128_offset(r, e0 & 63);
+                        uint2 hi, lo;
+                        split_bf16x2(h4.x, h4.y, hi.x, lo.x);
+                        split_bf16x2(h4.z, h4.w, hi.y, lo.y);
+                        *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = hi;
+                        if (a.three_pass) *reinterpret_cast<uint2 *>(smem + kOffALo + off) = lo;
                     }
                 }
             }
             fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-            mbar_arrive(bar(4));
+            mbar_arrive(bar(kBarAReady));
+        };
 
+        int tile = blockIdx.x;
+        if (tile < a.tiles_total) stage_tile(tile_info(tile));
+        for (; tile < a.tiles_total; tile += gridDim.x) {
+            const TileInfo t = tile_info(tile);
+            const int next = tile + gridDim.x;
+            const bool has_next = next < a.tiles_total;
+            if (has_next) prefetch_tile(tile_info(next));
             // ---- epilogue: thread tid owns row tid of the tile (TMEM lane tid)
-            const int m = row0 + tid;
-            const bool ok = m < M;
+            const int m = t.row0 + tid;
+            const bool ok = m < t.M;
             size_t mem_row = 0;
             float mk = 0.f;
-            if (ok) {
-                const int env = spatial ? m / H : m;
-                mem_row = spatial ? (size_t)env * stride + 1 + (m - env * H) : (size_t)env * stride;
-                mk = a.masks[env];
-            }
-            const float *bias = s_bias + p * 4 * 256;
+            if (ok) { int env; mem_row = mem_row_of(t, m, env); mk = a.masks[env]; }
+            const float *bias = s_bias + t.p * 4 * 256;
             for (int ct = 0; ct < kColTiles; ++ct, ++ctg) {
                 const uint32_t buf = ctg & 1u;
-                // h_prev of this row's 64 hidden units (just staged, so L2-resident) is fetched BEFORE the accumulator wait
+                // h_prev of this row's 32 hidden units (just staged, so L2-resident) is fetched BEFORE the accumulator wait
                 float4 hprev4[8];
                 const float4 *hp = reinterpret_cast<const float4 *>(a.h_in + mem_row * 256 + ct * 64 + chalf * 32);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) hprev4[q] = ok ? hp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                mbar_wait(bar(5 + buf), (ctg >> 1) & 1u);
+                mbar_wait(bar(kBarTmemFull + buf), (ctg >> 1) & 1u);
                 tc_fence_after();
+                // the last column tile's accumulators are complete => every MMA that reads A has retired: restage A for
+                // the next tile FIRST so its MMAs overlap this epilogue (the other TMEM buffer is already free)
+                if (ct == kColTiles - 1 && has_next) stage_tile(tile_info(next));
                 const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256u;
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -267,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(bar(7 + buf));
+                mbar_arrive(bar(kBarTmemEmpty + buf));
             }
         }
     } else if (warp == 8) {
@@ -281,11 +300,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                 for (int ct = 0; ct < kColTiles; ++ct)
                     for (int kb = 0; kb < kKBlocks; ++kb)
                         for (int part = 0; part < parts; ++part, ++chunk) {
-                            const uint32_t slot = chunk & 1u;
-                            mbar_wait(bar(2 + slot), ((chunk >> 1) & 1u) ^ 1u);
-                            mbar_expect_tx(bar(0 + slot), kBChunkBytes);
+                            const uint32_t slot = chunk % kBSlots;
+                            mbar_wait(bar(kBSlots + slot), ((chunk / kBSlots) & 1u) ^ 1u);
+                            mbar_expect_tx(bar(slot), kBChunkBytes);
                             bulk_g2s(s_base + kOffB + slot * kBChunkBytes,
-                                     img + ((size_t)(ct * kKBlocks + kb) * 2 + part) * kBChunkBytes, kBChunkBytes, bar(0 + slot));
+                                     img + ((size_t)(ct * kKBlocks + kb) * 2 + part) * kBChunkBytes, kBChunkBytes, bar(slot));
                         }
             }
         }
@@ -294,55 +313,46 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
         if (lane == 0) {
             uint32_t chunk = 0, ctg = 0, tile_iter = 0;
             constexpr uint32_t id192 = idesc_bf16(192), id128 = idesc_bf16(128), id64 = idesc_bf16(64);
+            // shared-memory descriptors: the high word is constant, the low word is (address >> 4) | LBO; stepping K by 16
+            // elements (32 B) or to another k-block / ring slot only adds to the low word, so one MMA costs a few instructions
+            constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            auto make_desc = [](uint32_t lo) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi)); return d; };
+            const uint32_t a_hi_desc_lo = ((s_base + kOffAHi) >> 4) | (1u << 16), a_lo_desc_lo = ((s_base + kOffALo) >> 4) | (1u << 16);
+            const uint32_t b_desc_lo = ((s_base + kOffB) >> 4) | (1u << 16);
             for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++tile_iter) {
-                mbar_wait(bar(4), tile_iter & 1u);
+                mbar_wait(bar(kBarAReady), tile_iter & 1u);
                 tc_fence_after();
                 for (int ct = 0; ct < kColTiles; ++ct, ++ctg) {
                     const uint32_t buf = ctg & 1u;
-                    mbar_wait(bar(7 + buf), ((ctg >> 1) & 1u) ^ 1u);
+                    mbar_wait(bar(kBarTmemEmpty + buf), ((ctg >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d0 = tmem_base + buf * 256u;
                     for (int kb = 0; kb < kKBlocks; ++kb) {
                         const uint32_t dcol = d0 + (kb == 0 ? 0u : 64u);
-                        // ---- chunk B_hi: passes A_hi*B_hi and (3-pass) A_lo*B_hi
-                        {
-                            const uint32_t slot = chunk & 1u;
-                            mbar_wait(bar(0 + slot), (chunk >> 1) & 1u);
+                        const int parts = a.three_pass ? 2 : 1;
+                        for (int part = 0; part < parts; ++part, ++chunk) {   // part 0: B_hi (passes A_hi, A_lo), part 1: B_lo (pass A_hi)
+                            const uint32_t slot = chunk % kBSlots;
+                            mbar_wait(bar(slot), (chunk / kBSlots) & 1u);
                             tc_fence_after();
-                            const uint32_t b_addr = s_base + kOffB + slot * kBChunkBytes;
-                            const int passes = a.three_pass ? 2 : 1;
+                            const uint32_t b_lo = b_desc_lo + slot * (kBChunkBytes >> 4);
+                            const int passes = (part == 0 && a.three_pass) ? 2 : 1;
                             for (int ps = 0; ps < passes; ++ps) {
-                                const uint32_t a_addr = s_base + (ps == 0 ? kOffAHi : kOffALo) + kb * kABlockBytes;
+                                const uint32_t a_lo = (ps == 0 ? a_hi_desc_lo : a_lo_desc_lo) + kb * (kABlockBytes >> 4);
 #pragma unroll
                                 for (int k16 = 0; k16 < 4; ++k16) {
-                                    const uint64_t ad = smem_desc_sw128(a_addr + k16 * 32);
-                                    const uint64_t bd = smem_desc_sw128(b_addr + k16 * 32);
-                                    const bool first = ps == 0 && k16 == 0;
-                                    if (first && kb == 0) umma_bf16(dcol, ad, bd, id192, 0u);          // overwrite n_i | r | z
-                                    else if (first && kb == 1) {                                        // r | z accumulate, n_h starts
+                                    const uint64_t ad = make_desc(a_lo + 2 * k16), bd = make_desc(b_lo + 2 * k16);
+                                    const bool first = part == 0 && ps == 0 && k16 == 0;
+                                    if (first && kb == 0) umma_bf16(dcol, ad, bd, id192, 0u);           // overwrite n_i | r | z
+                                    else if (first && kb == 1) {                                         // r | z accumulate, n_h starts
                                         umma_bf16(dcol, ad, bd, id128, 1u);
-                                        umma_bf16(dcol + 128u, ad, smem_desc_sw128(b_addr + 128 * 128 + k16 * 32), id64, 0u);
+                                        umma_bf16(dcol + 128u, ad, make_desc(b_lo + ((128 * 128) >> 4) + 2 * k16), id64, 0u);
                                     } else umma_bf16(dcol, ad, bd, id192, 1u);
                                 }
                             }
-                            umma_commit(bar(2 + slot));
-                            ++chunk;
-                        }
-                        // ---- chunk B_lo: pass A_hi*B_lo
-                        if (a.three_pass) {
-                            const uint32_t slot = chunk & 1u;
-                            mbar_wait(bar(0 + slot), (chunk >> 1) & 1u);
-                            tc_fence_after();
-                            const uint32_t b_addr = s_base + kOffB + slot * kBChunkBytes;
-                            const uint32_t a_addr = s_base + kOffAHi + kb * kABlockBytes;
-#pragma unroll
-                            for (int k16 = 0; k16 < 4; ++k16)
-                                umma_bf16(dcol, smem_desc_sw128(a_addr + k16 * 32), smem_desc_sw128(b_addr + k16 * 32), id192, 1u);
-                            umma_commit(bar(2 + slot));
-                            ++chunk;
+                            umma_commit(bar(kBSlots + slot));
                         }
                     }
-                    umma_commit(bar(5 + buf));       // accumulators of this column tile are complete
+                    umma_commit(bar(kBarTmemFull + buf));       // accumulators of this column tile are complete
                 }
             }
         }

@@ -26,7 +26,7 @@ struct CnDsrnn {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;   // events around the edge stage
     int num_sms;
     // tensor-core images of the stage 2-4 linears (dsrnn_tc_linear.cu)
-    TcLinear att_qt, emb, gi, gh, out, ac0, actor2, critic2, value, mean;
+    TcLinear att_qt, emb, gi, gh, out, ac0, actor2, critic2;
     float *att_wc = nullptr, *att_bc = nullptr;   // folded attention projection (W_s^T W_t, W_s^T b_t)
 };
 
@@ -254,7 +254,8 @@ __global__ void fold_attention_kernel(const float *__restrict__ wt, const float 
     }
 }
 
-// one warp per env: scores against qt, softmax over the H humans, weighted sum; writes cat = [o_t | c]  (N x 512)
+// one warp per env: ONE pass over the env's H edge outputs (each row is read from HBM once): score against qt,
+// online softmax (running max / sum, rescaled accumulator), weighted sum; writes cat = [o_t | c]  (N x 512)
 __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict__ h_edge, const float *__restrict__ qt,
                                                         float *__restrict__ cat, int N, int H)
 {
@@ -264,37 +265,64 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
     const float4 qa = *reinterpret_cast<const float4 *>(qt + (size_t)e * 256 + lane * 8);
     const float4 qb = *reinterpret_cast<const float4 *>(qt + (size_t)e * 256 + lane * 8 + 4);
     const float *ot = h_edge + (size_t)e * (H + 1) * 256;
-    float my_score = -INFINITY;
+    const float temp = (float)H / 8.0f;                       // num_edges / sqrt(attention_size)
+    float run_max = -INFINITY, run_sum = 0.0f;
+    float c[8] = {};
+    float4 n0 = *reinterpret_cast<const float4 *>(ot + 256 + lane * 8), n1 = *reinterpret_cast<const float4 *>(ot + 256 + lane * 8 + 4);
     for (int i = 0; i < H; ++i) {
-        const float *os = ot + (size_t)(1 + i) * 256 + lane * 8;
-        const float4 v0 = *reinterpret_cast<const float4 *>(os), v1 = *reinterpret_cast<const float4 *>(os + 4);
+        const float4 v0 = n0, v1 = n1;
+        if (i + 1 < H) {                                      // software prefetch of the next row
+            const float *os = ot + (size_t)(2 + i) * 256 + lane * 8;
+            n0 = *reinterpret_cast<const float4 *>(os); n1 = *reinterpret_cast<const float4 *>(os + 4);
+        }
         float s = qa.x * v0.x + qa.y * v0.y + qa.z * v0.z + qa.w * v0.w + qb.x * v1.x + qb.y * v1.y + qb.z * v1.z + qb.w * v1.w;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == i) my_score = s * ((float)H / 8.0f);      // temperature = num_edges / sqrt(attention_size)
+        s *= temp;
+        const float new_max = fmaxf(run_max, s);
+        const float scale = expf(run_max - new_max);          // 0 on the first row (run_max = -inf)
+        const float p = expf(s - new_max);
+        run_sum = run_sum * scale + p;
+        c[0] = fmaf(p, v0.x, c[0] * scale); c[1] = fmaf(p, v0.y, c[1] * scale); c[2] = fmaf(p, v0.z, c[2] * scale); c[3] = fmaf(p, v0.w, c[3] * scale);
+        c[4] = fmaf(p, v1.x, c[4] * scale); c[5] = fmaf(p, v1.y, c[5] * scale); c[6] = fmaf(p, v1.z, c[6] * scale); c[7] = fmaf(p, v1.w, c[7] * scale);
+        run_max = new_max;
     }
-    float mx = my_score;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float ex = lane < H ? expf(my_score - mx) : 0.0f;
-    float sum = ex;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float alpha = ex / sum;
-    float c[8] = {};
-    for (int i = 0; i < H; ++i) {
-        const float ai = __shfl_sync(0xffffffffu, alpha, i);
-        const float *os = ot + (size_t)(1 + i) * 256;
-        const float4 v0 = *reinterpret_cast<const float4 *>(os + lane * 8);
-        const float4 v1 = *reinterpret_cast<const float4 *>(os + lane * 8 + 4);
-        c[0] = fmaf(ai, v0.x, c[0]); c[1] = fmaf(ai, v0.y, c[1]); c[2] = fmaf(ai, v0.z, c[2]); c[3] = fmaf(ai, v0.w, c[3]);
-        c[4] = fmaf(ai, v1.x, c[4]); c[5] = fmaf(ai, v1.y, c[5]); c[6] = fmaf(ai, v1.z, c[6]); c[7] = fmaf(ai, v1.w, c[7]);
-    }
+    const float inv = 1.0f / run_sum;
     float *dst = cat + (size_t)e * 512;
     *reinterpret_cast<float4 *>(dst + lane * 8) = *reinterpret_cast<const float4 *>(ot + lane * 8);
     *reinterpret_cast<float4 *>(dst + lane * 8 + 4) = *reinterpret_cast<const float4 *>(ot + lane * 8 + 4);
-    *reinterpret_cast<float4 *>(dst + 256 + lane * 8) = make_float4(c[0], c[1], c[2], c[3]);
-    *reinterpret_cast<float4 *>(dst + 256 + lane * 8 + 4) = make_float4(c[4], c[5], c[6], c[7]);
+    *reinterpret_cast<float4 *>(dst + 256 + lane * 8) = make_float4(c[0] * inv, c[1] * inv, c[2] * inv, c[3] * inv);
+    *reinterpret_cast<float4 *>(dst + 256 + lane * 8 + 4) = make_float4(c[4] * inv, c[5] * inv, c[6] * inv, c[7] * inv);
+}
+
+// critic_linear (256 -> 1) and dist.fc_mean (256 -> 2): one warp per env, three dot products
+__global__ void __launch_bounds__(128) heads_kernel(const float *__restrict__ c2, const float *__restrict__ feat,
+                                                    const float *__restrict__ wv, const float *__restrict__ bv,
+                                                    const float *__restrict__ wm, const float *__restrict__ bm,
+                                                    float *__restrict__ value, float *__restrict__ mean, int N)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 4 + warp;
+    if (e >= N) return;
+    float v = 0.f, m0 = 0.f, m1 = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int k = half * 128 + lane * 4;
+        const float4 c = *reinterpret_cast<const float4 *>(c2 + (size_t)e * 256 + k);
+        const float4 f = *reinterpret_cast<const float4 *>(feat + (size_t)e * 256 + k);
+        const float4 a = *reinterpret_cast<const float4 *>(wv + k);
+        const float4 b0 = *reinterpret_cast<const float4 *>(wm + k), b1 = *reinterpret_cast<const float4 *>(wm + 256 + k);
+        v += c.x * a.x + c.y * a.y + c.z * a.z + c.w * a.w;
+        m0 += f.x * b0.x + f.y * b0.y + f.z * b0.z + f.w * b0.w;
+        m1 += f.x * b1.x + f.y * b1.y + f.z * b1.z + f.w * b1.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+        m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+    }
+    if (lane == 0) { value[e] = v + bv[0]; mean[2 * (size_t)e] = m0 + bm[0]; mean[2 * (size_t)e + 1] = m1 + bm[1]; }
 }
 
 // ---------------------------------------------------------------------------------------------- stage 3 helpers
@@ -366,7 +394,7 @@ size_t dsrnn_workspace_bytes(int n_envs, int human_num) { return carve_ws(nullpt
 
 static void destroy_tc_linears(CnDsrnn *m)
 {
-    TcLinear *all[] = {&m->att_qt, &m->emb, &m->gi, &m->gh, &m->out, &m->ac0, &m->actor2, &m->critic2, &m->value, &m->mean};
+    TcLinear *all[] = {&m->att_qt, &m->emb, &m->gi, &m->gh, &m->out, &m->ac0, &m->actor2, &m->critic2};
     for (TcLinear *L : all) tc_linear_destroy(L);
     if (m->att_wc) cudaFree(m->att_wc);
     if (m->att_bc) cudaFree(m->att_bc);
@@ -389,8 +417,6 @@ static const char *create_tc_linears(CnDsrnn *m, cudaStream_t s)
     CN_TCL(ac0, w.actor0_w, w.actor0_b, 256, w.critic0_w, w.critic0_b, 256, 256, 256);
     CN_TCL(actor2, w.actor2_w, w.actor2_b, 256, nullptr, nullptr, 0, 256, 256);
     CN_TCL(critic2, w.critic2_w, w.critic2_b, 256, nullptr, nullptr, 0, 256, 256);
-    CN_TCL(value, w.critic_lin_w, w.critic_lin_b, 1, nullptr, nullptr, 0, 256, 16);
-    CN_TCL(mean, w.mean_w, w.mean_b, 2, nullptr, nullptr, 0, 256, 16);
 #undef CN_TCL
     return nullptr;
 }
@@ -531,8 +557,9 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
         }
         run(m->actor2, w.actor2_w, w.actor2_b, call(ws.ac1, 512, N, feat, 256, ACT_TANH), 256, 256);
         run(m->critic2, w.critic2_w, w.critic2_b, call(ws.ac1 + 256, 512, N, ws.c2, 256, ACT_TANH), 256, 256);
-        run(m->value, w.critic_lin_w, w.critic_lin_b, call(ws.c2, 256, N, io->value, 1, ACT_NONE), 1, 256);
-        run(m->mean, w.mean_w, w.mean_b, call(feat, 256, N, io->action_mean, 2, ACT_NONE), 2, 256);
+        if (run.err) return run.err;
+        heads_kernel<<<(N + 3) / 4, 128, 0, s>>>(ws.c2, feat, w.critic_lin_w, w.critic_lin_b, w.mean_w, w.mean_b, io->value, io->action_mean, N);
+        ++launches;
     }
     if (run.err) return run.err;
     m->last_launches = launches;

@@ -171,6 +171,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
         if (lane == 0) {
             uint32_t it = 0, item_iter = 0;
             const uint32_t idesc = idesc_bf16(a.n_tile);
+            // descriptor high word is constant; K steps / slots / hi-lo images only add to the low word (address >> 4 | LBO)
+            constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            auto make_desc = [](uint32_t lo) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi)); return d; };
+            const uint32_t desc_lo0 = (s_base >> 4) | (1u << 16);
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_iter) {
                 mbar_wait(bar(9), (item_iter & 1u) ^ 1u);
                 tc_fence_after();
@@ -179,15 +183,14 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
                     mbar_wait(bar(0 + slot), (it >> 1) & 1u);
                     mbar_wait(bar(4 + slot), (it >> 1) & 1u);
                     tc_fence_after();
-                    const uint32_t a_hi = s_base + kOffA + slot * kASlotBytes, a_lo = a_hi + kRows * 128;
-                    const uint32_t b_hi = s_base + kOffB + slot * kBSlotBytes, b_lo = b_hi + a.n_tile * 128;
+                    const uint32_t a_hi = desc_lo0 + ((kOffA + slot * kASlotBytes) >> 4), a_lo = a_hi + ((kRows * 128) >> 4);
+                    const uint32_t b_hi = desc_lo0 + ((kOffB + slot * kBSlotBytes) >> 4), b_lo = b_hi + ((a.n_tile * 128) >> 4);
                     const int passes = a.three_pass ? 3 : 1;
                     for (int ps = 0; ps < passes; ++ps) {
                         const uint32_t aa = ps == 1 ? a_lo : a_hi, bb = ps == 2 ? b_lo : b_hi;
 #pragma unroll
                         for (int k16 = 0; k16 < 4; ++k16)
-                            umma_bf16(tmem_base, smem_desc_sw128(aa + k16 * 32), smem_desc_sw128(bb + k16 * 32), idesc,
-                                      (kb | ps | k16) != 0 ? 1u : 0u);
+                            umma_bf16(tmem_base, make_desc(aa + 2 * k16), make_desc(bb + 2 * k16), idesc, (kb | ps | k16) != 0 ? 1u : 0u);
                     }
                     umma_commit(bar(2 + slot));
                     umma_commit(bar(6 + slot));
