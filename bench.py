@@ -313,7 +313,7 @@ def run_ours(args, wl):
         "metric": "env_steps_per_sec_incl_dsrnn_forward", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (3-pass split bf16, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (3-pass split bf16, fp32 accumulate)", "bf16": "bf16", "fp16": "fp16 (fp32 accumulate)"}[args.precision],
         "data": "synthetic scenarios (device reset, counter-based RNG); weights of the shipped checkpoint %s" % wl["weights"],
         "config": {"workload": wl["label"], "human_num": H, "envs_per_gpu": N, "global_envs": N * world,
                    "parallelism": "env-sharded x%d, no data-path collective" % world, "precision": args.precision,
@@ -336,7 +336,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16", "fp16"])
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--prime", type=int, default=150, help="untimed steps before warm-up so episodes are de-phased")
     ap.add_argument("--e2e-steps", type=int, default=50)

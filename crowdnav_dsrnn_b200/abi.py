@@ -27,8 +27,8 @@ INFO_COLUMNS = {
     "dmin": 0, "aggregate_nav_time": 1, "path_violation": 2, "personal_violation": 3, "jerk_cost": 4,
     "dist_to_goal": 5, "speed_violation": 6, "side_left": 7, "side_right": 8, "separation": 9,
 }
-PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_FP16 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp16": PREC_FP16}
 
 
 class CnConfig(C.Structure):

@@ -254,7 +254,7 @@ extern "C" int cn_dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnD
     if (!io->robot_node || !io->temporal_edges || !io->spatial_edges || !io->h_node_in || !io->h_edge_in || !io->masks ||
         !io->h_node_out || !io->h_edge_out || !io->value || !io->action_mean)
         return fail(CN_ERR_ARG, "CnDsrnnIO has a NULL required member");
-    if (precision != CN_PREC_FP32 && precision != CN_PREC_BF16X3 && precision != CN_PREC_BF16)
+    if (precision < CN_PREC_FP32 || precision > CN_PREC_FP16)
         return fail(CN_ERR_ARG, "unknown precision %d", precision);
     const size_t need = dsrnn_workspace_bytes(n_envs, human_num);
     if (!workspace_dev || workspace_bytes < need) return fail(CN_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, need);

@@ -36,7 +36,7 @@ constexpr int kOffBar = kOffEnc + 2 * 192 * 4;                    // 222720  mba
 constexpr int kSmemBytes = kOffBar + 128;                         // 222848 (+1024 alignment slack at launch)
 
 struct TcState {
-    __nv_bfloat16 *wimg;   // [2 problems][4 ct][5 kb][2 parts] x 24 KB swizzled images
+    __nv_bfloat16 *wimg;   // [2 problems][4 ct][5 kb][3 parts: bf16 hi | bf16 lo | fp16] x 24 KB swizzled images
     float *bias4;          // [2][4][256]: b_in | b_ir+b_hr | b_iz+b_hz | b_hn
     float *enc;            // [2][192]
     int num_sms;
@@ -73,10 +73,11 @@ __global__ void pack_edge_weights_kernel(const PackArgs a)
         }
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-        const size_t chunk = ((size_t)(p * kColTiles + ct) * kKBlocks + kb) * 2;
+        const size_t chunk = ((size_t)(p * kColTiles + ct) * kKBlocks + kb) * 3;
         char *base = reinterpret_cast<char *>(a.wimg);
         *reinterpret_cast<__nv_bfloat16 *>(base + (chunk + 0) * kBChunkBytes + sw128_offset(q, k)) = hi;
         *reinterpret_cast<__nv_bfloat16 *>(base + (chunk + 1) * kBChunkBytes + sw128_offset(q, k)) = lo;
+        *reinterpret_cast<__half *>(base + (chunk + 2) * kBChunkBytes + sw128_offset(q, k)) = __float2half_rn(w);
     }
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * 256; idx += gridDim.x * blockDim.x) {
         const int p = idx >> 8, c = idx & 255;
@@ -104,6 +105,7 @@ struct EdgeTcArgs {
     int N, H;
     int tiles_spatial, tiles_total;
     int three_pass;
+    int fp16;          // single pass with FP16 operands (images part 2) instead of BF16
 };
 
 __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a)
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                             e[i] = oks[b] ? fmaxf(fmaf(enc[64 + k], xs[b][1], enc[k] * xs[b][0]) + enc[128 + k], 0.f) : 0.f;
                         }
                         uint32_t hi, lo;
-                        split_bf16x2(e[0], e[1], hi, lo);
+                        if (a.fp16) { hi = pack_half2(e[0], e[1]); lo = 0u; } else split_bf16x2(e[0], e[1], hi, lo);
                         const int off = sw128_offset(r, 2 * lane);
                         *reinterpret_cast<uint32_t *>(smem + kOffAHi + off) = hi;
                         if (a.three_pass) *reinterpret_cast<uint32_t *>(smem + kOffALo + off) = lo;
@@ -218,8 +220,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                         h4.x *= mk; h4.y *= mk; h4.z *= mk; h4.w *= mk;
                         const int off = (1 + (e0 >> 6)) * kABlockBytes + sw128_offset(r, e0 & 63);
                         uint2 hi, lo;
-                        split_bf16x2(h4.x, h4.y, hi.x, lo.x);
-                        split_bf16x2(h4.z, h4.w, hi.y, lo.y);
+                        if (a.fp16) { hi.x = pack_half2(h4.x, h4.y); hi.y = pack_half2(h4.z, h4.w); lo.x = lo.y = 0u; }
+                        else { split_bf16x2(h4.x, h4.y, hi.x, lo.x); split_bf16x2(h4.z, h4.w, hi.y, lo.y); }
                         *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = hi;
                         if (a.three_pass) *reinterpret_cast<uint2 *>(smem + kOffALo + off) = lo;
                     }
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
             const int parts = a.three_pass ? 2 : 1;
             for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
                 const int p = tile < a.tiles_spatial ? 0 : 1;
-                const char *img = reinterpret_cast<const char *>(a.wimg) + (size_t)p * kColTiles * kKBlocks * 2 * kBChunkBytes;
+                const char *img = reinterpret_cast<const char *>(a.wimg) + (size_t)p * kColTiles * kKBlocks * 3 * kBChunkBytes;
                 for (int ct = 0; ct < kColTiles; ++ct)
                     for (int kb = 0; kb < kKBlocks; ++kb)
                         for (int part = 0; part < parts; ++part, ++chunk) {
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                             mbar_wait(bar(kBSlots + slot), ((chunk / kBSlots) & 1u) ^ 1u);
                             mbar_expect_tx(bar(slot), kBChunkBytes);
                             bulk_g2s(s_base + kOffB + slot * kBChunkBytes,
-                                     img + ((size_t)(ct * kKBlocks + kb) * 2 + part) * kBChunkBytes, kBChunkBytes, bar(slot));
+                                     img + ((size_t)(ct * kKBlocks + kb) * 3 + (a.fp16 ? 2 : part)) * kBChunkBytes, kBChunkBytes, bar(slot));
                         }
             }
         }
@@ -312,7 +314,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
         // =============================================================== MMA issuer (one lane)
         if (lane == 0) {
             uint32_t chunk = 0, ctg = 0, tile_iter = 0;
-            constexpr uint32_t id192 = idesc_bf16(192), id128 = idesc_bf16(128), id64 = idesc_bf16(64);
+            const uint32_t id192 = a.fp16 ? idesc_f16(192) : idesc_bf16(192), id128 = a.fp16 ? idesc_f16(128) : idesc_bf16(128),
+                           id64 = a.fp16 ? idesc_f16(64) : idesc_bf16(64);
             // shared-memory descriptors: the high word is constant, the low word is (address >> 4) | LBO; stepping K by 16
             // elements (32 B) or to another k-block / ring slot only adds to the low word, so one MMA costs a few instructions
             constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
@@ -376,7 +379,7 @@ const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void *
     *state = nullptr;
     TcState *st = new (std::nothrow) TcState();
     if (!st) return "out of host memory";
-    const size_t img_bytes = (size_t)2 * kColTiles * kKBlocks * 2 * kBChunkBytes;
+    const size_t img_bytes = (size_t)2 * kColTiles * kKBlocks * 3 * kBChunkBytes;
     if (cudaMalloc(&st->wimg, img_bytes) != cudaSuccess || cudaMalloc(&st->bias4, 2 * 4 * 256 * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&st->enc, 2 * 192 * sizeof(float)) != cudaSuccess) {
         delete st;
@@ -421,6 +424,7 @@ const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *, int n_env
     a.tiles_spatial = (int)(((size_t)n_envs * H + kRows - 1) / kRows);
     a.tiles_total = a.tiles_spatial + (n_envs + kRows - 1) / kRows;
     a.three_pass = precision == CN_PREC_BF16X3 ? 1 : 0;
+    a.fp16 = precision == CN_PREC_FP16 ? 1 : 0;
     const int grid = a.tiles_total < st->num_sms ? a.tiles_total : st->num_sms;
     edge_gru_tc_kernel<<<grid, kThreads, kSmemBytes + 1024, stream>>>(a);
     ++*launches;

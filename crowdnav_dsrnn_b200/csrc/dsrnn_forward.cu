@@ -472,6 +472,7 @@ struct LinearRun {
             launch_linear(a, s, launches);
         } else {
             c.three_pass = precision == CN_PREC_BF16X3 ? 1 : 0;
+            c.fp16 = precision == CN_PREC_FP16 ? 1 : 0;
             err = tc_linear_run(&tcl, c, m->num_sms, s);
             ++*launches;
         }

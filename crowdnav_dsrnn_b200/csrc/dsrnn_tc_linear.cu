@@ -38,7 +38,7 @@ struct LinTcArgs {
     const float *bias;             // [n_blocks * n_tile] (zero padded) or NULL
     int M, N, K, n_tile, n_blocks, m_tiles;
     float *Y; int ldy, ycol0;
-    int act, three_pass;
+    int act, three_pass, fp16;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_constant__ LinTcArgs a)
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
     const int kblocks = a.K >> 6;
     const int items = a.m_tiles * a.n_blocks;
     const uint32_t b_bytes = (uint32_t)(a.three_pass ? 2 : 1) * a.n_tile * 128;
+    const size_t img_kb_bytes = (size_t)3 * a.n_tile * 128;      // per (n block, k block): bf16 hi | bf16 lo | fp16 images
 
     if (threadIdx.x == 0) {
         mbar_init(bar(0), 256); mbar_init(bar(1), 256);
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
                     for (int b = 0; b < 8; ++b) {
                         const int r = warp * 16 + (rb + b) * 2 + sub;
                         uint2 hi, lo;
-                        split_bf16x2(v[b].x, v[b].y, hi.x, lo.x);
-                        split_bf16x2(v[b].z, v[b].w, hi.y, lo.y);
+                        if (a.fp16) { hi.x = pack_half2(v[b].x, v[b].y); hi.y = pack_half2(v[b].z, v[b].w); lo.x = lo.y = 0u; }
+                        else { split_bf16x2(v[b].x, v[b].y, hi.x, lo.x); split_bf16x2(v[b].z, v[b].w, hi.y, lo.y); }
                         const int off = sw128_offset(r, c4);
                         *reinterpret_cast<uint2 *>(dst + off) = hi;
                         if (a.three_pass) *reinterpret_cast<uint2 *>(dst + kRows * 128 + off) = lo;
@@ -157,12 +158,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
             uint32_t it = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 const int nb = item / a.m_tiles;
-                const char *img = reinterpret_cast<const char *>(a.wimg) + (size_t)nb * kblocks * 2 * a.n_tile * 128;
+                const char *img = reinterpret_cast<const char *>(a.wimg) + (size_t)nb * kblocks * img_kb_bytes + (a.fp16 ? (size_t)2 * a.n_tile * 128 : 0);
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const uint32_t slot = it & 1u;
                     mbar_wait(bar(6 + slot), ((it >> 1) & 1u) ^ 1u);
                     mbar_expect_tx(bar(4 + slot), b_bytes);
-                    bulk_g2s(s_base + kOffB + slot * kBSlotBytes, img + (size_t)kb * 2 * a.n_tile * 128, b_bytes, bar(4 + slot));
+                    bulk_g2s(s_base + kOffB + slot * kBSlotBytes, img + (size_t)kb * img_kb_bytes, b_bytes, bar(4 + slot));
                 }
             }
         }
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
         // =============================================================== MMA issuer
         if (lane == 0) {
             uint32_t it = 0, item_iter = 0;
-            const uint32_t idesc = idesc_bf16(a.n_tile);
+            const uint32_t idesc = a.fp16 ? idesc_f16(a.n_tile) : idesc_bf16(a.n_tile);
             // descriptor high word is constant; K steps / slots / hi-lo images only add to the low word (address >> 4 | LBO)
             constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
             auto make_desc = [](uint32_t lo) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi)); return d; };
@@ -226,9 +227,10 @@ __global__ void pack_linear_kernel(const float *W0, int n0, const float *W1, int
         else if (n < n0 + n1) w = W1[(size_t)(n - n0) * K + kb * 64 + k];
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-        char *base = reinterpret_cast<char *>(wimg) + ((size_t)nb * kblocks + kb) * 2 * n_tile * 128;
+        char *base = reinterpret_cast<char *>(wimg) + ((size_t)nb * kblocks + kb) * 3 * n_tile * 128;
         *reinterpret_cast<__nv_bfloat16 *>(base + sw128_offset(q, k)) = hi;
         *reinterpret_cast<__nv_bfloat16 *>(base + (size_t)n_tile * 128 + sw128_offset(q, k)) = lo;
+        *reinterpret_cast<__half *>(base + (size_t)2 * n_tile * 128 + sw128_offset(q, k)) = __float2half_rn(w);
     }
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_blocks * n_tile; n += gridDim.x * blockDim.x)
         bias[n] = n < n0 ? (b0 ? b0[n] : 0.f) : (n < n0 + n1 ? (b1 ? b1[n - n0] : 0.f) : 0.f);
@@ -242,7 +244,7 @@ const char *tc_linear_create(TcLinear *L, const float *W0, const float *b0, int 
     if (K % 64 != 0 || n_tile % 16 != 0 || n_tile < 16 || n_tile > kMaxNTile) return "tc_linear_create: unsupported shape";
     L->N = n0 + n1; L->K = K; L->n_tile = n_tile;
     L->n_blocks = (L->N + n_tile - 1) / n_tile;
-    const size_t bytes = (size_t)L->n_blocks * (K / 64) * 2 * n_tile * 128;
+    const size_t bytes = (size_t)L->n_blocks * (K / 64) * 3 * n_tile * 128;
     if (cudaMalloc(&L->wimg, bytes) != cudaSuccess || cudaMalloc(&L->bias, (size_t)L->n_blocks * n_tile * sizeof(float)) != cudaSuccess)
         return "tc_linear_create: cudaMalloc failed";
     pack_linear_kernel<<<128, 256, 0, stream>>>(W0, n0, W1, n1, b0, b1, K, n_tile, L->n_blocks,
@@ -271,7 +273,7 @@ const char *tc_linear_run(const TcLinear *L, const TcLinearCall &c, int num_sms,
     a.wimg = reinterpret_cast<const __nv_bfloat16 *>(L->wimg); a.bias = L->bias;
     a.M = c.M; a.N = L->N; a.K = L->K; a.n_tile = L->n_tile; a.n_blocks = L->n_blocks;
     a.m_tiles = (c.M + kRows - 1) / kRows;
-    a.Y = c.Y; a.ldy = c.ldy; a.ycol0 = c.ycol0; a.act = c.act; a.three_pass = c.three_pass;
+    a.Y = c.Y; a.ldy = c.ldy; a.ycol0 = c.ycol0; a.act = c.act; a.three_pass = c.fp16 ? 0 : c.three_pass; a.fp16 = c.fp16;
     const int items = a.m_tiles * a.n_blocks;
     linear_tc_kernel<<<items < num_sms ? items : num_sms, kThreads, kSmemBytes + 1024, stream>>>(a);
     const cudaError_t err = cudaGetLastError();

@@ -16,6 +16,7 @@ struct TcLinearCall {
     float *Y; int ldy; int ycol0 = 0;
     int act = 0;                                                // 0 none, 1 ReLU, 2 tanh
     int three_pass = 1;
+    int fp16 = 0;                                               // single pass with FP16 operands
 };
 
 // W = [W0 (n0 rows); W1 (n1 rows, may be NULL/0)], row-major [*, K]; each returns NULL or an error string

@@ -2,6 +2,7 @@
 // tcgen05.mma / commit / ld, shared-memory matrix descriptors, split-bf16 helpers.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace tc {
@@ -68,6 +69,14 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, BF16 x BF16, both K-major, M=128
 __host__ __device__ constexpr uint32_t idesc_bf16(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+// same with both operands FP16 (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+__device__ __forceinline__ uint32_t pack_half2(float x, float y)
+{
+    const __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
 
 // byte offset of element (row, k) inside a [rows x 64] bf16 block in the canonical K-major SW128 layout
 __host__ __device__ __forceinline__ int sw128_offset(int row, int k)

@@ -179,12 +179,13 @@ class Policy(nn.Module):
         return lib
 
     def __del__(self):
-        if getattr(self, "_handle", None) is not None:
-            try:
-                _lib.load().cn_dsrnn_destroy(self._handle)
-            except Exception:
-                pass
-            self._handle = None
+        try:  # best effort: at interpreter shutdown torch / ctypes may already be torn down
+            handle = self.__dict__.get("_handle")
+            if handle is not None:
+                self.__dict__["_handle"] = None
+                _lib.load().cn_dsrnn_destroy(handle)
+        except Exception:  # noqa: BLE001
+            pass
 
     def cuda_forward(self, inputs, rnn_hxs, masks, need_features=True):
         """One rollout-step forward on the GPU. Returns (value[N,1], mean[N,2], features[N,256]|None, h_node, h_edge)."""

@@ -210,7 +210,8 @@ typedef struct CnDsrnnIO {
 typedef struct CnDsrnn CnDsrnn;
 
 /* precision of the tensor-core contractions */
-enum { CN_PREC_FP32 = 0, CN_PREC_BF16X3 = 1, CN_PREC_BF16 = 2 };
+/* FP32: CUDA cores, exact.  BF16X3: 3-pass split bf16 (operands ~2^-17).  BF16 / FP16: one tensor-core pass. */
+enum { CN_PREC_FP32 = 0, CN_PREC_BF16X3 = 1, CN_PREC_BF16 = 2, CN_PREC_FP16 = 3 };
 
 int cn_dsrnn_create(const CnDsrnnWeights *w, int device, void *stream, CnDsrnn **out);
 int cn_dsrnn_destroy(CnDsrnn *m);
