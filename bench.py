@@ -37,6 +37,11 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from ONE `ncu --set full` capture of the bench loop at the
+# default sizes (profiles/r1_ncu_full_loop_summary.txt); only valid for that workload / batch, else null
+NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 357.97e6 + 307.29e6, "crowd_step_kernel": 17.12e6 + 3.69e6}}
+
+
 def step_bytes(H):          # algorithmic HBM bytes of the step kernel per env-step
     return 96 * H + 188
 
@@ -288,6 +293,10 @@ def run_ours(args, wl):
                  "unit": "GB/s", "kernel": "crowd_step_kernel", "ms_per_launch": step_avg_ms, "traffic": None,
                  "algorithmic_bytes_per_env_step": step_bytes(H), "share_of_step": step_avg_ms / (ms / args.steps)}
     roof_step["frac"] = roof_step["achieved"] / roof_step["peak"]
+    roof_step["note"] = ("ORCA is O(H^2) branchy fp32: at H=20 the kernel is instruction-issue bound (ncu sm__throughput 70 %, "
+                         "dram 0.4 %), see profiles/README.md")
+    traffic = NCU_TRAFFIC_BYTES.get((args.workload, N), {})
+    roof_step["traffic"] = traffic.get("crowd_step_kernel")
     edge_kernel = "edge_gru_simt_kernel" if args.precision == "fp32" else "edge_gru_tc_kernel"
     passes = 3 if args.precision == "bf16x3" else 1
     roof_edge = {"bound": "tensor", "achieved": N * edge_stage_flops(H) / (edge_avg_ms * 1e-3) / 1e12,
@@ -295,6 +304,7 @@ def run_ours(args, wl):
                  "ms_per_launch": edge_avg_ms, "traffic": None, "algorithmic_flops_per_env_step": edge_stage_flops(H),
                  "tensor_passes": passes, "share_of_step": edge_avg_ms / (ms / args.steps)}
     roof_edge["frac"] = roof_edge["achieved"] / roof_edge["peak"]
+    roof_edge["traffic"] = traffic.get(edge_kernel)
     dominant = roof_edge if edge_avg_ms >= step_avg_ms else roof_step
     other = roof_step if dominant is roof_edge else roof_edge
 
