@@ -78,79 +78,98 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
     if (warp < 8) {
         // =============================================================== A staging + epilogue
         const int tid = (warp & 3) * 32 + lane;      // row of the tile (TMEM lane) owned in the epilogue
-        const int chalf = warp >> 2;                 // warps 0-3 take the even 16-column chunks, warps 4-7 the odd ones
+        const int chalf = warp >> 2;                 // warps 0-3 take the even 32-column blocks, warps 4-7 the odd ones
         const int sub = lane >> 4, c4 = (lane & 15) * 4;     // two rows per warp instruction, 16 lanes x float4 each
         uint32_t it = 0, item_iter = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_iter) {
             const int mt = item % a.m_tiles, nb = item / a.m_tiles;
             const int row0 = mt * kRows;
+            // row pointers / masks of the 8 rows this lane stages are fixed for the item
+            const float *rowp[8];
+            float rsc[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const int m = row0 + warp * 16 + b * 2 + sub;
+                rowp[b] = nullptr; rsc[b] = 1.f;
+                if (m < a.M) {
+                    const int env = m / a.rows_per_env;
+                    rowp[b] = a.X + ((size_t)env * a.env_stride_rows + a.first_row + (m - env * a.rows_per_env)) * a.ldx + c4;
+                    if (a.rowscale) rsc[b] = a.rowscale[env];
+                }
+            }
+            float4 cur[8], nxt[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) cur[b] = rowp[b] ? *reinterpret_cast<const float4 *>(rowp[b]) : make_float4(0.f, 0.f, 0.f, 0.f);
             for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                if (kb + 1 < kblocks) {      // the next k-block's loads are in flight while this one is converted
+#pragma unroll
+                    for (int b = 0; b < 8; ++b)
+                        nxt[b] = rowp[b] ? *reinterpret_cast<const float4 *>(rowp[b] + (kb + 1) * 64) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 const uint32_t slot = it & 1u;
                 mbar_wait(bar(2 + slot), ((it >> 1) & 1u) ^ 1u);
                 unsigned char *dst = smem + kOffA + slot * kASlotBytes;
-                {
-                    constexpr int rb = 0;
-                    float4 v[8];
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) {
-                        const int m = row0 + warp * 16 + (rb + b) * 2 + sub;
-                        v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (m < a.M) {
-                            const int env = m / a.rows_per_env;
-                            const size_t mem_row = (size_t)env * a.env_stride_rows + a.first_row + (m - env * a.rows_per_env);
-                            v[b] = *reinterpret_cast<const float4 *>(a.X + mem_row * a.ldx + kb * 64 + c4);
-                            if (a.rowscale) { const float sc = a.rowscale[env]; v[b].x *= sc; v[b].y *= sc; v[b].z *= sc; v[b].w *= sc; }
-                        }
-                    }
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) {
-                        const int r = warp * 16 + (rb + b) * 2 + sub;
-                        uint2 hi, lo;
-                        if (a.fp16) { hi.x = pack_half2(v[b].x, v[b].y); hi.y = pack_half2(v[b].z, v[b].w); lo.x = lo.y = 0u; }
-                        else { split_bf16x2(v[b].x, v[b].y, hi.x, lo.x); split_bf16x2(v[b].z, v[b].w, hi.y, lo.y); }
-                        const int off = sw128_offset(r, c4);
-                        *reinterpret_cast<uint2 *>(dst + off) = hi;
-                        if (a.three_pass) *reinterpret_cast<uint2 *>(dst + kRows * 128 + off) = lo;
-                    }
+                for (int b = 0; b < 8; ++b) {
+                    const int r = warp * 16 + b * 2 + sub;
+                    const float sc = rsc[b];
+                    uint2 hi, lo;
+                    if (a.fp16) { hi.x = pack_half2(cur[b].x * sc, cur[b].y * sc); hi.y = pack_half2(cur[b].z * sc, cur[b].w * sc); lo.x = lo.y = 0u; }
+                    else { split_bf16x2(cur[b].x * sc, cur[b].y * sc, hi.x, lo.x); split_bf16x2(cur[b].z * sc, cur[b].w * sc, hi.y, lo.y); }
+                    const int off = sw128_offset(r, c4);
+                    *reinterpret_cast<uint2 *>(dst + off) = hi;
+                    if (a.three_pass) *reinterpret_cast<uint2 *>(dst + kRows * 128 + off) = lo;
                 }
                 fence_proxy_async();
                 mbar_arrive(bar(0 + slot));
+#pragma unroll
+                for (int b = 0; b < 8; ++b) cur[b] = nxt[b];
             }
-            // ---- epilogue: thread tid owns row tid
+            // ---- epilogue.  tcgen05.ld gives one row per lane; the tile is transposed through shared memory (the A ring is
+            //      idle once the accumulators are complete) so every global store instruction writes whole 128-byte lines.
             if (a.bias) for (int i = threadIdx.x; i < a.n_tile; i += 256) s_bias[i] = a.bias[nb * a.n_tile + i];
             asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 epilogue warps only
             mbar_wait(bar(8), item_iter & 1u);
             tc_fence_after();
-            const int m = row0 + tid;
-            const bool ok = m < a.M;
-            float *yrow = a.Y + (size_t)(ok ? m : 0) * a.ldy + a.ycol0 + nb * a.n_tile;
+            float *scratch = reinterpret_cast<float *>(smem + kOffA) + warp * (32 * 33);   // 32 rows x 32 cols, row stride 33
             const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-            for (int c0 = chalf * 16; c0 < a.n_tile; c0 += 32) {
-                float acc[16];
-                tmem_ld16(t0 + c0, acc);
+            const int rq = lane >> 3, cq = (lane & 7) * 4;       // store mapping: 4 rows x 128 B per instruction
+            for (int cb = chalf; cb * 32 < a.n_tile; cb += 2) {
+                float acc[32];
+                tmem_ld16(t0 + cb * 32, acc);
+                tmem_ld16(t0 + cb * 32 + 16, acc + 16);
                 tmem_ld_wait();
-                if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float v = acc[j] + (a.bias ? s_bias[c0 + j] : 0.f);
-                        if (a.act == 1) v = fmaxf(v, 0.f);
-                        else if (a.act == 2) v = fast_tanh(v);
-                        acc[j] = v;
-                    }
-                    const int ncol = nb * a.n_tile + c0;
-                    if (ncol + 16 <= a.N && ((a.ldy | a.ycol0) & 3) == 0) {
+                for (int j = 0; j < 32; ++j) {
+                    float v = acc[j] + (a.bias ? s_bias[cb * 32 + j] : 0.f);
+                    if (a.act == 1) v = fmaxf(v, 0.f);
+                    else if (a.act == 2) v = fast_tanh(v);
+                    scratch[lane * 33 + j] = v;
+                }
+                __syncwarp();
+                const int ncol = nb * a.n_tile + cb * 32 + cq;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            reinterpret_cast<float4 *>(yrow + c0)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) if (ncol + j < a.N) yrow[c0 + j] = acc[j];
+                for (int j = 0; j < 8; ++j) {
+                    const int rl = rq + 4 * j;                   // row inside the warp's 32-row slice
+                    const int m = row0 + (warp & 3) * 32 + rl;
+                    const float *sp = scratch + rl * 33 + cq;
+                    const float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    if (m < a.M) {
+                        float *y = a.Y + (size_t)m * a.ldy + a.ycol0 + ncol;
+                        if (ncol + 4 <= a.N && ((a.ldy | a.ycol0) & 3) == 0) *reinterpret_cast<float4 *>(y) = v;
+                        else {
+                            if (ncol + 0 < a.N) y[0] = v.x;
+                            if (ncol + 1 < a.N) y[1] = v.y;
+                            if (ncol + 2 < a.N) y[2] = v.z;
+                            if (ncol + 3 < a.N) y[3] = v.w;
+                        }
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(bar(9));
-            asm volatile("bar.sync 1, 256;" ::: "memory");        // s_bias may be rewritten by the next item
+            asm volatile("bar.sync 1, 256;" ::: "memory");        // scratch (= A ring) and s_bias are rewritten by the next item
         }
     } else if (warp == 8) {
         // =============================================================== weight producer
