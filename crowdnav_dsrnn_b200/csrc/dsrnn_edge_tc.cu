@@ -238,6 +238,9 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
             const int next = tile + gridDim.x;
             const bool has_next = next < a.tiles_total;
             if (has_next) prefetch_tile(tile_info(next));
+            // the epilogue reads h_prev back from the A image, whose rows were staged by OTHER warps: all staging stores
+            // of this tile must have landed before any warp starts its first column tile
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             // ---- epilogue: thread tid owns row tid of the tile (TMEM lane tid)
             const int m = t.row0 + tid;
             const bool ok = m < t.M;
@@ -247,16 +250,40 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
             const float *bias = s_bias + t.p * 4 * 256;
             for (int ct = 0; ct < kColTiles; ++ct, ++ctg) {
                 const uint32_t buf = ctg & 1u;
-                // h_prev of this row's 32 hidden units (just staged, so L2-resident) is fetched BEFORE the accumulator wait
-                float4 hprev4[8];
-                const float4 *hp = reinterpret_cast<const float4 *>(a.h_in + mem_row * 256 + ct * 64 + chalf * 32);
+                // h_prev (already masked) of this row's 32 hidden units comes from the staged A image in shared memory
+                // (bf16 hi + lo = 16 mantissa bits; conflict-free 16-byte reads thanks to the 128B swizzle) instead of
+                // 8 row-strided global loads per thread
+                float hprev[32];
+                {
+                    const int cb = ct * 64 + chalf * 32;                 // first hidden unit handled by this warp
+                    const unsigned char *img = smem + (1 + (cb >> 6)) * kABlockBytes;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) hprev4[q] = ok ? hp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int q = 0; q < 4; ++q) {                        // 4 chunks of 8 hidden units
+                        const int off = sw128_offset(tid, (cb & 63) + q * 8);
+                        const uint4 hi = *reinterpret_cast<const uint4 *>(img + kOffAHi + off);
+                        uint4 lo = make_uint4(0u, 0u, 0u, 0u);
+                        if (a.three_pass) lo = *reinterpret_cast<const uint4 *>(img + kOffALo + off);
+                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                        for (int w2 = 0; w2 < 4; ++w2) {
+                            if (a.fp16) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&hw[w2]));
+                                hprev[q * 8 + 2 * w2] = f.x; hprev[q * 8 + 2 * w2 + 1] = f.y;
+                            } else {
+                                hprev[q * 8 + 2 * w2] = __uint_as_float(hw[w2] << 16) + __uint_as_float(lw[w2] << 16);
+                                hprev[q * 8 + 2 * w2 + 1] = __uint_as_float(hw[w2] & 0xffff0000u) + __uint_as_float(lw[w2] & 0xffff0000u);
+                            }
+                        }
+                    }
+                }
                 mbar_wait(bar(kBarTmemFull + buf), (ctg >> 1) & 1u);
                 tc_fence_after();
                 // the last column tile's accumulators are complete => every MMA that reads A has retired: restage A for
                 // the next tile FIRST so its MMAs overlap this epilogue (the other TMEM buffer is already free)
-                if (ct == kColTiles - 1 && has_next) stage_tile(tile_info(next));
+                if (ct == kColTiles - 1 && has_next) {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");   // every warp has taken its h_prev out of the A image
+                    stage_tile(tile_info(next));
+                }
                 const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256u;
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -272,8 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                         float4 *ho = reinterpret_cast<float4 *>(a.h_out + mem_row * 256 + c0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 h4 = hprev4[cc * 4 + q];
-                            const float hprev[4] = {h4.x * mk, h4.y * mk, h4.z * mk, h4.w * mk};
+
                             float o[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -281,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                                 const float r = fast_sigmoid(rg[j] + bias[256 + c]);
                                 const float z = fast_sigmoid(zg[j] + bias[512 + c]);
                                 const float n = fast_tanh(ni[j] + bias[c] + r * (nh[j] + bias[768 + c]));
-                                o[i] = (1.0f - z) * n + z * hprev[i];
+                                o[i] = (1.0f - z) * n + z * hprev[cc * 16 + q * 4 + i];
                             }
                             ho[q] = make_float4(o[0], o[1], o[2], o[3]);
                         }
