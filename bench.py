@@ -254,9 +254,8 @@ def run_ours(args, wl):
         for _ in range(steps):
             _, action, _, hx = policy.act(obs, hx, masks, deterministic=True)
             pin_action.copy_(action, non_blocking=True)            # action.cpu() of VecPyTorch.step_async (envs.py:224-229)
-            torch.cuda.current_stream().synchronize()
-            host_action = pin_action                                # the host buffer the env API is driven from
-            obs, reward, done, infos = venv.step(host_action.to(dev, non_blocking=True))   # reward CPU tensor, done numpy
+            # the env API is driven from the pinned HOST buffer; the H2D copy is ordered after the D2H copy on the stream
+            obs, reward, done, infos = venv.step(pin_action.to(dev, non_blocking=True))    # reward CPU tensor, done numpy
             pin_masks.copy_(torch.from_numpy(1.0 - done.astype(np.float32)).unsqueeze(1))  # train.py:279
             masks = pin_masks.to(dev, non_blocking=True)
         return obs, hx, masks

@@ -108,6 +108,7 @@ class CrowdVecEnv(object):
         self._side = bool(config.test.side_preference)
         self._t0 = time.time()
         self._pending = None
+        self._pin_reward = self._pin_done = None
         self._test_case = test_case
         envs = [SimpleNamespace(env=_EnvView(self, i)) for i in range(min(self.num_envs, 64))]
         self.venv = SimpleNamespace(envs=envs, num_envs=self.num_envs)
@@ -126,8 +127,16 @@ class CrowdVecEnv(object):
     def step_wait(self):
         buf = self.engine.step(self._pending, auto_reset=True)
         self._pending = None
-        reward = buf.reward.to("cpu").unsqueeze(1)                 # VecPyTorch.step_wait keeps reward on the CPU (envs.py:238)
-        done = buf.done.to("cpu").numpy().astype(bool)
+        # VecPyTorch.step_wait keeps reward on the CPU and done as a numpy array (envs.py:231-239): both cross PCIe in
+        # ONE synchronisation through pinned staging buffers (fresh host tensors are returned, like the reference)
+        if self._pin_reward is None:
+            self._pin_reward = torch.empty(self.num_envs, dtype=torch.float32).pin_memory()
+            self._pin_done = torch.empty(self.num_envs, dtype=torch.uint8).pin_memory()
+        self._pin_reward.copy_(buf.reward, non_blocking=True)
+        self._pin_done.copy_(buf.done, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        reward = self._pin_reward.clone().unsqueeze(1)
+        done = self._pin_done.numpy().astype(bool)
         return buf.obs(), reward, done, LazyInfos(buf, self._side, self._t0)
 
     def step(self, actions):
