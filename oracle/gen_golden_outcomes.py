@@ -26,6 +26,24 @@ CASES = {
                                 ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),
     # reference defaults (circle_radius 6, random scenario per episode), holonomic, 5 humans
     "default_h5_holonomic": dict(over={}, ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),
+    # unicycle checkpoint with its own time step (data/example_model_unicycle/configs/config.py:20); needs oracle patch P1
+    "default_h5_unicycle": dict(over={"action_space.kinematics": "unicycle", "env.time_step": 0.1,
+                                      "reward.discomfort_penalty_factor": 1.0},
+                                ckpt="data/example_model_unicycle/checkpoints/55554.pt", episodes=2000),
+    # BASELINE.json configs[3], second half: side-preference scenarios (1 human, circle_radius 4, 200 episodes each;
+    # 2000 here to tighten the noise), config.py:27-40,51-54,87-92
+    "sidepref_passing": dict(over={"test.side_preference": True, "sim.test_sim": ["side_pref_passing"], "sim.circle_radius": 4,
+                                   "sim.human_num": 1, "env.test_size": 200, "humans.random_goal_changing": False,
+                                   "humans.end_goal_changing": False},
+                             ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),
+    "sidepref_overtaking": dict(over={"test.side_preference": True, "sim.test_sim": ["side_pref_overtaking"], "sim.circle_radius": 4,
+                                      "sim.human_num": 1, "env.test_size": 200, "humans.random_goal_changing": False,
+                                      "humans.end_goal_changing": False},
+                                ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),
+    "sidepref_crossing": dict(over={"test.side_preference": True, "sim.test_sim": ["side_pref_crossing"], "sim.circle_radius": 4,
+                                    "sim.human_num": 1, "env.test_size": 200, "humans.random_goal_changing": False,
+                                    "humans.end_goal_changing": False},
+                              ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),
 }
 
 
@@ -49,6 +67,7 @@ def _worker(args):
     env = renv.env
     env.scenario_counter = (episodes * rank) % 4 if cfg.test.social_metrics else 0
     H = cfg.sim.human_num
+    unicycle = cfg.action_space.kinematics == "unicycle"
     spaces = {"robot_node": ref_import.Box(-np.inf, np.inf, (1, 7)), "temporal_edges": ref_import.Box(-np.inf, np.inf, (1, 2)),
               "spatial_edges": ref_import.Box(-np.inf, np.inf, (H, 2))}
     policy = Policy(spaces, ref_import.Box(-np.inf, np.inf, (2,)), base="srnn", base_kwargs=cfg)
@@ -61,17 +80,30 @@ def _worker(args):
     ob = env.reset()
     for _ in range(episodes):
         done, steps, ret = False, 0, 0.0
+        sm = dict(personal_violation=0.0, path_violation=0.0, aggregate_nav_time=0.0, jerk_cost=0.0, speed_violation=0.0,
+                  left=0.0, right=0.0)
         while not done:
             obs = {"robot_node": t(ob["robot_node"], (1, 1, 7)), "temporal_edges": t(ob["temporal_edges"], (1, 1, 2)),
                    "spatial_edges": t(ob["spatial_edges"], (1, H, 2))}
             with torch.no_grad():
                 _, action, _, hx = policy.act(obs, hx, mask, deterministic=True)
-            ob, reward, done, info = env.step(action[0].numpy().copy())
+            if unicycle:                      # declared oracle patch P1 (see oracle/ref_harness.py)
+                renv._csd.ActionRot = renv._make_action_rot
+            try:
+                ob, reward, done, info = env.step(action[0].numpy().copy())
+            finally:
+                renv._csd.ActionRot = renv._ActionRot
             steps += 1
             ret += float(reward)
+            si = info["info"]                 # per-step accounting of evaluation.py:155-190 (counts, not yet times dt)
+            for k in ("personal_violation", "path_violation", "aggregate_nav_time", "jerk_cost", "speed_violation"):
+                sm[k] += float(si[k])
+            if cfg.test.side_preference:
+                sm["left"] += si[si["scenario"]]["left"]
+                sm["right"] += si[si["scenario"]]["right"]
             mask = torch.tensor([[0.0 if done else 1.0]])
         ev = type(info["info"]["event"]).__name__
-        rows.append((ev, info["info"]["scenario"], steps, ret))
+        rows.append((ev, info["info"]["scenario"], steps, ret, sm))
         ob = env.reset()
     return rows
 
@@ -92,6 +124,10 @@ def run_case(name, workers):
         "mean_steps_success": float(np.mean([r[2] for r in rows if r[0] == "ReachGoal"])),
         "mean_return": float(np.mean([r[3] for r in rows])),
         "per_scenario": {},
+        "social": {k: {"mean": float(np.mean([r[4][k] for r in rows])), "std": float(np.std([r[4][k] for r in rows]))}
+                   for k in ("personal_violation", "path_violation", "aggregate_nav_time", "jerk_cost", "speed_violation")},
+        "side_left_episodes": sum(r[4]["left"] > r[4]["right"] for r in rows) / n,
+        "side_right_episodes": sum(r[4]["right"] > r[4]["left"] for r in rows) / n,
         "overrides": case["over"], "checkpoint": case["ckpt"], "wall_seconds": time.time() - t0,
     }
     for scn in sorted(set(r[1] for r in rows)):

@@ -45,6 +45,14 @@ def test_outcome_rates_within_binomial_noise_of_reference(case):
     for k in ("success", "collision", "timeout"):
         assert _z(got[k], n, ref[k], ref["episodes"]) <= 4.0, (k, got[k], ref[k])
     assert abs(got["mean_steps_success"] - ref["mean_steps_success"]) <= 0.08 * ref["mean_steps_success"]
+    # social metrics SM1-SM5: per-episode means within 5 standard errors (+5 % relative slack for the heavy-tailed ones)
+    for k, r in ref.get("social", {}).items():
+        g_mean, g_std = got["mean_%s_per_episode" % k], got["std_%s_per_episode" % k]
+        se = math.sqrt(r["std"] ** 2 / ref["episodes"] + g_std ** 2 / n)
+        assert abs(g_mean - r["mean"]) <= 5.0 * se + 0.05 * abs(r["mean"]) + 1e-9, (k, g_mean, r)
+    if cfg.test.side_preference:   # SM6: which side the robot passes on
+        for k in ("side_left_episodes", "side_right_episodes"):
+            assert _z(got[k], n, ref[k], ref["episodes"]) <= 4.0, (k, got[k], ref[k])
     for scn, r in ref["per_scenario"].items():
         g = got["per_scenario"][scn]
         assert _z(g["success"], g["episodes"], r["success"], r["episodes"]) <= 4.5, (scn, g, r)
