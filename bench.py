@@ -220,24 +220,51 @@ def run_ours(args, wl):
     masks = torch.zeros(N, 1, device=dev)
     obs, hx, masks = rollout(args.prime, obs, hx, masks)      # de-phase the episodes (untimed)
     obs, hx, masks = rollout(args.warmup, obs, hx, masks)     # warm-up (untimed)
-    policy.act(obs, dict(hx), masks, deterministic=True)
-    lib.cn_dsrnn_enable_timing(policy._handle, 1)
-    lib.cn_env_enable_timing(eng.handle, 1)
-    launches0 = eng.launches + policy.gpu_launches
+    import ctypes as C
+    from crowdnav_dsrnn_b200.rollout import GraphedRollout
+
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    obs, hx, masks = rollout(args.steps, obs, hx, masks)
-    ev1.record()
-    barrier()
+    if args.no_graph:
+        launches0 = eng.launches + policy.gpu_launches
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        obs, hx, masks = rollout(args.steps, obs, hx, masks)
+        ev1.record()
+        barrier()
+        launches = eng.launches + policy.gpu_launches - launches0
+    else:
+        # the timed loop replays the rollout step (forward -> action -> crowd step -> reset) as a CUDA graph: the kernels
+        # and the data flow are those of the eager loop (tests/test_gpu_rollout_graph.py), only the launch path differs
+        roll = GraphedRollout(policy, venv, obs, hx, masks)
+        for _ in range(max(3, args.warmup)):
+            roll.step()
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            buf = roll.step()
+        ev1.record()
+        barrier()
+        launches = args.steps * roll.launches_per_step
+        obs = buf.obs()
+        hx, masks = roll.hidden()
+        hx = {k: v.clone() for k, v in hx.items()}
+        masks = masks.clone()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
-    launches = eng.launches + policy.gpu_launches - launches0
-    import ctypes as C
+    # per-kernel durations for the roofline: CUDA events recorded by the library around the dominant kernels on the
+    # launching stream, over a short eager continuation of the same rollout (events cannot be read back from a graph)
+    lib.cn_dsrnn_enable_timing(policy._handle, 1)
+    lib.cn_env_enable_timing(eng.handle, 1)
+    obs, hx, masks = rollout(min(args.steps, 50), obs, hx, masks)
+    torch.cuda.synchronize()
     edge_ms, n_fw, step_ms, n_st = C.c_float(), C.c_int(), C.c_float(), C.c_int()
     lib.cn_dsrnn_time_ms(policy._handle, C.byref(edge_ms), C.byref(n_fw))
     lib.cn_env_time_ms(eng.handle, C.byref(step_ms), C.byref(n_st))
@@ -328,7 +355,7 @@ def run_ours(args, wl):
                    "parallelism": "env-sharded x%d, no data-path collective" % world, "precision": args.precision,
                    "l2": "inputs larger than L2 (hidden state %.0f MB + env state %.0f MB per step vs 126 MB L2)" % (
                        N * (H + 1) * 256 * 4 * 2 / 1e6, N * step_bytes(H) / 1e6),
-                   "prime_steps": args.prime, "resets_per_env_total": resets, "peaks": peaks["source"]},
+                   "launch": "eager" if args.no_graph else "cuda-graph replay of the rollout step", "prime_steps": args.prime, "resets_per_env_total": resets, "peaks": peaks["source"]},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": dominant, "roofline_other": other, "cpu_baseline": cpu,
@@ -351,6 +378,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager loop instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -187,8 +187,10 @@ class Policy(nn.Module):
         except Exception:  # noqa: BLE001
             pass
 
-    def cuda_forward(self, inputs, rnn_hxs, masks, need_features=True):
-        """One rollout-step forward on the GPU. Returns (value[N,1], mean[N,2], features[N,256]|None, h_node, h_edge)."""
+    def cuda_forward(self, inputs, rnn_hxs, masks, need_features=True, out=None):
+        """One rollout-step forward on the GPU. Returns (value[N,1], mean[N,2], features[N,256]|None, h_node, h_edge).
+        `out` = dict of preallocated outputs (h_node, h_edge, value, mean) for callers that need static addresses
+        (CUDA-graph capture, rollout.py)."""
         rn, te, se = inputs["robot_node"], inputs["temporal_edges"], inputs["spatial_edges"]
         device = se.device
         if device.type != "cuda":
@@ -201,10 +203,16 @@ class Policy(nn.Module):
         if hn.numel() != N * 128 or he.numel() != N * (H + 1) * 256 or mk.numel() != N or rn.numel() != N * 7:
             raise ValueError("inconsistent batch shapes for the DS-RNN forward")
         opts = dict(dtype=torch.float32, device=device)
-        hn_out = torch.empty(N, 1, 128, **opts)
-        he_out = torch.empty(N, H + 1, 256, **opts)
-        value = torch.empty(N, 1, **opts)
-        mean = torch.empty(N, 2, **opts)
+        if out is None:
+            hn_out = torch.empty(N, 1, 128, **opts)
+            he_out = torch.empty(N, H + 1, 256, **opts)
+            value = torch.empty(N, 1, **opts)
+            mean = torch.empty(N, 2, **opts)
+        else:
+            hn_out, he_out, value, mean = out["h_node"], out["h_edge"], out["value"], out["mean"]
+            for t_, numel in ((hn_out, N * 128), (he_out, N * (H + 1) * 256), (value, N), (mean, 2 * N)):
+                if t_.numel() != numel or t_.dtype != torch.float32 or t_.device != device or not t_.is_contiguous():
+                    raise ValueError("preallocated forward outputs have the wrong shape / dtype / device")
         feat = torch.empty(N, 256, **opts) if need_features else None
         nbytes = lib.cn_dsrnn_workspace_bytes(N, H)
         if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
