@@ -249,7 +249,9 @@ class Policy(nn.Module):
         mean = self.dist.fc_mean(feat)
         std = self.dist.std().expand_as(mean)
         log_probs = _normal_log_prob(action, mean, std)
-        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + std.log()).sum(-1).mean()
+        # distributions.py:40 spells FixedNormal's override "entrop", so model.py:102 gets torch's element-wise Normal
+        # entropy and its .mean() averages over the action dimensions too (not summed over them); kept as is.
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + std.log()).mean()
         return value, log_probs, entropy, rnn_hxs
 
     # ------------------------------------------------------------------ differentiable torch restatement (training)

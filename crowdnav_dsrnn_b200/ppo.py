@@ -1,0 +1,123 @@
+"""PPO update for the DS-RNN policy, the reference's `PPO`
+(pytorchBaselines/a2c_ppo_acktr/algo/ppo.py:7-118) with the same constructor, the same `update(rollouts)` return value
+and the same arithmetic: advantage normalisation with the unbiased std + 1e-5, clipped surrogate, clipped value loss,
+`value_loss * value_loss_coef + action_loss - entropy * entropy_coef`, grad-norm clipping, Adam(lr, eps).
+
+Added for the sharded rollout (BASELINE.json configs[4]: envs sharded over 1/2/4/8 GPUs):
+
+* data parallel over `torch.distributed` (NCCL on GPUs, gloo in the CPU tests): every rank owns the rollouts of its own
+  envs; the advantage mean/std are computed over ALL ranks' samples (one float64 all-reduce of sum / sum-of-squares /
+  count) and the gradients of each minibatch are averaged with ONE all-reduce of a flat bucket before clipping, so a
+  W-rank update of W*n envs is the single-process update of the union minibatch;
+* `max_envs_per_pass`: a minibatch is processed in sub-chunks of whole env trajectories with gradient accumulation
+  (same gradient, bounded activation memory: T=30 steps x 21 edges x 768 gate columns per env are kept for backward).
+
+The rollout forward (`Policy.act`) is the CUDA hot path; the differentiable sequence forward used here is the torch
+restatement in model.py (`Policy.evaluate_actions`), autograd does the backward.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.optim as optim
+
+
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group)
+    return 1
+
+
+def normalized_advantages(rollouts, group=None):
+    """ppo.py:37-38 -- (A - mean) / (std + 1e-5) with torch's unbiased std, statistics taken over every rank."""
+    adv = rollouts.returns[:-1] - rollouts.value_preds[:-1]
+    if _world(group) == 1:
+        return (adv - adv.mean()) / (adv.std() + 1e-5)
+    a64 = adv.double()
+    stats = torch.stack([a64.sum(), (a64 * a64).sum(), torch.tensor(float(adv.numel()), dtype=torch.float64, device=adv.device)])
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    total, sq, count = stats[0], stats[1], stats[2]
+    mean = total / count
+    var = (sq - count * mean * mean).clamp_min(0.0) / (count - 1.0)
+    return ((a64 - mean) / (var.sqrt() + 1e-5)).float()
+
+
+class PPO:
+    def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef, lr=None, eps=None,
+                 max_grad_norm=None, use_clipped_value_loss=True, group=None, max_envs_per_pass=None):
+        self.actor_critic = actor_critic
+        self.clip_param = clip_param
+        self.ppo_epoch = ppo_epoch
+        self.num_mini_batch = num_mini_batch
+        self.value_loss_coef = value_loss_coef
+        self.entropy_coef = entropy_coef
+        self.max_grad_norm = max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.group = group
+        self.max_envs_per_pass = max_envs_per_pass
+        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, eps=eps)
+        self.perm_fn = None            # tests / reproducibility: callable(num_processes) -> env permutation
+        self.allreduce_calls = 0
+
+    # ------------------------------------------------------------------ pieces
+    def _losses(self, sample, weight):
+        obs, hx, actions, value_preds, returns, masks, old_log_probs, adv = sample
+        values, log_probs, entropy, _ = self.actor_critic.evaluate_actions(obs, hx, masks, actions)
+        ratio = torch.exp(log_probs - old_log_probs)
+        surr1 = ratio * adv
+        surr2 = torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param) * adv
+        action_loss = -torch.min(surr1, surr2).mean()
+        if self.use_clipped_value_loss:
+            clipped = value_preds + (values - value_preds).clamp(-self.clip_param, self.clip_param)
+            value_loss = 0.5 * torch.max((values - returns).pow(2), (clipped - returns).pow(2)).mean()
+        else:
+            value_loss = 0.5 * (returns - values).pow(2).mean()
+        total = value_loss * self.value_loss_coef + action_loss - entropy * self.entropy_coef
+        (total * weight).backward()
+        return value_loss.detach() * weight, action_loss.detach() * weight, entropy.detach() * weight
+
+    def _average_gradients(self):
+        world = _world(self.group)
+        if world == 1:
+            return
+        grads = [p.grad for p in self.actor_critic.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.allreduce_calls += 1
+        flat.div_(world)
+        offset = 0
+        for g in grads:
+            g.copy_(flat[offset:offset + g.numel()].view_as(g))
+            offset += g.numel()
+
+    # ------------------------------------------------------------------ reference interface
+    def update(self, rollouts):
+        advantages = normalized_advantages(rollouts, self.group)
+        N = rollouts.num_processes
+        n = N // self.num_mini_batch
+        per_pass = n if not self.max_envs_per_pass else max(1, min(n, int(self.max_envs_per_pass)))
+        sums = torch.zeros(3, device=advantages.device)
+        for _ in range(self.ppo_epoch):
+            perm = self.perm_fn(N) if self.perm_fn is not None else torch.randperm(N)
+            perm = torch.as_tensor(perm, dtype=torch.int64).to(advantages.device)
+            for start in range(0, n * self.num_mini_batch, n):
+                self.optimizer.zero_grad()
+                for a in range(0, n, per_pass):
+                    ind = perm[start + a:start + min(a + per_pass, n)]
+                    parts = self._losses(rollouts.gather(ind, advantages), ind.numel() / float(n))
+                    sums += torch.stack(parts)
+                self._average_gradients()
+                nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
+                self.optimizer.step()
+        sums /= float(self.ppo_epoch * self.num_mini_batch)
+        if _world(self.group) > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+            sums /= _world(self.group)
+        value_loss, action_loss, entropy = sums.tolist()
+        return value_loss, action_loss, entropy
+
+
+def update_linear_schedule(optimizer, epoch, total_num_epochs, initial_lr):
+    """pytorchBaselines/a2c_ppo_acktr/utils.py:46-50."""
+    lr = initial_lr - (initial_lr * (epoch / float(total_num_epochs)))
+    for group in optimizer.param_groups:
+        group["lr"] = lr

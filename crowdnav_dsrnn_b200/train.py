@@ -1,0 +1,112 @@
+"""Training driver: the loop of the reference's train.py:205-400 on the batched backend.
+
+Per update: `ppo.num_steps` rollout steps (`Policy.act` -> CUDA forward, `CrowdVecEnv.step_device` -> CUDA crowd step, both
+device resident, no host synchronisation inside the rollout), `get_value` bootstrap, `compute_returns`, `PPO.update`,
+`after_update`; checkpoints are `state_dict`s named `%.5i.pt` under `<output_dir>/checkpoints` (train.py:326-339) and
+`progress.csv` has the reference's columns (train.py:363-372).  Episode statistics are reduced on the device
+(the reference walks a Python list of info dicts per step, train.py:263-276).
+
+Under `torch.distributed` every rank runs this function with its own shard of `training.num_processes` envs
+(env ids offset by rank so the episode seeds do not collide) and `PPO` averages the gradients; rank 0 writes artefacts.
+"""
+import csv
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+from . import abi
+from .envs import CrowdVecEnv
+from .model import Policy
+from .ppo import PPO, update_linear_schedule
+from .storage import SRNNRolloutStorage
+
+
+def _rank_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def train(config, device=None, num_updates=None, output_dir=None, actor_critic=None, log=print, max_envs_per_pass=None,
+          keep_hidden_history=False):
+    rank, world = _rank_world()
+    device = torch.device(device if device is not None else "cuda:0")
+    torch.manual_seed(config.env.seed + rank)
+    torch.cuda.manual_seed_all(config.env.seed + rank)
+    N, T, H = int(config.training.num_processes), int(config.ppo.num_steps), int(config.sim.human_num)
+    envs = CrowdVecEnv(config, N, device, seed=config.env.seed, phase="train", env_id_offset=rank * N, nenv=N * world)
+    if actor_critic is None:
+        actor_critic = Policy(envs.observation_space.spaces, envs.action_space, base=config.robot.policy, base_kwargs=config)
+    actor_critic.to(device)
+    if world > 1:                         # same initial weights everywhere
+        for p in actor_critic.parameters():
+            dist.broadcast(p.data, src=0)
+    rollouts = SRNNRolloutStorage(T, N, envs.observation_space.spaces, envs.action_space, config.SRNN.human_node_rnn_size,
+                                  config.SRNN.human_human_edge_rnn_size, "GRU", device=device,
+                                  keep_hidden_history=keep_hidden_history)
+    agent = PPO(actor_critic, config.ppo.clip_param, config.ppo.epoch, config.ppo.num_mini_batch, config.ppo.value_loss_coef,
+                config.ppo.entropy_coef, lr=config.training.lr, eps=config.training.eps,
+                max_grad_norm=config.training.max_grad_norm, max_envs_per_pass=max_envs_per_pass)
+    obs = envs.reset()
+    for k in rollouts.obs:
+        rollouts.obs[k][0].copy_(obs[k])
+    total_updates = int(config.training.num_env_steps) // T // (N * world)
+    if num_updates is None:
+        num_updates = total_updates
+    out_dir = output_dir if output_dir is not None else config.training.output_dir
+    if rank == 0 and out_dir:
+        os.makedirs(os.path.join(out_dir, "checkpoints"), exist_ok=True)
+    # device-side episode statistics: [success, collision, timeout, episodes, return sum]
+    stats = torch.zeros(5, dtype=torch.float64, device=device)
+    history = []
+    start = time.time()
+    for j in range(num_updates):
+        if config.training.use_linear_lr_decay:
+            update_linear_schedule(agent.optimizer, j, max(total_updates, num_updates), config.training.lr)
+        stats.zero_()
+        for step in range(T):
+            value, action, log_prob, hx = actor_critic.act(rollouts.obs_at(step), dict(rollouts.hidden_at(step)),
+                                                           rollouts.masks[step])
+            obs, reward, done, buf = envs.step_device(action)
+            d = done.to(torch.float64)
+            stats += torch.stack([((buf.event == abi.EV_REACH_GOAL).to(torch.float64) * d).sum(),
+                                  ((buf.event == abi.EV_COLLISION).to(torch.float64) * d).sum(),
+                                  ((buf.event == abi.EV_TIMEOUT).to(torch.float64) * d).sum(), d.sum(),
+                                  (buf.episode_return.to(torch.float64) * d).sum()])
+            masks = 1.0 - done.to(torch.float32)
+            rollouts.insert(obs, hx, action, log_prob, value, reward, masks, None)
+        next_value = actor_critic.get_value(rollouts.obs_at(-1), dict(rollouts.hidden_at(-1)), rollouts.masks[-1]).detach()
+        rollouts.compute_returns(next_value, config.ppo.use_gae, config.reward.gamma, config.ppo.gae_lambda,
+                                 config.training.use_proper_time_limits)
+        value_loss, action_loss, entropy = agent.update(rollouts)
+        rollouts.after_update()
+        if world > 1:
+            dist.all_reduce(stats)
+        s = stats.tolist()
+        total_steps = (j + 1) * N * world * T
+        row = {"misc/nupdates": j, "misc/total_timesteps": total_steps, "fps": int(total_steps / (time.time() - start)),
+               "eprewmean": s[4] / s[3] if s[3] else float("nan"), "loss/policy_entropy": entropy,
+               "loss/policy_loss": action_loss, "loss/value_loss": value_loss,
+               "success": s[0] / s[3] if s[3] else float("nan"), "collision": s[1] / s[3] if s[3] else float("nan"),
+               "timeout": s[2] / s[3] if s[3] else float("nan"), "episodes": int(s[3])}
+        history.append(row)
+        if rank == 0 and out_dir:
+            if j % config.training.save_interval == 0 or j == num_updates - 1:
+                torch.save(actor_critic.state_dict(), os.path.join(out_dir, "checkpoints", "%.5i" % j + ".pt"))
+            if j % config.training.log_interval == 0:
+                path = os.path.join(out_dir, "progress.csv")
+                fresh = not os.path.exists(path) or j == 0
+                with open(path, "w" if fresh else "a", newline="") as f:
+                    w = csv.DictWriter(f, fieldnames=list(row)[:7], extrasaction="ignore")
+                    if fresh:
+                        w.writeheader()
+                    w.writerow(row)
+        if rank == 0 and log is not None and j % config.training.log_interval == 0:
+            log("Updates %d, num timesteps %d, FPS %d, episodes %d: mean reward %.3f, success %.3f, collision %.3f, timeout %.3f, "
+                "entropy %.4f, value loss %.4f, policy loss %.5f" % (j, total_steps, row["fps"], row["episodes"], row["eprewmean"],
+                                                                      row["success"], row["collision"], row["timeout"], entropy,
+                                                                      value_loss, action_loss))
+    envs.close()
+    return actor_critic, history

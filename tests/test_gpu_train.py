@@ -1,0 +1,75 @@
+"""GPU: the training loop -- CUDA rollout + torch PPO update on the device, reference artefact
+names, and the CUDA forward picking up the weights Adam just changed."""
+import csv
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from crowdnav_dsrnn_b200 import Config
+from crowdnav_dsrnn_b200.model import Policy
+from crowdnav_dsrnn_b200.spaces import crowd_spaces
+from crowdnav_dsrnn_b200.train import train
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _shipped_policy(cfg):
+    w = np.load(os.path.join(GOLDEN, "weights_holonomic_27776.npz"))
+    obs, act = crowd_spaces(cfg.sim.human_num)
+    p = Policy(obs.spaces, act, base="srnn", base_kwargs=cfg)
+    p.load_state_dict({k: torch.from_numpy(w[k]) for k in w.files})
+    return p.to(DEV)
+
+
+def test_training_loop_runs_and_writes_reference_artefacts(tmp_path):
+    cfg = Config()
+    cfg.training.num_processes = 256
+    cfg.training.log_interval = 1
+    cfg.training.save_interval = 2
+    policy = _shipped_policy(cfg)
+    before = {k: v.detach().clone() for k, v in policy.state_dict().items()}
+    policy2, history = train(cfg, DEV, num_updates=4, output_dir=str(tmp_path), actor_critic=policy, log=None,
+                             max_envs_per_pass=64)
+    assert policy2 is policy and len(history) == 4
+    for row in history:
+        assert all(math.isfinite(row[k]) for k in ("loss/value_loss", "loss/policy_loss", "loss/policy_entropy"))
+    # the shipped policy keeps solving the task while being fine-tuned with sampled actions (reference: 0.93 deterministic)
+    episodes = sum(r["episodes"] for r in history)
+    success = sum(r["success"] * r["episodes"] for r in history) / episodes
+    assert episodes > 300 and success > 0.75, (episodes, success)
+    changed = [k for k, v in policy.state_dict().items() if not torch.equal(v, before[k])]
+    assert len(changed) == len(before)
+    assert sorted(os.listdir(tmp_path / "checkpoints")) == ["00000.pt", "00002.pt", "00003.pt"]
+    sd = torch.load(tmp_path / "checkpoints" / "00003.pt", map_location="cpu")
+    assert sorted(sd) == sorted(before) and torch.equal(sd["dist.logstd._bias"], policy.state_dict()["dist.logstd._bias"].cpu())
+    with open(tmp_path / "progress.csv") as f:
+        rows = list(csv.DictReader(f))
+    assert list(rows[0]) == ["misc/nupdates", "misc/total_timesteps", "fps", "eprewmean", "loss/policy_entropy",
+                             "loss/policy_loss", "loss/value_loss"] and len(rows) == 4
+    assert int(rows[-1]["misc/total_timesteps"]) == 4 * 256 * 30
+
+
+def test_cuda_forward_tracks_optimizer_updates():
+    """Adam updates the parameters in place; the next `act` must run on the new weights (re-packed tcgen05 images)."""
+    cfg = Config()
+    policy = _shipped_policy(cfg)
+    n, H = 32, 5
+    g = torch.Generator(device="cpu").manual_seed(3)
+    obs = {"robot_node": torch.randn(n, 1, 7, generator=g).to(DEV), "temporal_edges": torch.randn(n, 1, 2, generator=g).to(DEV),
+           "spatial_edges": torch.randn(n, H, 2, generator=g).to(DEV)}
+    hx = lambda: {"human_node_rnn": torch.zeros(n, 1, 128, device=DEV), "human_human_edge_rnn": torch.zeros(n, H + 1, 256, device=DEV)}
+    masks = torch.ones(n, 1, device=DEV)
+    v0, a0, _, _ = policy.act(obs, hx(), masks, deterministic=True)
+    opt = torch.optim.Adam(policy.parameters(), lr=1e-2)
+    value, _, _, _ = policy.evaluate_actions(obs, hx(), masks, a0)
+    value.mean().backward()
+    opt.step()
+    v1, a1, _, _ = policy.act(obs, hx(), masks, deterministic=True)
+    vt, _, _, _ = policy.evaluate_actions(obs, hx(), masks, a1)
+    assert (v1 - v0).abs().max() > 1e-3                    # the weights moved ...
+    assert (v1 - vt.detach()).abs().max() < 1e-3 * max(1.0, float(vt.abs().max()))   # ... and CUDA and torch paths agree on them
