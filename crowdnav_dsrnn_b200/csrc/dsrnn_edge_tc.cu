@@ -11,38 +11,63 @@
 //   warp 9     owns TMEM (512 columns = 2 accumulator buffers) and issues tcgen05.mma.kind::f16 (M=128, N=192, K=16).
 // Precision: CN_PREC_BF16X3 runs A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (fp32 accumulate in TMEM, ~2^-16 relative operand
 // error); CN_PREC_BF16 runs the first pass only.
+#include <cuda.h>
+#include <cstdlib>
 #include <new>
 #include "dsrnn.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int kRows = 128;                 // UMMA M
+constexpr int kRows = 128;                 // rows per CTA; the CTA pair multiplies 256 rows per MMA (cta_group::2)
 constexpr int kKBlocks = 5;                // 64-wide k-blocks: 1 encoded-input block + 4 hidden blocks
 constexpr int kColTiles = 4;               // 64 hidden units per column tile
 constexpr int kABlockBytes = kRows * 128;  // 128 rows x 64 bf16
 constexpr int kBChunkRows = 192;                 // weight rows per (column tile, k-block, part): [n_i|r|z] or [r|z|n_h] x 64
 constexpr int kBChunkBytes = kBChunkRows * 128;
-constexpr int kBSlots = 2;
-constexpr int kBarAReady = 2 * kBSlots, kBarTmemFull = kBarAReady + 1, kBarTmemEmpty = kBarTmemFull + 2;
-constexpr int kThreads = 320;              // 8 staging/epilogue warps + weight producer + MMA issuer
+constexpr int kBHalfBytes = kBChunkBytes / 2;    // each CTA of the pair holds 96 of the 192 weight rows (N is split)
+constexpr int kBSlots = 5;
+constexpr int kEpiWarps = 8, kStageWarps = 8, kWarpProducer = 16, kWarpMma = 17;
+constexpr int kThreads = 20 * 32;            // 5 warpgroups: 2 epilogue, 2 staging, 1 (producer, MMA, 2 idle warps)
+constexpr int kRegsEpi = 128, kRegsStage = 96, kRegsMisc = 32;   // setmaxnreg budgets (640 threads start at 96 registers each)
+static_assert(256 * kRegsEpi + 256 * kRegsStage + 128 * kRegsMisc <= 640 * 96, "setmaxnreg only moves registers inside the CTA's launch allocation");
+// mbarrier map
+constexpr int kBarFull = 0, kBarEmpty = kBSlots, kBarAReady = 2 * kBSlots, kBarAFree = kBarAReady + 2,
+              kBarTmemFull = kBarAFree + 2, kBarTmemEmpty = kBarTmemFull + 2, kBarHprev = kBarTmemEmpty + 2, kNumBars = kBarHprev + 1;
 
 constexpr int kOffAHi = 0;
 constexpr int kOffALo = kOffAHi + kKBlocks * kABlockBytes;        //  81920
 constexpr int kOffB = kOffALo + kKBlocks * kABlockBytes;          // 163840
-constexpr int kOffBias = kOffB + kBSlots * kBChunkBytes;                // 212992  float[2][4][256]
-constexpr int kOffEnc = kOffBias + 2 * 4 * 256 * 4;               // 221184  float[2][192]: w0[64] w1[64] b[64]
-constexpr int kOffBar = kOffEnc + 2 * 192 * 4;                    // 222720  mbarriers
-constexpr int kSmemBytes = kOffBar + 128;                         // 222848 (+1024 alignment slack at launch)
+constexpr int kOffEnc = kOffB + kBSlots * kBHalfBytes;            // 225280  float[2][192]: w0[64] w1[64] b[64]
+constexpr int kOffBias = kOffEnc + 2 * 192 * 4;                   // 226816  float[4][256] of the CURRENT problem: b_in | b_r | b_z | b_hn
+constexpr int kOffBar = kOffBias + 4 * 256 * 4;                   // 230912  mbarriers + TMEM base
+constexpr int kSmemBytes = kOffBar + 256;                         // 231168 (+1024 alignment slack at launch)
+static_assert(kSmemBytes + 1024 <= 232448, "shared memory budget of one sm_100 CTA");
 
 struct TcState {
     __nv_bfloat16 *wimg;   // [2 problems][4 ct][5 kb][3 parts: bf16 hi | bf16 lo | fp16] x 24 KB swizzled images
     float *bias4;          // [2][4][256]: b_in | b_ir+b_hr | b_iz+b_hz | b_hn
     float *enc;            // [2][192]
     int num_sms;
+    CUtensorMap wmap;      // the weight images as a [rows x 64] 16-bit tensor, box = 96 rows (one CTA's half of a chunk)
 };
 
 using namespace tc;
+
+#ifdef EDGE_PROFILE
+__device__ unsigned long long g_edge_prof[32];
+#define PROF_DECL(n) long long n = 0
+#define PROF_T0(t) const long long t = clock64()
+#define PROF_ADD(n, t) n += clock64() - t
+#define PROF_OUT(i, n) atomicAdd(&g_edge_prof[i], (unsigned long long)(n))
+#define DBG(bit) (a.debug & (bit))
+#else
+#define DBG(bit) 0
+#define PROF_DECL(n)
+#define PROF_T0(t)
+#define PROF_ADD(n, t)
+#define PROF_OUT(i, n)
+#endif
 
 // ---------------------------------------------------------------------------------------------- weight packing
 struct PackArgs {
@@ -103,159 +128,119 @@ struct EdgeTcArgs {
     const __nv_bfloat16 *wimg;
     const float *bias4, *enc;
     int N, H;
-    int tiles_spatial, tiles_total;
+    int tiles_spatial, tiles_temporal;   // 128-row tiles per problem
+    int pairs_spatial, pairs_total;      // 256-row tile pairs (one per CTA pair and iteration); a pair never mixes problems
     int three_pass;
     int fp16;          // single pass with FP16 operands (images part 2) instead of BF16
+    int debug;         // EDGE_PROFILE builds: what-if switches (timing only, results are wrong), 0 otherwise
 };
 
-__global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a)
+struct TileInfo { bool spatial; int p, row0, M; };
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__ CUtensorMap wmap)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const uint32_t s_base = smem_u32(smem);
-    float *s_bias = reinterpret_cast<float *>(smem + kOffBias);
     float *s_enc = reinterpret_cast<float *>(smem + kOffEnc);
+    float *s_bias = reinterpret_cast<float *>(smem + kOffBias);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 112);   // 13 mbarriers occupy the first 104 bytes
-    // barrier map: 0,1 full_b | 2,3 empty_b | 4 a_ready | 5,6 tmem_full | 7,8 tmem_empty
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 8 * kNumBars);
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = a.H, stride = a.H + 1;
+    const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs of the pair)
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
-    for (int i = threadIdx.x; i < 2 * 4 * 256; i += kThreads) s_bias[i] = a.bias4[i];
     for (int i = threadIdx.x; i < 2 * 192; i += kThreads) s_enc[i] = a.enc[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * kBSlots; ++i) mbar_init(bar(i), 1);
-        mbar_init(bar(kBarAReady), 256);
+        for (int i = 0; i < kBSlots; ++i) {
+            mbar_init(bar(kBarFull + i), 1);       // leader only: both halves of a weight chunk landed (24 KB of complete_tx)
+            mbar_init(bar(kBarEmpty + i), 1);      // MMAs reading the slot retired (commit, both CTAs)
+        }
+        mbar_init(bar(kBarAReady), 2 * kStageWarps); mbar_init(bar(kBarAReady + 1), 2 * kStageWarps);   // leader only
+        mbar_init(bar(kBarAFree), 1); mbar_init(bar(kBarAFree + 1), 1);
+        mbar_init(bar(kBarHprev), kEpiWarps);     // this CTA's epilogue warps took h_prev of column tiles 2, 3 out of the A image
         mbar_init(bar(kBarTmemFull), 1); mbar_init(bar(kBarTmemFull + 1), 1);
-        mbar_init(bar(kBarTmemEmpty), 256); mbar_init(bar(kBarTmemEmpty + 1), 256);
+        mbar_init(bar(kBarTmemEmpty), 2 * kEpiWarps); mbar_init(bar(kBarTmemEmpty + 1), 2 * kEpiWarps);   // leader only
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == kWarpMma) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    // accumulator columns of one buffer: n_i [0,64) | r [64,128) | z [128,192) | n_h [192,256).  Every MMA is N = 192: the
+    // input block overwrites n_i|r|z, the four hidden blocks accumulate into r|z|n_h -- so n_h has to start from zero: the
+    // epilogue clears it after reading (and here, once, before the first tile).
+    if (warp < kEpiWarps) {
+        const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 192u + (uint32_t)(warp >> 2) * 32u;
+        tmem_st16_zero(t0); tmem_st16_zero(t0 + 16u); tmem_st16_zero(t0 + 256u); tmem_st16_zero(t0 + 256u + 16u);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
 
-    if (warp < 8) {
-        // =============================================================== staging + epilogue warps
-        const int tid = (warp & 3) * 32 + lane;   // row of the tile (TMEM lane) this thread owns in the epilogue
+    auto tile_info = [&](int pair) {
+        TileInfo t;
+        t.spatial = pair < a.pairs_spatial;
+        t.p = t.spatial ? 0 : 1;
+        const int tile = 2 * (t.spatial ? pair : pair - a.pairs_spatial) + (int)rank;
+        const bool valid = tile < (t.spatial ? a.tiles_spatial : a.tiles_temporal);
+        t.row0 = tile * kRows;
+        t.M = valid ? (t.spatial ? a.N * H : a.N) : 0;          // an odd tile count leaves the peer of the last pair idle
+        return t;
+    };
+    auto mem_row_of = [&](const TileInfo &t, int m, int &env) {
+        env = t.spatial ? m / H : m;
+        return t.spatial ? env * stride + 1 + (m - env * H) : env * stride;
+    };
+
+    if (warp < kEpiWarps) {
+        // =============================================================== epilogue warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+        const int tid = (warp & 3) * 32 + lane;   // row of the tile = TMEM lane this thread owns
         const int chalf = warp >> 2;              // warps 0-3: hidden units 0..31 of a column tile, warps 4-7: 32..63
+        const uint32_t empty_remote = mapa_rank(bar(kBarTmemEmpty), 0);
         uint32_t ctg = 0;                         // column tiles consumed so far (selects the TMEM buffer / parity)
-
-        struct TileInfo { bool spatial; int p, row0, M; };
-        auto tile_info = [&](int tile) {
-            TileInfo t;
-            t.spatial = tile < a.tiles_spatial;
-            t.p = t.spatial ? 0 : 1;
-            t.row0 = (t.spatial ? tile : tile - a.tiles_spatial) * kRows;
-            t.M = t.spatial ? a.N * H : a.N;
-            return t;
-        };
-        auto mem_row_of = [&](const TileInfo &t, int m, int &env) {
-            env = t.spatial ? m / H : m;
-            return t.spatial ? (size_t)env * stride + 1 + (m - env * H) : (size_t)env * stride;
-        };
-        // pull the NEXT tile's hidden-state rows into L2 while this tile is being computed (128 rows x 8 lines / 256 threads)
-        auto prefetch_tile = [&](const TileInfo &t) {
-            const int r = threadIdx.x >> 1, m = t.row0 + r;
-            if (m < t.M) {
-                int env;
-                const float *row = a.h_in + mem_row_of(t, m, env) * 256 + (threadIdx.x & 1) * 128;
-#pragma unroll
-                for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + l * 32));
-            }
-        };
-        // stage A: warp w converts rows w*16 .. w*16+15, 8 rows per batch so 16 x 16 B loads per lane are in flight
-        // before the first conversion (a warp reads one 1 KB row with two float4 loads per lane)
-        auto stage_tile = [&](const TileInfo &t) {
-            const float *enc = s_enc + t.p * 192;
-#pragma unroll 1
-            for (int rb = 0; rb < 16; rb += 8) {
-                float4 hv[8][2];
-                float xs[8][2], mks[8];
-                bool oks[8];
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const int m = t.row0 + warp * 16 + rb + b;
-                    oks[b] = m < t.M;
-                    hv[b][0] = hv[b][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    xs[b][0] = xs[b][1] = mks[b] = 0.f;
-                    if (oks[b]) {
-                        int env;
-                        const float *hrow = a.h_in + mem_row_of(t, m, env) * 256 + lane * 4;
-                        hv[b][0] = *reinterpret_cast<const float4 *>(hrow);
-                        hv[b][1] = *reinterpret_cast<const float4 *>(hrow + 128);
-                        mks[b] = a.masks[env];
-                        const float *x = t.spatial ? a.spatial_edges + 2 * (size_t)m : a.temporal_edges + 2 * (size_t)m;
-                        xs[b][0] = x[0]; xs[b][1] = x[1];
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const int r = warp * 16 + rb + b;
-                    {   // encoded input block (k-block 0): lane owns k = 2*lane, 2*lane+1
-                        float e[2];
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const int k = 2 * lane + i;
-                            e[i] = oks[b] ? fmaxf(fmaf(enc[64 + k], xs[b][1], enc[k] * xs[b][0]) + enc[128 + k], 0.f) : 0.f;
-                        }
-                        uint32_t hi, lo;
-                        if (a.fp16) { hi = pack_half2(e[0], e[1]); lo = 0u; } else split_bf16x2(e[0], e[1], hi, lo);
-                        const int off = sw128_offset(r, 2 * lane);
-                        *reinterpret_cast<uint32_t *>(smem + kOffAHi + off) = hi;
-                        if (a.three_pass) *reinterpret_cast<uint32_t *>(smem + kOffALo + off) = lo;
-                    }
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {   // hidden blocks: elements half*128 + lane*4 .. +3
-                        const int e0 = half * 128 + lane * 4;
-                        float4 h4 = hv[b][half];
-                        const float mk = mks[b];
-                        h4.x *= mk; h4.y *= mk; h4.z *= mk; h4.w *= mk;
-                        const int off = (1 + (e0 >> 6)) * kABlockBytes + sw128_offset(r, e0 & 63);
-                        uint2 hi, lo;
-                        if (a.fp16) { hi.x = pack_half2(h4.x, h4.y); hi.y = pack_half2(h4.z, h4.w); lo.x = lo.y = 0u; }
-                        else { split_bf16x2(h4.x, h4.y, hi.x, lo.x); split_bf16x2(h4.z, h4.w, hi.y, lo.y); }
-                        *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = hi;
-                        if (a.three_pass) *reinterpret_cast<uint2 *>(smem + kOffALo + off) = lo;
-                    }
-                }
-            }
-            fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-            mbar_arrive(bar(kBarAReady));
-        };
-
-        int tile = blockIdx.x;
-        if (tile < a.tiles_total) stage_tile(tile_info(tile));
-        for (; tile < a.tiles_total; tile += gridDim.x) {
-            const TileInfo t = tile_info(tile);
-            const int next = tile + gridDim.x;
-            const bool has_next = next < a.tiles_total;
-            if (has_next) prefetch_tile(tile_info(next));
-            // the epilogue reads h_prev back from the A image, whose rows were staged by OTHER warps: all staging stores
-            // of this tile must have landed before any warp starts its first column tile
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            // ---- epilogue: thread tid owns row tid of the tile (TMEM lane tid)
+        int bias_p = -1;                          // problem whose biases are in shared memory
+        PROF_DECL(p_waitfull); PROF_DECL(p_epi); PROF_DECL(p_hprev); PROF_DECL(p_total);
+        PROF_T0(t_all);
+        for (int pair = cluster_id; pair < a.pairs_total; pair += num_clusters) {
+            const TileInfo t = tile_info(pair);
             const int m = t.row0 + tid;
             const bool ok = m < t.M;
             size_t mem_row = 0;
-            float mk = 0.f;
-            if (ok) { int env; mem_row = mem_row_of(t, m, env); mk = a.masks[env]; }
-            const float *bias = s_bias + t.p * 4 * 256;
+            if (ok) { int env; mem_row = (size_t)mem_row_of(t, m, env); }
+            if (t.p != bias_p) {                  // at most twice per CTA: spatial pairs come first, then temporal ones
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                reinterpret_cast<float4 *>(s_bias)[threadIdx.x] = __ldg(reinterpret_cast<const float4 *>(a.bias4 + t.p * 4 * 256) + threadIdx.x);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                bias_p = t.p;
+            }
+            float *orow = a.h_out + mem_row * 256;
             for (int ct = 0; ct < kColTiles; ++ct, ++ctg) {
                 const uint32_t buf = ctg & 1u;
-                // h_prev (already masked) of this row's 32 hidden units comes from the staged A image in shared memory
-                // (bf16 hi + lo = 16 mantissa bits; conflict-free 16-byte reads thanks to the 128B swizzle) instead of
-                // 8 row-strided global loads per thread
+                const int cb = ct * 64 + chalf * 32;                 // first hidden unit handled by this warp
+                PROF_T0(t_w);
+                mbar_wait(bar(kBarTmemFull + buf), (ctg >> 1) & 1u);
+                tc_fence_after();
+                PROF_ADD(p_waitfull, t_w);
+                // h_prev (already masked) of this row's 32 hidden units comes back out of the staged A image (bf16 hi + lo =
+                // 16 mantissa bits; conflict-free 16-byte reads thanks to the 128B swizzle); the accumulators being complete implies
+                // that the staging warps' writes of this tile are complete and visible.  The staging warps overwrite
+                // k-blocks 0-2 only after the MMAs of column tile 3 passed k-block 2 -- those MMAs wait for the epilogue of
+                // column tile 1, so the reads for tiles 0, 1 are long done -- and k-blocks 3-4 only after kBarHprev.
+                PROF_T0(t_h);
                 float hprev[32];
                 {
-                    const int cb = ct * 64 + chalf * 32;                 // first hidden unit handled by this warp
                     const unsigned char *img = smem + (1 + (cb >> 6)) * kABlockBytes;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {                        // 4 chunks of 8 hidden units
@@ -276,14 +261,9 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                         }
                     }
                 }
-                mbar_wait(bar(kBarTmemFull + buf), (ctg >> 1) & 1u);
-                tc_fence_after();
-                // the last column tile's accumulators are complete => every MMA that reads A has retired: restage A for
-                // the next tile FIRST so its MMAs overlap this epilogue (the other TMEM buffer is already free)
-                if (ct == kColTiles - 1 && has_next) {
-                    asm volatile("bar.sync 1, 256;" ::: "memory");   // every warp has taken its h_prev out of the A image
-                    stage_tile(tile_info(next));
-                }
+                if (ct == kColTiles - 1) { __syncwarp(); if (lane == 0) mbar_arrive(bar(kBarHprev)); }
+                PROF_ADD(p_hprev, t_h);
+                PROF_T0(t_e);
                 const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256u;
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -295,109 +275,255 @@ __global__ void __launch_bounds__(kThreads, 1) edge_gru_tc_kernel(const __grid_c
                     tmem_ld16(t0 + 3 * 64 + c16 * 16, nh);
                     tmem_ld_wait();
                     const int c0 = ct * 64 + c16 * 16;
-                    if (ok) {
-                        float4 *ho = reinterpret_cast<float4 *>(a.h_out + mem_row * 256 + c0);
+                    if (ok && !DBG(4)) {
+                        float4 *ho = reinterpret_cast<float4 *>(orow + c0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-
+                            const int c = c0 + q * 4;
+                            const float4 b_n = *reinterpret_cast<const float4 *>(s_bias + c), b_r = *reinterpret_cast<const float4 *>(s_bias + 256 + c),
+                                         b_z = *reinterpret_cast<const float4 *>(s_bias + 512 + c), b_h = *reinterpret_cast<const float4 *>(s_bias + 768 + c);
+                            const float bn[4] = {b_n.x, b_n.y, b_n.z, b_n.w}, br[4] = {b_r.x, b_r.y, b_r.z, b_r.w},
+                                        bz[4] = {b_z.x, b_z.y, b_z.z, b_z.w}, bh[4] = {b_h.x, b_h.y, b_h.z, b_h.w};
                             float o[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int c = c0 + q * 4 + i, j = q * 4 + i;
-                                const float r = fast_sigmoid(rg[j] + bias[256 + c]);
-                                const float z = fast_sigmoid(zg[j] + bias[512 + c]);
-                                const float n = fast_tanh(ni[j] + bias[c] + r * (nh[j] + bias[768 + c]));
-                                o[i] = (1.0f - z) * n + z * hprev[cc * 16 + q * 4 + i];
+                                const int j = q * 4 + i;
+                                o[i] = gru_blend(rg[j] + br[i], zg[j] + bz[i], ni[j] + bn[i], nh[j] + bh[i], hprev[cc * 16 + j]);
                             }
                             ho[q] = make_float4(o[0], o[1], o[2], o[3]);
                         }
                     }
                 }
+                tmem_st16_zero(t0 + 192u + (uint32_t)chalf * 32u);          // n_h starts the next column tile from zero
+                tmem_st16_zero(t0 + 192u + (uint32_t)chalf * 32u + 16u);
+                tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(bar(kBarTmemEmpty + buf));
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(empty_remote + 8u * buf);
+                PROF_ADD(p_epi, t_e);
             }
         }
-    } else if (warp == 8) {
-        // =============================================================== weight producer (one lane)
+        PROF_ADD(p_total, t_all);
+        if (threadIdx.x == 0) { PROF_OUT(1, p_waitfull); PROF_OUT(2, p_epi); PROF_OUT(3, p_hprev); PROF_OUT(4, p_total); PROF_OUT(5, 1); }
+    } else if (warp < kEpiWarps + kStageWarps) {
+        // =============================================================== staging warps: fp32 rows -> split-bf16 A image
+        static_assert(kRegsStage == 96, "staging warps keep the launch allocation");
+        const int sw = warp - kEpiWarps;          // this warp converts rows sw*16 .. sw*16+15 of the tile
+        const uint32_t ready_remote = mapa_rank(bar(kBarAReady), 0);
+        uint32_t it = 0;
+        PROF_DECL(p_stage); PROF_DECL(p_wfree);
+        for (int pair = cluster_id; pair < a.pairs_total; pair += num_clusters, ++it) {
+            const TileInfo t = tile_info(pair);
+            const float *enc = s_enc + t.p * 192;
+            // lane b (and b+16) holds the bookkeeping of row b of this warp's 16 rows
+            const int m_l = t.row0 + sw * 16 + (lane & 15);
+            const bool ok_l = m_l < t.M;
+            int ridx_l = 0;
+            float mk_l = 0.f, x0_l = 0.f, x1_l = 0.f;
+            if (ok_l) {
+                int env;
+                ridx_l = mem_row_of(t, m_l, env);
+                mk_l = a.masks[env];
+                const float *x = t.spatial ? a.spatial_edges + 2 * (size_t)m_l : a.temporal_edges + 2 * (size_t)m_l;
+                x0_l = x[0]; x1_l = x[1];
+            }
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {   // hidden units [0,128) (+ the encoded input block), then [128,256)
+                float4 hv[16];
+#pragma unroll
+                for (int b = 0; b < 16; ++b) {        // 16 x 512 B in flight per warp before the first conversion
+                    const int ridx = __shfl_sync(0xffffffffu, ridx_l, b);
+                    const bool okb = __shfl_sync(0xffffffffu, (int)ok_l, b) != 0;
+                    hv[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (okb && !DBG(8)) hv[b] = *reinterpret_cast<const float4 *>(a.h_in + (size_t)ridx * 256 + half * 128 + lane * 4);
+                }
+                // the loads above are in flight while the pair's MMAs on the previous tile finish reading k-blocks 0-2 / 3-4
+                PROF_T0(t_f);
+                if (it > 0) {
+                    mbar_wait(bar(kBarAFree + half), (it - 1) & 1u);
+                    if (half) mbar_wait(bar(kBarHprev), (it - 1) & 1u);
+                }
+                PROF_ADD(p_wfree, t_f);
+                PROF_T0(t_s);
+#pragma unroll
+                for (int b = 0; b < 16; ++b) {
+                    const int r = sw * 16 + b;
+                    const float mk = __shfl_sync(0xffffffffu, mk_l, b);
+                    if (half == 0) {   // encoded input block (k-block 0): lane owns k = 2*lane, 2*lane+1
+                        const float x0 = __shfl_sync(0xffffffffu, x0_l, b), x1 = __shfl_sync(0xffffffffu, x1_l, b);
+                        const bool okb = __shfl_sync(0xffffffffu, (int)ok_l, b) != 0;
+                        float e[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int k = 2 * lane + i;
+                            e[i] = okb ? fmaxf(fmaf(enc[64 + k], x1, enc[k] * x0) + enc[128 + k], 0.f) : 0.f;
+                        }
+                        uint32_t hi, lo;
+                        if (a.fp16) { hi = pack_half2(e[0], e[1]); lo = 0u; } else split_bf16x2(e[0], e[1], hi, lo);
+                        const int off = sw128_offset(r, 2 * lane);
+                        *reinterpret_cast<uint32_t *>(smem + kOffAHi + off) = hi;
+                        if (a.three_pass) *reinterpret_cast<uint32_t *>(smem + kOffALo + off) = lo;
+                    }
+                    const int e0 = half * 128 + lane * 4;
+                    float4 h4 = hv[b];
+                    h4.x *= mk; h4.y *= mk; h4.z *= mk; h4.w *= mk;
+                    const int off = (1 + (e0 >> 6)) * kABlockBytes + sw128_offset(r, e0 & 63);
+                    uint2 hi, lo;
+                    if (a.fp16) { hi.x = pack_half2(h4.x, h4.y); hi.y = pack_half2(h4.z, h4.w); lo.x = lo.y = 0u; }
+                    else { split_bf16x2(h4.x, h4.y, hi.x, lo.x); split_bf16x2(h4.z, h4.w, hi.y, lo.y); }
+                    *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = hi;
+                    if (a.three_pass) *reinterpret_cast<uint2 *>(smem + kOffALo + off) = lo;
+                }
+                fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ready_remote + 8u * half);   // k-blocks 0-2, then 3-4, of this CTA's rows
+                PROF_ADD(p_stage, t_s);
+            }
+            // pull the NEXT tile's hidden-state rows into L2 while this one is being multiplied (16 rows x 8 lines per warp)
+            const int next = pair + num_clusters;
+            if (next < a.pairs_total) {
+                const TileInfo tn = tile_info(next);
+                const int mn = tn.row0 + sw * 16 + (lane & 15);
+                if (mn < tn.M) {
+                    int env;
+                    const float *row = a.h_in + (size_t)mem_row_of(tn, mn, env) * 256 + (lane >> 4) * 128;
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + l * 32));
+                }
+            }
+        }
+        if (threadIdx.x == kEpiWarps * 32) { PROF_OUT(0, p_stage); PROF_OUT(6, p_wfree); }
+    } else {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMisc));
+      if (warp == kWarpProducer) {
+        // =============================================================== weight producer (one lane): this CTA's half of
+        // every 192-row chunk = 96 weight rows = 12 KB, one TMA box; both CTAs' copies report to the LEADER's barrier
+        // (cp.async.bulk.tensor .cta_group::2), so the MMA thread waits on one barrier per chunk
         if (lane == 0) {
-            uint32_t chunk = 0;
+            uint32_t slot = 0, empty_parity = 1;
             const int parts = a.three_pass ? 2 : 1;
-            for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
-                const int p = tile < a.tiles_spatial ? 0 : 1;
-                const char *img = reinterpret_cast<const char *>(a.wimg) + (size_t)p * kColTiles * kKBlocks * 3 * kBChunkBytes;
+            const uint32_t full_leader = mapa_rank(bar(kBarFull), 0);
+            PROF_DECL(p_wait); PROF_DECL(p_total);
+            PROF_T0(t_all);
+            for (int pair = cluster_id; pair < a.pairs_total; pair += num_clusters) {
+                const int p = pair < a.pairs_spatial ? 0 : 1;
                 for (int ct = 0; ct < kColTiles; ++ct)
                     for (int kb = 0; kb < kKBlocks; ++kb)
-                        for (int part = 0; part < parts; ++part, ++chunk) {
-                            const uint32_t slot = chunk % kBSlots;
-                            mbar_wait(bar(kBSlots + slot), ((chunk / kBSlots) & 1u) ^ 1u);
-                            mbar_expect_tx(bar(slot), kBChunkBytes);
-                            bulk_g2s(s_base + kOffB + slot * kBChunkBytes,
-                                     img + ((size_t)(ct * kKBlocks + kb) * 3 + (a.fp16 ? 2 : part)) * kBChunkBytes, kBChunkBytes, bar(slot));
+                        for (int part = 0; part < parts; ++part) {
+                            PROF_T0(tw);
+                            mbar_wait(bar(kBarEmpty + slot), empty_parity);
+                            PROF_ADD(p_wait, tw);
+                            if (rank == 0) mbar_expect_tx(bar(kBarFull + slot), kBChunkBytes);
+                            const int row = ((((p * kColTiles + ct) * kKBlocks + kb) * 3 + (a.fp16 ? 2 : part)) * kBChunkRows) + (int)rank * (kBChunkRows / 2);
+                            tma_load_2d_pair(s_base + kOffB + slot * kBHalfBytes, &wmap, 0, row, full_leader + 8u * slot);
+                            if (++slot == kBSlots) { slot = 0; empty_parity ^= 1u; }
                         }
             }
+            PROF_ADD(p_total, t_all);
+            PROF_OUT(16, p_wait); PROF_OUT(17, p_total);
         }
-    } else {
-        // =============================================================== MMA issuer (one lane)
+      } else if (warp != kWarpMma) {
+        // warps 18, 19 only pad the last warpgroup
+      } else if (rank != 0) {
+        // the peer's lane of this warp has nothing to issue: cta_group::2 MMAs come from the leader alone
+      } else {
+        // =============================================================== MMA issuer (one lane of the leader CTA)
         if (lane == 0) {
-            uint32_t chunk = 0, ctg = 0, tile_iter = 0;
-            const uint32_t id192 = a.fp16 ? idesc_f16(192) : idesc_bf16(192), id128 = a.fp16 ? idesc_f16(128) : idesc_bf16(128),
-                           id64 = a.fp16 ? idesc_f16(64) : idesc_bf16(64);
+            uint32_t ctg = 0, it = 0;
+            const uint32_t id192 = a.fp16 ? idesc_f16_m256(192) : idesc_bf16_m256(192);
             // shared-memory descriptors: the high word is constant, the low word is (address >> 4) | LBO; stepping K by 16
-            // elements (32 B) or to another k-block / ring slot only adds to the low word, so one MMA costs a few instructions
+            // elements (32 B) or to another k-block / ring slot only adds to the low word, so one MMA costs a few instructions.
+            // The same offsets are valid in the peer CTA (identical shared-memory layout), which is what cta_group::2 reads.
             constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
             auto make_desc = [](uint32_t lo) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi)); return d; };
             const uint32_t a_hi_desc_lo = ((s_base + kOffAHi) >> 4) | (1u << 16), a_lo_desc_lo = ((s_base + kOffALo) >> 4) | (1u << 16);
             const uint32_t b_desc_lo = ((s_base + kOffB) >> 4) | (1u << 16);
-            for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++tile_iter) {
-                mbar_wait(bar(kBarAReady), tile_iter & 1u);
+            PROF_DECL(p_wa); PROF_DECL(p_we); PROF_DECL(p_wb); PROF_DECL(p_total);
+            PROF_T0(t_all);
+            uint32_t slot = 0, full_parity = 0;       // ring position, advanced incrementally (no division in the loop)
+            // four K=16 steps of one 64-wide k-block: D[dcol..+192) (+)= A(a_lo) * B(b_lo)^T on both CTAs of the pair
+            auto mma_kblock = [&](uint32_t dcol, uint32_t a_lo, uint32_t b_lo, bool overwrite_first) {
+                umma2_f16(dcol, make_desc(a_lo), make_desc(b_lo), id192, overwrite_first ? 0u : 1u);
+                umma2_f16(dcol, make_desc(a_lo + 2), make_desc(b_lo + 2), id192, 1u);
+                umma2_f16(dcol, make_desc(a_lo + 4), make_desc(b_lo + 4), id192, 1u);
+                umma2_f16(dcol, make_desc(a_lo + 6), make_desc(b_lo + 6), id192, 1u);
+            };
+            auto next_chunk = [&](uint32_t &b_lo) {     // wait for the next weight chunk (both halves), return its descriptor word
+                PROF_T0(twb);
+                mbar_wait(bar(kBarFull + slot), full_parity);
                 tc_fence_after();
+                PROF_ADD(p_wb, twb);
+                b_lo = b_desc_lo + slot * (kBHalfBytes >> 4);
+            };
+            PROF_DECL(p_commit);
+            auto release_chunk = [&]() {
+                PROF_T0(tc0);
+                umma2_commit_pair(bar(kBarEmpty + slot));
+                PROF_ADD(p_commit, tc0);
+                if (++slot == kBSlots) { slot = 0; full_parity ^= 1u; }
+            };
+            for (int pair = cluster_id; pair < a.pairs_total; pair += num_clusters, ++it) {
                 for (int ct = 0; ct < kColTiles; ++ct, ++ctg) {
                     const uint32_t buf = ctg & 1u;
-                    mbar_wait(bar(kBarTmemEmpty + buf), ((ctg >> 1) & 1u) ^ 1u);
+                    PROF_T0(twe);
+                    mbar_wait_cluster(bar(kBarTmemEmpty + buf), ((ctg >> 1) & 1u) ^ 1u);
                     tc_fence_after();
+                    PROF_ADD(p_we, twe);
                     const uint32_t d0 = tmem_base + buf * 256u;
+#pragma unroll 1
                     for (int kb = 0; kb < kKBlocks; ++kb) {
-                        const uint32_t dcol = d0 + (kb == 0 ? 0u : 64u);
-                        const int parts = a.three_pass ? 2 : 1;
-                        for (int part = 0; part < parts; ++part, ++chunk) {   // part 0: B_hi (passes A_hi, A_lo), part 1: B_lo (pass A_hi)
-                            const uint32_t slot = chunk % kBSlots;
-                            mbar_wait(bar(slot), (chunk / kBSlots) & 1u);
+                        if (ct == 0 && (kb == 0 || kb == 3)) {      // both CTAs' staging warps finished k-blocks 0-2 / 3-4
+                            PROF_T0(twa);
+                            mbar_wait_cluster(bar(kBarAReady + (kb ? 1 : 0)), it & 1u);
                             tc_fence_after();
-                            const uint32_t b_lo = b_desc_lo + slot * (kBChunkBytes >> 4);
-                            const int passes = (part == 0 && a.three_pass) ? 2 : 1;
-                            for (int ps = 0; ps < passes; ++ps) {
-                                const uint32_t a_lo = (ps == 0 ? a_hi_desc_lo : a_lo_desc_lo) + kb * (kABlockBytes >> 4);
-#pragma unroll
-                                for (int k16 = 0; k16 < 4; ++k16) {
-                                    const uint64_t ad = make_desc(a_lo + 2 * k16), bd = make_desc(b_lo + 2 * k16);
-                                    const bool first = part == 0 && ps == 0 && k16 == 0;
-                                    if (first && kb == 0) umma_bf16(dcol, ad, bd, id192, 0u);           // overwrite n_i | r | z
-                                    else if (first && kb == 1) {                                         // r | z accumulate, n_h starts
-                                        umma_bf16(dcol, ad, bd, id128, 1u);
-                                        umma_bf16(dcol + 128u, ad, make_desc(b_lo + ((128 * 128) >> 4) + 2 * k16), id64, 0u);
-                                    } else umma_bf16(dcol, ad, bd, id192, 1u);
-                                }
-                            }
-                            umma_commit(bar(kBSlots + slot));
+                            PROF_ADD(p_wa, twa);
                         }
+                        const uint32_t dcol = d0 + (kb == 0 ? 0u : 64u);
+                        const uint32_t a_hi = a_hi_desc_lo + kb * (kABlockBytes >> 4), a_lo = a_lo_desc_lo + kb * (kABlockBytes >> 4);
+                        uint32_t b_lo;
+                        next_chunk(b_lo);                                   // B_hi (bf16 hi, or the fp16 image)
+                        if (!DBG(2)) {
+                            mma_kblock(dcol, a_hi, b_lo, kb == 0);          // the input block overwrites n_i | r | z
+                            if (a.three_pass) mma_kblock(dcol, a_lo, b_lo, false);
+                        }
+                        release_chunk();
+                        if (a.three_pass) {
+                            next_chunk(b_lo);                               // B_lo
+                            if (!DBG(2)) mma_kblock(dcol, a_hi, b_lo, false);
+                            release_chunk();
+                        }
+                        if (ct == kColTiles - 1 && kb == 2) umma2_commit_pair(bar(kBarAFree));       // k-blocks 0-2 of A are free
                     }
-                    umma_commit(bar(kBarTmemFull + buf));       // accumulators of this column tile are complete
+                    umma2_commit_pair(bar(kBarTmemFull + buf));     // accumulators of this column tile are complete in both CTAs
                 }
+                umma2_commit_pair(bar(kBarAFree + 1));              // every MMA that reads this tile's A image has retired
             }
+            PROF_ADD(p_total, t_all);
+            PROF_OUT(8, p_wa); PROF_OUT(9, p_we); PROF_OUT(10, p_wb); PROF_OUT(11, p_commit); PROF_OUT(12, p_total);
         }
+      }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 9) {
+    cluster_sync_all();                     // the peer may still be signalling barriers in this CTA's shared memory
+    if (warp == kWarpMma) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------- host side
+#ifdef EDGE_PROFILE
+// development builds only (make NET_FLAGS=-DEDGE_PROFILE): per-role cycle counters summed over CTAs, see tools/edge_profile.py
+extern "C" int cn_debug_edge_profile(unsigned long long *out32, int reset)
+{
+    if (out32 && cudaMemcpyFromSymbol(out32, g_edge_prof, sizeof(g_edge_prof)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[32] = {}; if (cudaMemcpyToSymbol(g_edge_prof, z, sizeof(z)) != cudaSuccess) return 1; }
+    return 0;
+}
+#endif
 void dsrnn_tc_destroy(void *state);
 
 const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void **state)
@@ -410,6 +536,26 @@ const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void *
         cudaMalloc(&st->enc, 2 * 192 * sizeof(float)) != cudaSuccess) {
         delete st;
         return "cudaMalloc of the packed edge weights failed";
+    }
+    {   // the driver entry point is resolved at run time so that the library has no link-time dependency on libcuda
+        typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            dsrnn_tc_destroy(st);
+            return "cuTensorMapEncodeTiled is not available from this driver";
+        }
+        const cuuint64_t dims[2] = {64, (cuuint64_t)(img_bytes / 128)};      // 128-byte rows of the pre-swizzled images
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {64, kBChunkRows / 2}, estr[2] = {1, 1};
+        if (reinterpret_cast<EncodeTiled>(fn)(&st->wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, st->wimg, dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            dsrnn_tc_destroy(st);
+            return "cuTensorMapEncodeTiled failed for the edge weight images";
+        }
     }
     int dev = 0;
     cudaGetDevice(&dev);
@@ -448,11 +594,18 @@ const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *, int n_env
     a.h_out = io->h_edge_out; a.wimg = st->wimg; a.bias4 = st->bias4; a.enc = st->enc;
     a.N = n_envs; a.H = H;
     a.tiles_spatial = (int)(((size_t)n_envs * H + kRows - 1) / kRows);
-    a.tiles_total = a.tiles_spatial + (n_envs + kRows - 1) / kRows;
+    a.tiles_temporal = (n_envs + kRows - 1) / kRows;
+    a.pairs_spatial = (a.tiles_spatial + 1) / 2;
+    a.pairs_total = a.pairs_spatial + (a.tiles_temporal + 1) / 2;
     a.three_pass = precision == CN_PREC_BF16X3 ? 1 : 0;
     a.fp16 = precision == CN_PREC_FP16 ? 1 : 0;
-    const int grid = a.tiles_total < st->num_sms ? a.tiles_total : st->num_sms;
-    edge_gru_tc_kernel<<<grid, kThreads, kSmemBytes + 1024, stream>>>(a);
+    a.debug = 0;
+#ifdef EDGE_PROFILE
+    if (const char *dbg = getenv("CN_EDGE_DEBUG")) a.debug = atoi(dbg);
+#endif
+    const int max_pairs = st->num_sms / 2;                        // one CTA pair (cluster of 2) per TPC, persistent
+    const int grid = 2 * (a.pairs_total < max_pairs ? a.pairs_total : max_pairs);
+    edge_gru_tc_kernel<<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap);
     ++*launches;
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

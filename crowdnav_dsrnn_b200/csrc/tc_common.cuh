@@ -58,6 +58,61 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v)
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// ---- 2-CTA (cta_group::2) and cluster variants
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all prior MMAs of this thread arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// one TMA box into THIS CTA's shared memory; the bytes are reported to `mbar_cluster`, which may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void *tmap, int c0, int c1, uint32_t mbar_cluster)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(mbar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                 ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024>>4 |
@@ -72,6 +127,9 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int n) { return (1u << 4) | (1
 
 // same with both operands FP16 (a_format = b_format = 0)
 __host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+// M = 256 (cta_group::2: 128 rows per CTA of the pair)
+__host__ __device__ constexpr uint32_t idesc_bf16_m256(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24); }
+__host__ __device__ constexpr uint32_t idesc_f16_m256(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24); }
 __device__ __forceinline__ uint32_t pack_half2(float x, float y)
 {
     const __half2 h = __floats2half2_rn(x, y);
@@ -87,6 +145,25 @@ __host__ __device__ __forceinline__ int sw128_offset(int row, int k)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
+
+__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// GRU cell output from the four pre-activations (biases included): r = s(xr), z = s(xz), n = tanh(xn + r*xh),
+// h' = n + z*(h - n).  5 MUFU ops per element instead of 6: z and the tanh share one reciprocal, 1/((1+e^-xz)(1+e^2u));
+// the exponents are clamped to 2^+-60 so the product stays finite (s and tanh are saturated to 1 ulp long before that).
+__device__ __forceinline__ float gru_blend(float xr, float xz, float xn, float xh, float h)
+{
+    const float kLog2e = 1.4426950408889634f;
+    const float r = fast_rcp(1.0f + fast_exp2(-kLog2e * xr));
+    const float u = xn + r * xh;
+    const float ez = fast_exp2(fminf(-kLog2e * xz, 60.0f));
+    const float en = fast_exp2(fminf(2.0f * kLog2e * u, 60.0f));
+    const float q = fast_rcp((1.0f + ez) * (1.0f + en));
+    const float z = q * (1.0f + en);
+    const float n = 1.0f - 2.0f * q * (1.0f + ez);
+    return n + z * (h - n);
+}
 
 // split an fp32 pair into bf16 hi and bf16 lo (residual) pairs: x ~= hi + lo with ~2^-17 relative error
 __device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t &hi, uint32_t &lo)
