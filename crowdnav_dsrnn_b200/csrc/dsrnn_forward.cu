@@ -16,12 +16,22 @@
 #include "dsrnn.cuh"
 #include "dsrnn_tc_linear.cuh"
 
+#include <cstdlib>
 #include <vector>
+
+// dsrnn_node_tc.cu: stages 3 + 4 as one tcgen05 kernel
+const char *dsrnn_node_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void **state);
+void dsrnn_node_tc_destroy(void *state);
+const char *dsrnn_node_tc_forward(void *state, int n_envs, const CnDsrnnIO *io, const float *cat, float *feat, int precision,
+                                  cudaStream_t stream, int *launches);
+
 struct CnDsrnn {
     CnDsrnnWeights w;
     int device;
     int last_launches;
     void *tc_state;   // packed bf16 weights of the tensor-core edge stage (dsrnn_edge_tc.cu)
+    void *node_state = nullptr;   // packed weights of the fused node / heads kernel (dsrnn_node_tc.cu)
+    bool unfused_node = false;    // CN_NODE_UNFUSED=1: one launch per layer (development A/B switch)
     bool timing;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;   // events around the edge stage
     int num_sms;
@@ -431,7 +441,10 @@ const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t strea
     m->tc_state = nullptr;
     m->timing = false;
     cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
+    const char *env = getenv("CN_NODE_UNFUSED");
+    m->unfused_node = env && env[0] == '1';
     const char *msg = dsrnn_tc_create(w, stream, &m->tc_state);
+    if (!msg) msg = dsrnn_node_tc_create(w, stream, &m->node_state);
     if (!msg) msg = create_tc_linears(m, stream);
     if (msg) { dsrnn_destroy(m); return msg; }
     *out = m;
@@ -441,6 +454,7 @@ const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t strea
 void dsrnn_destroy(CnDsrnn *m)
 {
     if (m->tc_state) dsrnn_tc_destroy(m->tc_state);
+    if (m->node_state) dsrnn_node_tc_destroy(m->node_state);
     destroy_tc_linears(m);
     dsrnn_time_ms(m, nullptr);
     for (auto &p : m->pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -452,8 +466,11 @@ const char *dsrnn_update_weights(CnDsrnn *m, const CnDsrnnWeights *w, cudaStream
     m->w = *w;
     if (m->tc_state) dsrnn_tc_destroy(m->tc_state);
     m->tc_state = nullptr;
+    if (m->node_state) dsrnn_node_tc_destroy(m->node_state);
+    m->node_state = nullptr;
     destroy_tc_linears(m);
     const char *msg = dsrnn_tc_create(w, stream, &m->tc_state);
+    if (!msg) msg = dsrnn_node_tc_create(w, stream, &m->node_state);
     return msg ? msg : create_tc_linears(m, stream);
 }
 
@@ -529,6 +546,16 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
         run(m->att_qt, m->att_wc, m->att_bc, q, 256, 256);
         attention_kernel<<<(N + 3) / 4, 128, 0, s>>>(io->h_edge_out, ws.qt, ws.cat, N, H);
         ++launches;
+    }
+
+    // ---- stages 3 + 4 on the tensor cores: one kernel for the node RNN and the heads
+    if (precision != CN_PREC_FP32 && !m->unfused_node) {
+        const char *msg = dsrnn_node_tc_forward(m->node_state, N, io, ws.cat, io->actor_features, precision, s, &launches);
+        if (msg) return msg;
+        if (run.err) return run.err;
+        m->last_launches = launches;
+        const cudaError_t err = cudaGetLastError();
+        return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
     }
 
     // ---- stage 3: node RNN
