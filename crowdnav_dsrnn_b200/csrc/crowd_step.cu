@@ -32,7 +32,10 @@ template <int G> struct GroupOps {
     int gbase;       // first lane of the group
     int gl;          // lane index inside the group
     __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(gmask, v, src, G); }
+    __device__ __forceinline__ int shfl_i(int v, int src) const { return __shfl_sync(gmask, v, src, G); }
     __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(gmask, p) >> gbase) & kLow; }
+    // group-relative mask of the lanes holding the same value
+    __device__ __forceinline__ unsigned match(int v) const { return (__match_any_sync(gmask, v) >> gbase) & kLow; }
     // min/max over the group in ONE redux.sync each: floats are mapped to integers with the same total order
     // (exact: a reduction only selects one of its inputs; the LP never feeds NaNs here)
     static __device__ __forceinline__ int ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
@@ -185,12 +188,14 @@ __device__ __forceinline__ float2 orca_group(const CnConfig &cfg, const GroupOps
     const bool in = have && dist_sq < cfg.orca_neighbor_dist * cfg.orca_neighbor_dist;
     const unsigned in_bits = g.ballot(in);
     const int n = __popc(in_bits);
+    // rank = number of in-range neighbours that sort before this one.  dist_sq >= +0, so its bit pattern orders like the
+    // float; out-of-range slots get the largest key and never count.  Ties (equal distSq, lower index first) come from one
+    // MATCH instruction instead of a second comparison per candidate.
+    const int key = in ? __float_as_int(dist_sq) : 0x7fffffff;
     int rank = 0;
-#pragma unroll 4
-    for (int k = 0; k < M; ++k) {   // slots >= M are never in range
-        const float dk = g.shfl(dist_sq, k);
-        if (((in_bits >> k) & 1u) && (dk < dist_sq || (dk == dist_sq && k < g.gl))) ++rank;
-    }
+#pragma unroll 8
+    for (int k = 0; k < M; ++k) rank += (g.shfl_i(key, k) < key) ? 1 : 0;   // slots >= M are never in range
+    rank += __popc(g.match(key) & in_bits & ((1u << g.gl) - 1u));
 
     // computeNewVelocity: this lane's half-plane
     Line ln; ln.px = ln.py = ln.dx = ln.dy = 0.0f;
