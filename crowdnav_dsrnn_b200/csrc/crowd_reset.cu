@@ -8,9 +8,10 @@
 // (bounded) rejection loops, the first accepted thread wins -- identical to the sequential loop
 // because every candidate is a pure function of (episode key, human, try) under the counter-based
 // Philox4x32-10 contract (oracle/crowd_oracle.c restates the same contract sequentially).
+#include <cstdio>
 #include "env_common.cuh"
 
-#define RESET_THREADS 128
+#define RESET_THREADS 256
 
 __device__ __forceinline__ void write_reset_obs(const EnvParams &P, const CnObsOut &obs, int e, int lane, int H,
                                                 float4 rpv, float4 rgr, float theta, bool reset_flag)
@@ -61,13 +62,17 @@ __device__ __forceinline__ int cta_first_ok(bool ok, int *s_vote)
     return first == 0x7fffffff ? -1 : first;
 }
 
-// grid: one CTA of 128 threads per env (envs whose mask byte is 0 exit at once); thread t evaluates try
-// t, t+128, ... of each bounded rejection loop, so a typical spawn needs a single round per human.
+// grid: one CTA of RESET_THREADS threads per env (envs whose mask byte is 0 exit at once); thread t evaluates try
+// t, t+RESET_THREADS, ... of each bounded rejection loop, so a typical spawn needs a single round per human.
+// (-DRESET_PROFILE prints per-env cycle counts of the phases; tools/reset_stats.py summarises them.)
 __global__ void __launch_bounds__(RESET_THREADS)
 crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnObsOut obs,
                    const uint8_t *__restrict__ mask)
 {
-    __shared__ float4 s_h[CN_MAX_HUMANS];   // px, py, radius of the humans spawned so far
+    __shared__ double s_hx[CN_MAX_HUMANS], s_hy[CN_MAX_HUMANS], s_hr[CN_MAX_HUMANS];   // px, py, radius of the humans spawned so far
+    // fp32 pre-filter of the min-distance rule against earlier human k: squared distance below s_lo[k] / above s_hi[k]
+    // decides the fp64 comparison for certain (band of 1e-4 relative, fp32 error of the squared distance < 1e-5 there)
+    __shared__ float s_fx[CN_MAX_HUMANS], s_fy[CN_MAX_HUMANS], s_lo[CN_MAX_HUMANS], s_hi[CN_MAX_HUMANS];
     __shared__ int s_vote[RESET_THREADS / 32];
     __shared__ double s_pick[6];
     const CnConfig &cfg = P.cfg;
@@ -76,6 +81,12 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
     const int e = blockIdx.x;
     if (e >= P.n_envs) return;
     if (mask && !mask[e]) return;
+#ifdef RESET_PROFILE
+    const long long pt0 = clock64();
+    long long pt_mid = 0;
+    long long pq[3] = {0, 0, 0};
+    int prounds = 0;
+#endif
     int4 ctr = P.a.ctr[e];
     const uint64_t key = episode_key(cfg, ctr.z, e);
     const uint4 g0 = philox4x32(key, 0, 0, 0, RNG_RESET);
@@ -99,7 +110,7 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
                 cpx = -R + 2.0 * R * u01(x.x); cpy = -R + 2.0 * R * u01(x.y);
                 cgx = -R + 2.0 * R * u01(x.z); cgy = -R + 2.0 * R * u01(x.w);
             }
-            const bool ok = t < cfg.max_robot_tries && norm2d(cpx - cgx, cpy - cgy) >= 6.0;
+            const bool ok = t < cfg.max_robot_tries && !norm2d_lt(cpx - cgx, cpy - cgy, 6.0);
             int src = cta_first_ok(ok, s_vote);
             const bool last_round = t0 + RESET_THREADS >= cfg.max_robot_tries;
             if (src < 0 && last_round) src = (cfg.max_robot_tries - 1) - t0;        // keep the last try
@@ -118,8 +129,14 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
     const float4 rpv = make_float4((float)rpx, (float)rpy, 0.0f, 0.0f);
     const float4 rgr = make_float4((float)rgx, (float)rgy, (float)cfg.robot_radius, (float)cfg.robot_v_pref);
 
+#ifdef RESET_PROFILE
+    const long long pt1 = clock64();
+#endif
     // ---- humans, sequentially; tries in parallel (crowd_sim.py:359-393)
     for (int i = 0; i < H; ++i) {
+#ifdef RESET_PROFILE
+        if (i == H / 2) pt_mid = clock64();
+#endif
         double v_pref = cfg.human_v_pref, radius = cfg.human_radius;
         if (cfg.randomize_attributes) {
             const uint4 x = philox4x32(key, 0, (uint32_t)i, 0, RNG_ATTR);
@@ -127,26 +144,60 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
             radius = 0.3 + (0.5 - 0.3) * u01(x.y);
         }
         const float radius_f = (float)radius;
+        if (tid < i) {
+            const double md = (double)radius_f + s_hr[tid] + cfg.discomfort_dist, md2 = md * md;
+            s_lo[tid] = (float)(md2 * (1.0 - 1e-4));
+            s_hi[tid] = (float)(md2 * (1.0 + 1e-4));
+        }
+        __syncthreads();
         SpawnCand c;
         c.px = c.py = c.gx = c.gy = c.heading = c.v_pref = 0.0;
         for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += RESET_THREADS) {
             const int t = t0 + tid;
+#ifdef RESET_PROFILE
+            ++prounds;
+            const long long q0 = clock64();
+#endif
             const uint4 xa = philox4x32(key, (uint32_t)t, (uint32_t)i, 0, RNG_SPAWN);
             const uint4 xb = philox4x32(key, (uint32_t)t, (uint32_t)i, 1, RNG_SPAWN);
             const double u6[6] = {u01(xa.x), u01(xa.y), u01(xa.z), u01(xa.w), u01(xb.x), u01(xb.y)};
             c = agent_attributes(cfg, scenario, (double)radius_f, v_pref, (double)rgr.z, u6);
+#ifdef RESET_PROFILE
+            const long long q1 = clock64();
+#endif
             bool collide;
             {
                 const double md = (cfg.kinematics == CN_UNICYCLE) ? R / 2.0 : (double)radius_f + (double)rgr.z + cfg.discomfort_dist;
-                collide = norm2d(c.px - (double)rpv.x, c.py - (double)rpv.y) < md;
+                collide = norm2d_lt(c.px - (double)rpv.x, c.py - (double)rpv.y, md);
             }
-            for (int k = 0; k < i && !collide; ++k) {
-                const float4 a = s_h[k];
-                const double md = (double)radius_f + (double)a.z + cfg.discomfort_dist;
-                if (norm2d(c.px - (double)a.x, c.py - (double)a.y) < md) collide = true;
+            // branch-free fp32 pass over the earlier humans (positions are stored as floats, so s_fx / s_fy are exact);
+            // the exact fp64 rule only runs for a candidate that lands inside some pair's 1e-4 band without a certain hit
+            {
+                const float fx = (float)c.px, fy = (float)c.py;
+                bool band = false;
+#pragma unroll 4
+                for (int k = 0; k < i; ++k) {
+                    const float dx = fx - s_fx[k], dy = fy - s_fy[k];
+                    const float sq = dx * dx + dy * dy;
+                    collide |= sq < s_lo[k];
+                    band |= (sq >= s_lo[k]) & (sq <= s_hi[k]);
+                }
+                if (band && !collide) {
+                    for (int k = 0; k < i; ++k) {
+                        const double md = (double)radius_f + s_hr[k] + cfg.discomfort_dist;
+                        collide |= norm2d_lt(c.px - s_hx[k], c.py - s_hy[k], md);
+                    }
+                }
             }
             const bool ok = t < cfg.max_spawn_tries && !collide;
+#ifdef RESET_PROFILE
+            const long long q2 = clock64();
+#endif
             int src = cta_first_ok(ok, s_vote);
+#ifdef RESET_PROFILE
+            const long long q3 = clock64();
+            pq[0] += q1 - q0; pq[1] += q2 - q1; pq[2] += q3 - q2;
+#endif
             const bool last_round = t0 + RESET_THREADS >= cfg.max_spawn_tries;
             if (src < 0 && last_round) src = (cfg.max_spawn_tries - 1) - t0;        // keep the last try
             if (src >= 0) {
@@ -161,7 +212,8 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
         __syncthreads();                    // everyone has read s_pick / the old s_h before they change
         if (tid == 0) {
             const size_t hi = (size_t)e * H + i;
-            s_h[i] = make_float4(pv.x, pv.y, radius_f, 0.0f);
+            s_hx[i] = (double)pv.x; s_hy[i] = (double)pv.y; s_hr[i] = (double)radius_f;
+            s_fx[i] = pv.x; s_fy[i] = pv.y;
             P.a.hum_pv[hi] = pv;
             P.a.hum_gr[hi] = gr;
             P.a.hum_th[hi] = (float)c.heading;
@@ -169,6 +221,10 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
         __syncthreads();
     }
 
+#ifdef RESET_PROFILE
+    if (tid == 0 && e < 1500) printf("reset e=%d scn=%d robot %lld first-half %lld second-half %lld cycles, %d rounds | draw %lld collide %lld vote %lld\n", e, scenario,
+                                     pt1 - pt0, pt_mid - pt1, clock64() - pt_mid, prounds, pq[0], pq[1], pq[2]);
+#endif
     // ---- counters, potential, observation (warp 0 only; its lane 0 wrote the humans above)
     if (tid >= 32) return;
     ctr.x = 0;

@@ -325,14 +325,14 @@ __device__ __forceinline__ bool goal_collides(const CnConfig &cfg, int H, int i,
     const double ri = (double)s_gr[i].z, dd = cfg.discomfort_dist;
     {
         const double md = ri + (double)rob_gr.z + dd;
-        if (norm2d(gx - (double)rob_pv.x, gy - (double)rob_pv.y) < md ||
-            norm2d(gx - (double)rob_gr.x, gy - (double)rob_gr.y) < md) return true;
+        if (norm2d_lt(gx - (double)rob_pv.x, gy - (double)rob_pv.y, md) ||
+            norm2d_lt(gx - (double)rob_gr.x, gy - (double)rob_gr.y, md)) return true;
     }
     for (int k = 0; k < H; ++k) {
         if (k == i) continue;
         const float4 p = s_pv[k], q = s_gr[k];
         const double md = ri + (double)q.z + dd;
-        if (norm2d(gx - (double)p.x, gy - (double)p.y) < md || norm2d(gx - (double)q.x, gy - (double)q.y) < md) return true;
+        if (norm2d_lt(gx - (double)p.x, gy - (double)p.y, md) || norm2d_lt(gx - (double)q.x, gy - (double)q.y, md)) return true;
     }
     return false;
 }
@@ -390,7 +390,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
     velocity_rect_d(rpv.x, rpv.y, rpv.z, rpv.w, rgr.z, rvr);
     velocity_rect_d(hpv.x, hpv.y, hpv.z, hpv.w, hgr.z, hvr);
     const int vec_viol = __popc(__ballot_sync(FULL, counted && rects_intersect_d(rvr, hvr)));
-    const bool h_reached = norm2d((double)hpv.x - (double)hgr.x, (double)hpv.y - (double)hgr.y) < (double)hgr.z;
+    const bool h_reached = norm2d_lt((double)hpv.x - (double)hgr.x, (double)hpv.y - (double)hgr.y, (double)hgr.z);
     int agg_nav = __popc(__ballot_sync(FULL, counted && !h_reached));
     const double dgoal = norm2d((double)rpv.x - (double)rgr.x, (double)rpv.y - (double)rgr.y);
     const bool reaching_goal = dgoal < (double)rgr.z;
@@ -533,7 +533,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
         for (int i = 0; i < H; ++i) {
             const float4 pi_ = s_pv[i];
             const float4 gi = s_gr[i];
-            if (!(norm2d((double)gi.x - (double)pi_.x, (double)gi.y - (double)pi_.y) < (double)gi.z)) continue;
+            if (!norm2d_lt((double)gi.x - (double)pi_.x, (double)gi.y - (double)pi_.y, (double)gi.z)) continue;
             const uint4 dec = philox4x32(key, RNG_DECISION, (uint32_t)i, su, RNG_GOAL_END);
             if (!(u01(dec.x) <= cfg.end_goal_change_chance)) continue;
             for (int t0 = 0; t0 < cfg.max_goal_tries; t0 += 32) {

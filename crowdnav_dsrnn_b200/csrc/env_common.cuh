@@ -95,6 +95,16 @@ __device__ __forceinline__ uint64_t step_key(const CnConfig &cfg, int scenario_c
 }
 
 __device__ __forceinline__ double norm2d(double x, double y) { return sqrt(x * x + y * y); }
+// exactly (norm2d(x, y) < r), but the fp64 square root (a ~30-instruction Newton sequence) only runs when the squared
+// values are within 1e-9 relative of each other; further apart, rounding (1e-16) cannot change the outcome
+__device__ __forceinline__ bool norm2d_lt(double x, double y, double r)
+{
+    const double s = x * x + y * y, r2 = r * r;
+    if (!(r > 0.0)) return false;
+    if (s < r2 * (1.0 - 1e-9)) return true;
+    if (s > r2 * (1.0 + 1e-9)) return false;
+    return sqrt(s) < r;
+}
 
 __device__ __forceinline__ double shfl_d(unsigned mask, double v, int src)
 {
