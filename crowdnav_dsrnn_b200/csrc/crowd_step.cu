@@ -530,10 +530,16 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
         }
     }
     if (cfg.end_goal_changing) {
-        for (int i = 0; i < H; ++i) {
-            const float4 pi_ = s_pv[i];
+        // lane i tests human i (a new goal of an earlier human does not enter a later human's own reached-goal test),
+        // the warp then walks the few humans that did reach their goal in index order
+        bool reached = false;
+        if (lane < H) {
+            const float4 pl = s_pv[lane], gl = s_gr[lane];
+            reached = norm2d_lt((double)gl.x - (double)pl.x, (double)gl.y - (double)pl.y, (double)gl.z);
+        }
+        for (unsigned todo = __ballot_sync(FULL, reached); todo; todo &= todo - 1u) {
+            const int i = __ffs(todo) - 1;
             const float4 gi = s_gr[i];
-            if (!norm2d_lt((double)gi.x - (double)pi_.x, (double)gi.y - (double)pi_.y, (double)gi.z)) continue;
             const uint4 dec = philox4x32(key, RNG_DECISION, (uint32_t)i, su, RNG_GOAL_END);
             if (!(u01(dec.x) <= cfg.end_goal_change_chance)) continue;
             for (int t0 = 0; t0 < cfg.max_goal_tries; t0 += 32) {
@@ -642,8 +648,11 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
         const int group = threadIdx.x / G;
         constexpr int kGroups = STEP_THREADS / G;
         float4 *scratch = s_scr + group * G;
-        for (int task = group; task < ne * H; task += kGroups) {
-            const int el = task / H, i = task - el * H;
+        // (el, i) = divmod(task, H) kept incrementally: one division per thread instead of one per task
+        const int step_el = kGroups / H, step_i = kGroups - step_el * H;
+        int el = group / H, i = group - el * H;
+        for (int task = group; task < ne * H; task += kGroups, el += step_el, i += step_i) {
+            if (i >= H) { i -= H; ++el; }
             const float4 rob = cfg.robot_visible ? s_rob_pv[el] : make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 rrt = cfg.robot_visible ? s_rob_rt[el] : make_float2(0.f, 0.f);
             const float2 nv = orca_group<G>(cfg, g, i, H, s_pv + el * H, s_gr + el * H, s_th + el * H, rob, rrt.x, rrt.y, scratch);
