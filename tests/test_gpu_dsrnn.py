@@ -57,7 +57,9 @@ def test_forward_matches_reference_policy(case, prec):
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
-@pytest.mark.parametrize("H,n", [(5, 1000), (20, 777), (1, 130), (32, 65)])
+# (20, 4000): 329 tile pairs for 74 CTA pairs -> every persistent CTA of the edge kernel walks several tiles (barrier phases wrap);
+# (1, 20000): 157 node tiles for 148 CTAs; (20, 129): odd tile counts in both problems; (3, 1): a single env
+@pytest.mark.parametrize("H,n", [(5, 1000), (20, 777), (1, 130), (32, 65), (20, 4000), (1, 20000), (20, 129), (3, 1)])
 def test_forward_matches_torch_restatement(H, n, prec):
     sd = dsrnn_oracle.random_state_dict(seed=H)
     policy, sd = _policy(H, {k: v.numpy() for k, v in sd.items()})
