@@ -142,21 +142,26 @@ __device__ __forceinline__ void lp3_group(const GroupOps<G> &g, const Line &ln, 
     }
 }
 
+// preferred velocity (orca.py:118-122), Python floats -> narrowed at the rvo2 boundary.  One fp64 sqrt and two fp64
+// divisions per human: computed by ONE thread per human while the CTA stages its envs, not by every lane of the solve.
+__device__ __forceinline__ float2 preferred_velocity(float4 pv, float4 gr)
+{
+    const double gdx = (double)gr.x - (double)pv.x, gdy = (double)gr.y - (double)pv.y;
+    const double gsp = norm2d(gdx, gdy);
+    return make_float2((float)(gsp > 1.0 ? gdx / gsp : gdx), (float)(gsp > 1.0 ? gdy / gsp : gdy));
+}
+
 // One human's ORCA solve by one G-lane group.  s_pv/s_gr/s_th: this env's humans (pre-step).
 template <int G>
 __device__ __forceinline__ float2 orca_group(const CnConfig &cfg, const GroupOps<G> &g, int i, int H,
-                                             const float4 *s_pv, const float4 *s_gr, const float *s_th,
+                                             const float4 *s_pv, const float4 *s_gr, const float *s_th, float2 pref,
                                              float4 rob_pv, float rob_radius, float rob_theta, float4 *s_scratch)
 {
     const float4 me = s_pv[i];
     const float4 me_g = s_gr[i];
     const float radius = (float)((double)me_g.z + 0.01 + (double)cfg.orca_safety_space);
     const float max_speed = me_g.w;
-    // preferred velocity (orca.py:118-122), Python floats -> narrowed at the rvo2 boundary
-    const double gdx = (double)me_g.x - (double)me.x, gdy = (double)me_g.y - (double)me.y;
-    const double gsp = norm2d(gdx, gdy);
-    const float prefx = (float)(gsp > 1.0 ? gdx / gsp : gdx);
-    const float prefy = (float)(gsp > 1.0 ? gdy / gsp : gdy);
+    const float prefx = pref.x, prefy = pref.y;
 
     const int M = H - 1 + (cfg.robot_visible ? 1 : 0);
     const bool have = g.gl < M;
@@ -626,8 +631,10 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
     const size_t base = (size_t)e0 * H;
     const bool need_th = cfg.human_fov < 2.0 * CN_PI && cfg.kinematics != CN_HOLONOMIC;
     for (int k = threadIdx.x; k < ne * H; k += STEP_THREADS) {
-        s_pv[k] = P.a.hum_pv[base + k];
-        s_gr[k] = P.a.hum_gr[base + k];
+        const float4 pv = P.a.hum_pv[base + k], gr = P.a.hum_gr[base + k];
+        s_pv[k] = pv;
+        s_gr[k] = gr;
+        s_nv[k] = preferred_velocity(pv, gr);      // phase A replaces it with the new velocity of the same human
         if (need_th) s_th[k] = P.a.hum_th[base + k];
     }
     if (cfg.robot_visible) {
@@ -655,7 +662,7 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
             if (i >= H) { i -= H; ++el; }
             const float4 rob = cfg.robot_visible ? s_rob_pv[el] : make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 rrt = cfg.robot_visible ? s_rob_rt[el] : make_float2(0.f, 0.f);
-            const float2 nv = orca_group<G>(cfg, g, i, H, s_pv + el * H, s_gr + el * H, s_th + el * H, rob, rrt.x, rrt.y, scratch);
+            const float2 nv = orca_group<G>(cfg, g, i, H, s_pv + el * H, s_gr + el * H, s_th + el * H, s_nv[task], rob, rrt.x, rrt.y, scratch);
             if (g.gl == 0) s_nv[task] = nv;
         }
     }
