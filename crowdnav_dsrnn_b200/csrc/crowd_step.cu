@@ -18,6 +18,7 @@
 // float4 loads; nothing is re-read from HBM.  ORCA arithmetic is fp32 without
 // FMA contraction (bit-identical to a stock x86-64 build of RVO2 and to
 // oracle/orca_core.h); everything the reference does in Python floats is fp64.
+#include <cstdlib>
 #include "env_common.cuh"
 
 #define ORCA_EPS 0.00001f
@@ -690,6 +691,7 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     // envs per CTA: ~2 rounds of ORCA groups per CTA, at most 64 (s_rob_* capacity), at least 8 (one tail warp each)
     int E = (2 * (STEP_THREADS / G) + H - 1) / H;
     E = E < 8 ? 8 : (E > 64 ? 64 : E);
+    if (const char *dbg = getenv("CN_STEP_ENVS_PER_CTA")) { const int v = atoi(dbg); if (v >= 1 && v <= 64) E = v; }   // tuning knob
     const size_t smem = (size_t)E * H * (16 + 16 + 8 + 4) + STEP_THREADS * 16;
     const int grid = (P->n_envs + E - 1) / E;
     switch (G) {

@@ -32,8 +32,8 @@ constexpr int kThreads = 20 * 32;            // 5 warpgroups: 2 epilogue, 2 stag
 constexpr int kRegsEpi = 128, kRegsStage = 96, kRegsMisc = 32;   // setmaxnreg budgets (640 threads start at 96 registers each)
 static_assert(256 * kRegsEpi + 256 * kRegsStage + 128 * kRegsMisc <= 640 * 96, "setmaxnreg only moves registers inside the CTA's launch allocation");
 // mbarrier map
-constexpr int kBarFull = 0, kBarEmpty = kBSlots, kBarAReady = 2 * kBSlots, kBarAFree = kBarAReady + 2,
-              kBarTmemFull = kBarAFree + 2, kBarTmemEmpty = kBarTmemFull + 2, kBarHprev = kBarTmemEmpty + 2, kNumBars = kBarHprev + 1;
+constexpr int kBarFull = 0, kBarEmpty = kBSlots, kBarAReady = 2 * kBSlots, kBarAFree = kBarAReady + 3,
+              kBarTmemFull = kBarAFree + 3, kBarTmemEmpty = kBarTmemFull + 2, kBarHprev = kBarTmemEmpty + 2, kNumBars = kBarHprev + 1;
 
 constexpr int kOffAHi = 0;
 constexpr int kOffALo = kOffAHi + kKBlocks * kABlockBytes;        //  81920
@@ -161,8 +161,10 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
             mbar_init(bar(kBarFull + i), 1);       // leader only: both halves of a weight chunk landed (24 KB of complete_tx)
             mbar_init(bar(kBarEmpty + i), 1);      // MMAs reading the slot retired (commit, both CTAs)
         }
-        mbar_init(bar(kBarAReady), 2 * kStageWarps); mbar_init(bar(kBarAReady + 1), 2 * kStageWarps);   // leader only
-        mbar_init(bar(kBarAFree), 1); mbar_init(bar(kBarAFree + 1), 1);
+        for (int i = 0; i < 3; ++i) {              // A image pieces: k-block 0 (encoded input) | k-blocks 1-2 | k-blocks 3-4
+            mbar_init(bar(kBarAReady + i), 2 * kStageWarps);   // leader only
+            mbar_init(bar(kBarAFree + i), 1);
+        }
         mbar_init(bar(kBarHprev), kEpiWarps);     // this CTA's epilogue warps took h_prev of column tiles 2, 3 out of the A image
         mbar_init(bar(kBarTmemFull), 1); mbar_init(bar(kBarTmemFull + 1), 1);
         mbar_init(bar(kBarTmemEmpty), 2 * kEpiWarps); mbar_init(bar(kBarTmemEmpty + 1), 2 * kEpiWarps);   // leader only
@@ -328,7 +330,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                 x0_l = x[0]; x1_l = x[1];
             }
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {   // hidden units [0,128) (+ the encoded input block), then [128,256)
+            for (int half = 0; half < 2; ++half) {   // hidden units [0,128) = k-blocks 1-2, then [128,256) = k-blocks 3-4
                 float4 hv[16];
 #pragma unroll
                 for (int b = 0; b < 16; ++b) {        // 16 x 512 B in flight per warp before the first conversion
@@ -337,19 +339,15 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     hv[b] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (okb && !DBG(8)) hv[b] = *reinterpret_cast<const float4 *>(a.h_in + (size_t)ridx * 256 + half * 128 + lane * 4);
                 }
-                // the loads above are in flight while the pair's MMAs on the previous tile finish reading k-blocks 0-2 / 3-4
-                PROF_T0(t_f);
-                if (it > 0) {
-                    mbar_wait(bar(kBarAFree + half), (it - 1) & 1u);
-                    if (half) mbar_wait(bar(kBarHprev), (it - 1) & 1u);
-                }
-                PROF_ADD(p_wfree, t_f);
-                PROF_T0(t_s);
+                // the loads above are in flight while the pair's MMAs on the previous tile finish reading the A image; its
+                // pieces are released (and handed back) one by one so the next tile's first MMAs do not wait for all of it
+                if (half == 0) {   // piece 0: encoded input block (k-block 0), no global data needed: lane owns k = 2*lane, 2*lane+1
+                    PROF_T0(t_f0);
+                    if (it > 0) mbar_wait(bar(kBarAFree), (it - 1) & 1u);
+                    PROF_ADD(p_wfree, t_f0);
 #pragma unroll
-                for (int b = 0; b < 16; ++b) {
-                    const int r = sw * 16 + b;
-                    const float mk = __shfl_sync(0xffffffffu, mk_l, b);
-                    if (half == 0) {   // encoded input block (k-block 0): lane owns k = 2*lane, 2*lane+1
+                    for (int b = 0; b < 16; ++b) {
+                        const int r = sw * 16 + b;
                         const float x0 = __shfl_sync(0xffffffffu, x0_l, b), x1 = __shfl_sync(0xffffffffu, x1_l, b);
                         const bool okb = __shfl_sync(0xffffffffu, (int)ok_l, b) != 0;
                         float e[2];
@@ -364,6 +362,21 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                         *reinterpret_cast<uint32_t *>(smem + kOffAHi + off) = hi;
                         if (a.three_pass) *reinterpret_cast<uint32_t *>(smem + kOffALo + off) = lo;
                     }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(ready_remote);
+                }
+                PROF_T0(t_f);
+                if (it > 0) {
+                    mbar_wait(bar(kBarAFree + 1 + half), (it - 1) & 1u);
+                    if (half) mbar_wait(bar(kBarHprev), (it - 1) & 1u);
+                }
+                PROF_ADD(p_wfree, t_f);
+                PROF_T0(t_s);
+#pragma unroll
+                for (int b = 0; b < 16; ++b) {
+                    const int r = sw * 16 + b;
+                    const float mk = __shfl_sync(0xffffffffu, mk_l, b);
                     const int e0 = half * 128 + lane * 4;
                     float4 h4 = hv[b];
                     h4.x *= mk; h4.y *= mk; h4.z *= mk; h4.w *= mk;
@@ -376,7 +389,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                 }
                 fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(ready_remote + 8u * half);   // k-blocks 0-2, then 3-4, of this CTA's rows
+                if (lane == 0) mbar_arrive_cluster(ready_remote + 8u * (1 + half));   // k-blocks 1-2, then 3-4, of this CTA's rows
                 PROF_ADD(p_stage, t_s);
             }
             // pull the NEXT tile's hidden-state rows into L2 while this one is being multiplied (16 rows x 8 lines per warp)
@@ -472,9 +485,9 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     const uint32_t d0 = tmem_base + buf * 256u;
 #pragma unroll 1
                     for (int kb = 0; kb < kKBlocks; ++kb) {
-                        if (ct == 0 && (kb == 0 || kb == 3)) {      // both CTAs' staging warps finished k-blocks 0-2 / 3-4
+                        if (ct == 0 && (kb == 0 || kb == 1 || kb == 3)) {      // both CTAs' staging warps finished k-block 0 / 1-2 / 3-4
                             PROF_T0(twa);
-                            mbar_wait_cluster(bar(kBarAReady + (kb ? 1 : 0)), it & 1u);
+                            mbar_wait_cluster(bar(kBarAReady + (kb == 0 ? 0 : kb == 1 ? 1 : 2)), it & 1u);
                             tc_fence_after();
                             PROF_ADD(p_wa, twa);
                         }
@@ -492,11 +505,12 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                             if (!DBG(2)) mma_kblock(dcol, a_hi, b_lo, false);
                             release_chunk();
                         }
-                        if (ct == kColTiles - 1 && kb == 2) umma2_commit_pair(bar(kBarAFree));       // k-blocks 0-2 of A are free
+                        if (ct == kColTiles - 1 && kb == 0) umma2_commit_pair(bar(kBarAFree));            // k-block 0 of A is free
+                        if (ct == kColTiles - 1 && kb == 2) umma2_commit_pair(bar(kBarAFree + 1));        // k-blocks 1-2 are free
                     }
                     umma2_commit_pair(bar(kBarTmemFull + buf));     // accumulators of this column tile are complete in both CTAs
                 }
-                umma2_commit_pair(bar(kBarAFree + 1));              // every MMA that reads this tile's A image has retired
+                umma2_commit_pair(bar(kBarAFree + 2));              // every MMA that reads this tile's A image has retired
             }
             PROF_ADD(p_total, t_all);
             PROF_OUT(8, p_wa); PROF_OUT(9, p_we); PROF_OUT(10, p_wb); PROF_OUT(11, p_commit); PROF_OUT(12, p_total);
