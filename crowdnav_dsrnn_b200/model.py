@@ -157,15 +157,24 @@ class Policy(nn.Module):
         sd = dict(self.named_parameters())
         return [sd[abi.DSRNN_STATE_DICT_KEYS[f]] for f in abi.DSRNN_WEIGHT_FIELDS]
 
+    def _apply(self, fn, *args, **kwargs):      # .to() / .cuda() / .float(): forget the cached parameter list
+        self.__dict__.pop("_param_list", None)
+        return super()._apply(fn, *args, **kwargs)
+
     def _ensure_handle(self, device):
-        tensors = self._weight_tensors()
-        for t in tensors:
-            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
-                raise _lib.CrowdNavLibraryError("Policy parameters must be contiguous float32 on %s (call .to(device))" % device)
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        # called once per forward, right after the host synchronisation of the previous env step in a train.py-style
+        # loop: keep it to ~40 attribute reads (Parameter objects are stable; their storage / version are not)
+        tensors = self.__dict__.get("_param_list")
+        if tensors is None:
+            tensors = self._weight_tensors()
+            self.__dict__["_param_list"] = tensors
+        key = (device, tuple([(t.data_ptr(), t._version) for t in tensors]))
         lib = _lib.load()
         if self._handle is not None and key == self._weights_key:
             return lib
+        for t in tensors:
+            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise _lib.CrowdNavLibraryError("Policy parameters must be contiguous float32 on %s (call .to(device))" % device)
         w = abi.CnDsrnnWeights(*[_ptr(t) for t in tensors])
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         index = device.index if device.index is not None else torch.cuda.current_device()
@@ -197,7 +206,7 @@ class Policy(nn.Module):
             raise _lib.CrowdNavLibraryError("Policy.act/get_value run on a B200 only; inputs are on %s (no CPU fallback)" % device)
         lib = self._ensure_handle(device)
         N, H = se.shape[0], se.shape[1]
-        f = lambda t: t.detach().to(dtype=torch.float32).contiguous()
+        f = lambda t: t if (t.dtype is torch.float32 and t.is_contiguous()) else t.detach().to(dtype=torch.float32).contiguous()
         rn, te, se = f(rn), f(te), f(se)
         hn, he, mk = f(rnn_hxs["human_node_rnn"]), f(rnn_hxs["human_human_edge_rnn"]), f(masks)
         if hn.numel() != N * 128 or he.numel() != N * (H + 1) * 256 or mk.numel() != N or rn.numel() != N * 7:
@@ -259,14 +268,8 @@ class Policy(nn.Module):
         b = self.base
         N, H = se.shape[0], se.shape[1]
 
-        def gru(mod, x, h):
-            gi = x @ mod.weight_ih_l0.t() + mod.bias_ih_l0
-            gh = h @ mod.weight_hh_l0.t() + mod.bias_hh_l0
-            i_r, i_z, i_n = gi.chunk(3, -1)
-            h_r, h_z, h_n = gh.chunk(3, -1)
-            r, z = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
-            n = torch.tanh(i_n + r * h_n)
-            return (1.0 - z) * n + z * h
+        def gru(mod, x, h):   # one GRU step; ATen's fused cell (two GEMMs + one gate kernel, with autograd)
+            return torch.gru_cell(x, h, mod.weight_ih_l0, mod.weight_hh_l0, mod.bias_ih_l0, mod.bias_hh_l0)
 
         h_edge = h_edge * m.view(N, 1, 1)
         h_node = h_node * m.view(N, 1)
