@@ -39,7 +39,7 @@ WORKLOADS = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from ONE `ncu --set full` capture of the bench loop at the
 # default sizes (profiles/r1_ncu_full_loop_summary.txt); only valid for that workload / batch, else null
-NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 357.97e6 + 307.29e6, "crowd_step_kernel": 17.12e6 + 3.69e6}}
+NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 361.40e6 + 309.38e6, "crowd_step_kernel": 16.97e6 + 4.86e6}}   # profiles/r1_ncu_final_kernels.txt
 
 
 def step_bytes(H):          # algorithmic HBM bytes of the step kernel per env-step
@@ -319,7 +319,7 @@ def run_ours(args, wl):
                  "unit": "GB/s", "kernel": "crowd_step_kernel", "ms_per_launch": step_avg_ms, "traffic": None,
                  "algorithmic_bytes_per_env_step": step_bytes(H), "share_of_step": step_avg_ms / (ms / args.steps)}
     roof_step["frac"] = roof_step["achieved"] / roof_step["peak"]
-    roof_step["note"] = ("ORCA is O(H^2) branchy fp32: at H=20 the kernel is instruction-issue bound (ncu sm__throughput 70 %, "
+    roof_step["note"] = ("ORCA is O(H^2) branchy fp32: at H=20 the kernel is instruction-issue bound (ncu issue slots 75 % busy, "
                          "dram 0.4 %), see profiles/README.md")
     traffic = NCU_TRAFFIC_BYTES.get((args.workload, N), {})
     roof_step["traffic"] = traffic.get("crowd_step_kernel")
