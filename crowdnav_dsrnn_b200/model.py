@@ -223,9 +223,12 @@ class Policy(nn.Module):
                 if t_.numel() != numel or t_.dtype != torch.float32 or t_.device != device or not t_.is_contiguous():
                     raise ValueError("preallocated forward outputs have the wrong shape / dtype / device")
         feat = torch.empty(N, 256, **opts) if need_features else None
-        nbytes = lib.cn_dsrnn_workspace_bytes(N, H)
-        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
-            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        ws_key = (N, H, device)
+        if self.__dict__.get("_workspace_key") != ws_key:
+            nbytes = lib.cn_dsrnn_workspace_bytes(N, H)
+            if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
+                self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self.__dict__["_workspace_key"] = ws_key
         io = abi.CnDsrnnIO(_ptr(rn), _ptr(te), _ptr(se), _ptr(hn), _ptr(he), _ptr(mk), _ptr(hn_out), _ptr(he_out),
                            _ptr(value), _ptr(mean), _ptr(feat))
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
@@ -238,9 +241,24 @@ class Policy(nn.Module):
     def act(self, inputs, rnn_hxs, masks, deterministic=False):
         with torch.no_grad():
             value, mean, _, hn, he = self.cuda_forward(inputs, rnn_hxs, masks, need_features=False)
-            std = self.dist.std().expand_as(mean)
-            action = mean if deterministic else torch.normal(mean, std)
-            log_probs = _normal_log_prob(action, mean, std)
+            # DiagGaussian sample + log-prob (distributions.py:36-45, 85-94) in as few launches as possible -- in a
+            # train.py-style loop this runs on the host's critical path right after the env step's synchronisation:
+            # log N(a; mean, std) = -0.5 sum(eps^2) - sum(logstd) - A/2 log(2 pi) with eps = (a - mean) / std
+            bias = self.dist.logstd._bias
+            cached = self.__dict__.get("_gauss_cache")
+            if cached is None or cached[0] != (bias.data_ptr(), bias._version):      # recomputed after an optimiser step
+                logstd = bias.detach().view(1, -1)
+                const = -logstd.sum() - 0.5 * mean.shape[-1] * math.log(2 * math.pi)      # 0-dim, stays on the device
+                cached = ((bias.data_ptr(), bias._version), const, logstd.exp())
+                self.__dict__["_gauss_cache"] = cached
+            _, const, std = cached
+            if deterministic:
+                action = mean
+                log_probs = const.expand(mean.shape[0], 1)
+            else:
+                eps = torch.randn_like(mean)
+                action = torch.addcmul(mean, eps, std)
+                log_probs = eps.square().sum(-1, keepdim=True).mul_(-0.5).add_(const)
         rnn_hxs["human_node_rnn"] = hn            # the reference mutates the dict it was given (srnn_model.py:481-491)
         rnn_hxs["human_human_edge_rnn"] = he
         return value, action, log_probs, rnn_hxs

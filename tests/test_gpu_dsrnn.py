@@ -80,6 +80,29 @@ def test_forward_matches_torch_restatement(H, n, prec):
     assert _rel_err(hn2.cpu().numpy(), ref["h_node"].numpy()) <= TOL_NET_REL
 
 
+def test_stochastic_act_log_prob_is_the_diag_gaussian_density():
+    """act(deterministic=False): log-prob returned with the sample equals Normal(mean, exp(logstd)).log_prob(action).sum(-1)
+    (distributions.py:36-38), and the samples have the right spread."""
+    sd = dsrnn_oracle.random_state_dict(seed=3)
+    policy, _ = _policy(5, {k: v.numpy() for k, v in sd.items()})
+    with torch.no_grad():
+        policy.dist.logstd._bias.copy_(torch.tensor([[-0.3], [0.2]], device="cuda"))
+    n = 4096
+    g = torch.Generator().manual_seed(11)
+    obs = {"robot_node": torch.randn(n, 1, 7, generator=g).cuda(), "temporal_edges": torch.randn(n, 1, 2, generator=g).cuda(),
+           "spatial_edges": torch.randn(n, 5, 2, generator=g).cuda()}
+    hx = lambda: {"human_node_rnn": torch.zeros(n, 1, 128).cuda(), "human_human_edge_rnn": torch.zeros(n, 6, 256).cuda()}
+    masks = torch.ones(n, 1).cuda()
+    _, mean, _, _ = policy.act(obs, hx(), masks, deterministic=True)
+    torch.manual_seed(5)
+    _, action, lp, _ = policy.act(obs, hx(), masks, deterministic=False)
+    std = policy.dist.logstd._bias.detach().view(1, 2).exp()
+    want = torch.distributions.Normal(mean, std.expand_as(mean)).log_prob(action).sum(-1, keepdim=True)
+    assert lp.shape == (n, 1) and (lp - want).abs().max() < 1e-4
+    z = (action - mean) / std
+    assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1.0) < 0.05
+
+
 def test_cpu_tensors_fail_loudly():
     policy, _ = _policy(5, {k: v.numpy() for k, v in dsrnn_oracle.random_state_dict(1).items()})
     obs = {"robot_node": torch.zeros(2, 1, 7), "temporal_edges": torch.zeros(2, 1, 2), "spatial_edges": torch.zeros(2, 5, 2)}
