@@ -278,7 +278,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     tmem_ld_wait();
                     const int c0 = ct * 64 + c16 * 16;
                     if (ok && !DBG(4)) {
-                        float4 *ho = reinterpret_cast<float4 *>(orow + c0);
+                        float o8[8];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int c = c0 + q * 4;
@@ -286,13 +286,14 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                                          b_z = *reinterpret_cast<const float4 *>(s_bias + 512 + c), b_h = *reinterpret_cast<const float4 *>(s_bias + 768 + c);
                             const float bn[4] = {b_n.x, b_n.y, b_n.z, b_n.w}, br[4] = {b_r.x, b_r.y, b_r.z, b_r.w},
                                         bz[4] = {b_z.x, b_z.y, b_z.z, b_z.w}, bh[4] = {b_h.x, b_h.y, b_h.z, b_h.w};
-                            float o[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int j = q * 4 + i;
-                                o[i] = gru_blend(rg[j] + br[i], zg[j] + bz[i], ni[j] + bn[i], nh[j] + bh[i], hprev[cc * 16 + j]);
+                                o8[(q & 1) * 4 + i] = gru_blend(rg[j] + br[i], zg[j] + bz[i], ni[j] + bn[i], nh[j] + bh[i], hprev[cc * 16 + j]);
                             }
-                            ho[q] = make_float4(o[0], o[1], o[2], o[3]);
+                            // a row is 1 KB away from the next lane's row: every store instruction touches 32 lines, so the
+                            // 32-byte form halves the LSU work of the epilogue
+                            if (q & 1) st_global_v8(orow + c0 + (q - 1) * 4, o8);
                         }
                     }
                 }
