@@ -24,8 +24,9 @@ static int fail(int code, const char *fmt, ...)
         if (err__ != cudaSuccess) return fail(CN_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(err__)); \
     } while (0)
 
-extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, cudaStream_t stream);
-extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, cudaStream_t stream);
+extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, int auto_reset, cudaStream_t stream);
+extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, int mode, cudaStream_t stream);
+enum { CN_RESET_LIVE = 0, CN_RESET_SPARE = 1, CN_RESET_SYNC = 2 };   // crowd_reset.cu
 extern "C" int cn_launch_crowd_observe(const EnvParams *P, const CnObsOut *obs, cudaStream_t stream);
 extern "C" int cn_launch_state_convert(const EnvParams *P, const CnStateView *v, int dir, cudaStream_t stream);
 
@@ -67,7 +68,32 @@ struct CnEnv {
     int device;
     int last_launches;
     EventTimer timer;
+    // spare episodes are generated on an internal stream that forks from / joins the caller's stream with events
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_spare = nullptr;
+    bool refill_pending = false;
 };
+
+// the caller's stream waits for the spare refill that is still in flight (if any)
+static int join_refill(CnEnv *env, cudaStream_t s)
+{
+    if (env->refill_pending) {
+        CN_CUDA(cudaStreamWaitEvent(s, env->ev_spare, 0));
+        env->refill_pending = false;
+    }
+    return CN_OK;
+}
+
+// generate the next episode of every env flagged in need_spare, concurrently with whatever the caller enqueues next
+static int fork_refill(CnEnv *env, cudaStream_t s)
+{
+    CN_CUDA(cudaEventRecord(env->ev_fork, s));
+    CN_CUDA(cudaStreamWaitEvent(env->side, env->ev_fork, 0));
+    CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, nullptr, nullptr, CN_RESET_SPARE, env->side));
+    CN_CUDA(cudaEventRecord(env->ev_spare, env->side));
+    env->refill_pending = true;
+    return CN_OK;
+}
 
 extern "C" const char *cn_last_error(void) { return g_err; }
 extern "C" int cn_abi_version(void) { return CN_ABI_VERSION; }
@@ -118,14 +144,39 @@ extern "C" int cn_env_create(const CnConfig *cfg, int n_envs, int device, void *
     env->device = device;
     env->last_launches = 0;
     cn_carve(&env->p.a, state_dev, n_envs, cfg->human_num);
+    CN_CUDA(cudaSetDevice(device));
+    if (cudaStreamCreateWithFlags(&env->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&env->ev_spare, cudaEventDisableTiming) != cudaSuccess) {
+        cn_env_destroy(env);
+        return fail(CN_ERR_CUDA, "could not create the spare-episode stream / events");
+    }
+    // spare bookkeeping starts empty whatever the caller's buffer holds: no valid spares, nothing flagged
+    const size_t n = (size_t)n_envs;
+    if (cudaMemset(env->p.a.sp_meta, 0, n * sizeof(int4)) != cudaSuccess || cudaMemset(env->p.a.need_spare, 0, n) != cudaSuccess ||
+        cudaMemset(env->p.a.need_sync, 0, n) != cudaSuccess || cudaMemset(env->p.a.sync_count, 0, 4 * sizeof(int)) != cudaSuccess) {
+        cn_env_destroy(env);
+        return fail(CN_ERR_CUDA, "could not clear the spare-episode flags");
+    }
     *out = env;
     return CN_OK;
 }
 
 extern "C" int cn_env_destroy(CnEnv *env)
 {
+    if (!env) return CN_OK;
+    if (env->side) { cudaStreamSynchronize(env->side); cudaStreamDestroy(env->side); }
+    if (env->ev_fork) cudaEventDestroy(env->ev_fork);
+    if (env->ev_spare) cudaEventDestroy(env->ev_spare);
     delete env;
     return CN_OK;
+}
+
+extern "C" int cn_env_join(CnEnv *env, void *stream)
+{
+    if (!env) return fail(CN_ERR_ARG, "env is NULL");
+    CN_CUDA(cudaSetDevice(env->device));
+    return join_refill(env, (cudaStream_t)stream);
 }
 
 static int check_obs(const CnObsOut *obs)
@@ -142,8 +193,12 @@ extern "C" int cn_env_reset(CnEnv *env, const uint8_t *mask_dev, const CnObsOut 
     int rc = check_obs(obs);
     if (rc != CN_OK) return rc;
     CN_CUDA(cudaSetDevice(env->device));
-    CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, obs, mask_dev, (cudaStream_t)stream));
-    env->last_launches = 1;
+    rc = join_refill(env, (cudaStream_t)stream);
+    if (rc != CN_OK) return rc;
+    CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, obs, mask_dev, CN_RESET_LIVE, (cudaStream_t)stream));
+    rc = fork_refill(env, (cudaStream_t)stream);       // the next episodes of the envs that were just reset
+    if (rc != CN_OK) return rc;
+    env->last_launches = 2;
     return CN_OK;
 }
 
@@ -155,13 +210,19 @@ extern "C" int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut 
     if (rc != CN_OK) return rc;
     if (!out->reward || !out->done || !out->event) return fail(CN_ERR_ARG, "CnStepOut needs reward, done and event");
     CN_CUDA(cudaSetDevice(env->device));
+    rc = join_refill(env, (cudaStream_t)stream);        // the step kernel reads (and consumes) the spares
+    if (rc != CN_OK) return rc;
     env->timer.begin((cudaStream_t)stream);
-    CN_CUDA((cudaError_t)cn_launch_crowd_step(&env->p, out, action_dev, (cudaStream_t)stream));
+    CN_CUDA((cudaError_t)cn_launch_crowd_step(&env->p, out, action_dev, auto_reset ? 1 : 0, (cudaStream_t)stream));
     env->timer.end((cudaStream_t)stream);
     env->last_launches = 1;
     if (auto_reset) {
-        CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, &out->obs, out->done, (cudaStream_t)stream));
-        env->last_launches = 2;
+        // finished episodes were replaced by their spares inside the step kernel; the fall-back handles the envs whose
+        // spare was missing (normally none: it exits at once), the refill runs beside the caller's next kernels
+        CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, &out->obs, nullptr, CN_RESET_SYNC, (cudaStream_t)stream));
+        rc = fork_refill(env, (cudaStream_t)stream);
+        if (rc != CN_OK) return rc;
+        env->last_launches = 3;
     }
     return CN_OK;
 }
@@ -181,6 +242,7 @@ static int convert(CnEnv *env, const CnStateView *view, int dir, void *stream)
 {
     if (!env || !view) return fail(CN_ERR_ARG, "env/view is NULL");
     CN_CUDA(cudaSetDevice(env->device));
+    if (join_refill(env, (cudaStream_t)stream) != CN_OK) return CN_ERR_CUDA;      // the refill reads the counters
     CN_CUDA((cudaError_t)cn_launch_state_convert(&env->p, view, dir, (cudaStream_t)stream));
     env->last_launches = 1;
     return CN_OK;

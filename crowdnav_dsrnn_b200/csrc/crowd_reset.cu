@@ -13,41 +13,6 @@
 
 #define RESET_THREADS 256
 
-__device__ __forceinline__ void write_reset_obs(const EnvParams &P, const CnObsOut &obs, int e, int lane, int H,
-                                                float4 rpv, float4 rgr, float theta, bool reset_flag)
-{
-    // generate_ob (crowd_sim_dict.py:72-103) from the state in HBM; reset_flag picks the (15,15,0,0,0.3) belief
-    const CnConfig &cfg = P.cfg;
-    bool vis = false;
-    if (lane < H) {
-        const size_t hi = (size_t)e * H + lane;
-        const float4 hpv = P.a.hum_pv[hi];
-        if (cfg.robot_fov >= 2.0 * CN_PI) vis = !((double)hpv.x - (double)rpv.x == 0.0 && (double)hpv.y - (double)rpv.y == 0.0);
-        else vis = detect_visible_d(cfg.kinematics, rpv.x, rpv.y, rpv.z, rpv.w, theta, hpv.x, hpv.y, cfg.robot_fov);
-        float4 bel;
-        if (vis) { bel = hpv; P.a.hum_br[hi] = P.a.hum_gr[hi].z; }
-        else if (reset_flag) { bel = make_float4(15.0f, 15.0f, 0.0f, 0.0f); P.a.hum_br[hi] = 0.3f; }
-        else {
-            bel = P.a.hum_bel[hi];
-            bel.x = (float)((double)bel.x + (double)bel.z * cfg.time_step);
-            bel.y = (float)((double)bel.y + (double)bel.w * cfg.time_step);
-        }
-        P.a.hum_bel[hi] = bel;
-        if (obs.spatial_edges)
-            reinterpret_cast<float2 *>(obs.spatial_edges)[hi] =
-                make_float2((float)((double)bel.x - (double)rpv.x), (float)((double)bel.y - (double)rpv.y));
-    }
-    const unsigned vis_bits = __ballot_sync(0xffffffffu, vis);
-    if (lane < 7 && obs.robot_node) {
-        const float v = lane == 0 ? rpv.x : lane == 1 ? rpv.y : lane == 2 ? rgr.z : lane == 3 ? rgr.x
-                      : lane == 4 ? rgr.y : lane == 5 ? rgr.w : theta;
-        obs.robot_node[(size_t)e * 7 + lane] = v;
-    } else if (lane >= 7 && lane < 9 && obs.temporal_edges) {
-        obs.temporal_edges[(size_t)e * 2 + (lane - 7)] = lane == 7 ? rpv.z : rpv.w;
-    }
-    if (lane == 0 && obs.visible_mask) obs.visible_mask[e] = vis_bits;
-}
-
 // first thread (in try order) whose candidate is acceptable, over the whole CTA; -1 if none.  s_vote: 4 ints.
 __device__ __forceinline__ int cta_first_ok(bool ok, int *s_vote)
 {
@@ -65,9 +30,17 @@ __device__ __forceinline__ int cta_first_ok(bool ok, int *s_vote)
 // grid: one CTA of RESET_THREADS threads per env (envs whose mask byte is 0 exit at once); thread t evaluates try
 // t, t+RESET_THREADS, ... of each bounded rejection loop, so a typical spawn needs a single round per human.
 // (-DRESET_PROFILE prints per-env cycle counts of the phases; tools/reset_stats.py summarises them.)
+//
+// mode CN_RESET_LIVE   reset the envs whose mask byte is set (all when mask == NULL): cn_env_reset
+// mode CN_RESET_SPARE  generate the NEXT episode of every env flagged in need_spare into the spare arrays, from the
+//                      counters the next reset will see; runs on a side stream, off the critical path
+// mode CN_RESET_SYNC   fall-back of the step kernel: envs flagged in need_sync (their spare was missing or stale, e.g.
+//                      after cn_env_set_state changed the counters); exits at once when sync_count is 0
+enum { CN_RESET_LIVE = 0, CN_RESET_SPARE = 1, CN_RESET_SYNC = 2 };
+
 __global__ void __launch_bounds__(RESET_THREADS)
 crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnObsOut obs,
-                   const uint8_t *__restrict__ mask)
+                   const uint8_t *mask, int mode)
 {
     __shared__ double s_hx[CN_MAX_HUMANS], s_hy[CN_MAX_HUMANS], s_hr[CN_MAX_HUMANS];   // px, py, radius of the humans spawned so far
     // fp32 pre-filter of the min-distance rule against earlier human k: squared distance below s_lo[k] / above s_hi[k]
@@ -78,9 +51,17 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
     const CnConfig &cfg = P.cfg;
     const int H = cfg.human_num;
     const int tid = threadIdx.x, lane = threadIdx.x & 31;
-    const int e = blockIdx.x;
-    if (e >= P.n_envs) return;
-    if (mask && !mask[e]) return;
+    const bool spare = mode == CN_RESET_SPARE;
+    if (mode == CN_RESET_SYNC) {
+        if (P.a.sync_count[0] == 0) return;
+        mask = P.a.need_sync;
+    } else if (spare) {
+        mask = P.a.need_spare;
+    }
+    float4 *dst_pv = spare ? P.a.sp_pv : P.a.hum_pv, *dst_gr = spare ? P.a.sp_gr : P.a.hum_gr;
+    float *dst_th = spare ? P.a.sp_th : P.a.hum_th;
+    for (int e = blockIdx.x; e < P.n_envs; e += gridDim.x) {      // one env per CTA except in the fall-back mode
+    if (mask && !mask[e]) continue;
 #ifdef RESET_PROFILE
     const long long pt0 = clock64();
     long long pt_mid = 0;
@@ -214,9 +195,9 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
             const size_t hi = (size_t)e * H + i;
             s_hx[i] = (double)pv.x; s_hy[i] = (double)pv.y; s_hr[i] = (double)radius_f;
             s_fx[i] = pv.x; s_fy[i] = pv.y;
-            P.a.hum_pv[hi] = pv;
-            P.a.hum_gr[hi] = gr;
-            P.a.hum_th[hi] = (float)c.heading;
+            dst_pv[hi] = pv;
+            dst_gr[hi] = gr;
+            dst_th[hi] = (float)c.heading;
         }
         __syncthreads();
     }
@@ -226,23 +207,43 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
                                      pt1 - pt0, pt_mid - pt1, clock64() - pt_mid, prounds, pq[0], pq[1], pq[2]);
 #endif
     // ---- counters, potential, observation (warp 0 only; its lane 0 wrote the humans above)
-    if (tid >= 32) return;
-    ctr.x = 0;
-    ctr.z = (int)(uint32_t)(((uint64_t)(uint32_t)ctr.z + (uint64_t)cfg.nenv) % cfg.case_size);
-    ctr.w = scenario;
-    ctr.y += 1;
-    __threadfence_block();
-    write_reset_obs(P, obs, e, lane, H, rpv, rgr, (float)rth, true);
-    if (lane == 0) {
-        float4 rx = P.a.rob_x[e];
-        rx.x = (float)rth;
-        rx.y = 0.0f;
-        rx.z = (float)(-fabs(norm2d((double)rpv.x - (double)rgr.x, (double)rpv.y - (double)rgr.y)));
-        rx.w = 0.0f;
-        P.a.rob_pv[e] = rpv;
-        P.a.rob_gr[e] = rgr;
-        P.a.rob_x[e] = rx;
-        P.a.ctr[e] = ctr;
+    if (tid < 32) {
+        if (spare) {
+            if (lane == 0) {
+                P.a.sp_rob_pv[e] = rpv;
+                P.a.sp_rob_gr[e] = rgr;
+                P.a.sp_theta[e] = (float)rth;
+                P.a.sp_meta[e] = make_int4(1, ctr.z, ctr.y, scenario);
+                P.a.need_spare[e] = 0;
+            }
+        } else {
+            ctr.x = 0;
+            ctr.z = (int)(uint32_t)(((uint64_t)(uint32_t)ctr.z + (uint64_t)cfg.nenv) % cfg.case_size);
+            ctr.w = scenario;
+            ctr.y += 1;
+            __threadfence_block();
+            write_reset_obs(P, obs, e, lane, H, rpv, rgr, (float)rth, true);
+            if (lane == 0) {
+                float4 rx = P.a.rob_x[e];
+                rx.x = (float)rth;
+                rx.y = 0.0f;
+                rx.z = (float)(-fabs(norm2d((double)rpv.x - (double)rgr.x, (double)rpv.y - (double)rgr.y)));
+                rx.w = 0.0f;
+                P.a.rob_pv[e] = rpv;
+                P.a.rob_gr[e] = rgr;
+                P.a.rob_x[e] = rx;
+                P.a.ctr[e] = ctr;
+                P.a.sp_meta[e] = make_int4(0, 0, 0, 0);     // the counters moved on: whatever spare there was is stale
+                P.a.need_spare[e] = 1;
+                if (mode == CN_RESET_SYNC) P.a.need_sync[e] = 0;
+            }
+        }
+    }
+    __syncthreads();          // shared arrays are reused by the next env of this CTA (fall-back mode)
+    }
+    if (mode == CN_RESET_SYNC) {          // the last CTA to finish re-arms the counter for the next step
+        __threadfence();
+        if (tid == 0 && atomicAdd(&P.a.sync_count[1], 1) == (int)gridDim.x - 1) { P.a.sync_count[0] = 0; P.a.sync_count[1] = 0; }
     }
 }
 
@@ -310,9 +311,12 @@ __global__ void state_convert_kernel(const __grid_constant__ EnvParams P, const 
     }
 }
 
-extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, cudaStream_t stream)
+extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, int mode, cudaStream_t stream)
 {
-    crowd_reset_kernel<<<P->n_envs, RESET_THREADS, 0, stream>>>(*P, *obs, mask);
+    CnObsOut none = {};
+    // the fall-back normally finds nothing to do: a small grid that strides over the envs keeps its launch cheap
+    const int grid = mode == CN_RESET_SYNC ? (P->n_envs < 592 ? P->n_envs : 592) : P->n_envs;
+    crowd_reset_kernel<<<grid, RESET_THREADS, 0, stream>>>(*P, obs ? *obs : none, mask, mode);
     return (int)cudaGetLastError();
 }
 

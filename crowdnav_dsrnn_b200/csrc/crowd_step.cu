@@ -343,9 +343,52 @@ __device__ __forceinline__ bool goal_collides(const CnConfig &cfg, int H, int i,
     return false;
 }
 
+// Episode over: replace the env's state by its spare episode (= what crowd_reset_kernel would produce from these
+// counters, crowd_reset.cu) and write the reset observation; a missing or stale spare is left to the synchronous
+// fall-back launched after this kernel.  One warp per env.
+__device__ __noinline__ void swap_in_spare(const EnvParams &P, const CnStepOut &out, int e, int lane, int4 ctr)
+{
+    const CnConfig &cfg = P.cfg;
+    const int H = cfg.human_num;
+    const int4 meta = P.a.sp_meta[e];
+    __syncwarp();          // lane 0's goal writes in env_tail are ordered before the other lanes' writes below
+    if (meta.x == 1 && meta.y == ctr.z && meta.z == ctr.y) {
+        if (lane < H) {
+            const size_t hi = (size_t)e * H + lane;
+            P.a.hum_pv[hi] = P.a.sp_pv[hi];
+            P.a.hum_gr[hi] = P.a.sp_gr[hi];
+            P.a.hum_th[hi] = P.a.sp_th[hi];
+        }
+        const float4 npv = P.a.sp_rob_pv[e], ngr = P.a.sp_rob_gr[e];
+        const float nth = P.a.sp_theta[e];
+        ctr.x = 0;
+        ctr.z = (int)(uint32_t)(((uint64_t)(uint32_t)ctr.z + (uint64_t)cfg.nenv) % cfg.case_size);
+        ctr.w = meta.w;
+        ctr.y += 1;
+        __syncwarp();
+        write_reset_obs(P, out.obs, e, lane, H, npv, ngr, nth, true);
+        if (lane == 0) {
+            float4 nx;
+            nx.x = nth;
+            nx.y = 0.0f;
+            nx.z = (float)(-fabs(norm2d((double)npv.x - (double)ngr.x, (double)npv.y - (double)ngr.y)));
+            nx.w = 0.0f;
+            P.a.rob_pv[e] = npv;
+            P.a.rob_gr[e] = ngr;
+            P.a.rob_x[e] = nx;
+            P.a.ctr[e] = ctr;
+            P.a.sp_meta[e] = make_int4(0, 0, 0, 0);
+            P.a.need_spare[e] = 1;
+        }
+    } else if (lane == 0) {
+        P.a.need_sync[e] = 1;
+        atomicAdd(&P.a.sync_count[0], 1);
+    }
+}
+
 // one warp finishes one env: reward/done/info, integration, observation, goal updates
 __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &out, const float *__restrict__ action, int e,
-                                         int lane, float4 *s_pv, float4 *s_gr, const float2 *s_nv)
+                                         int lane, float4 *s_pv, float4 *s_gr, const float2 *s_nv, int auto_reset)
 {
     const CnConfig &cfg = P.cfg;
     const int H = cfg.human_num;
@@ -604,6 +647,10 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
         }
         out.info[(size_t)e * CN_INFO_DIM + lane] = v;
     }
+
+    // ---- episode over: swap the pre-generated spare episode in (out of line: it runs for ~3 % of the envs per step and
+    // must not cost the common path registers)
+    if (done && auto_reset) swap_in_spare(P, out, e, lane, ctr);
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -612,7 +659,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
 template <int G>
 __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS)
 crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnStepOut out,
-                  const float *__restrict__ action, int E)
+                  const float *__restrict__ action, int E, int auto_reset)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const CnConfig &cfg = P.cfg;
@@ -673,7 +720,7 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int el = warp; el < ne; el += STEP_THREADS / 32)
-            env_tail(P, out, action, e0 + el, lane, s_pv + el * H, s_gr + el * H, s_nv + el * H);
+            env_tail(P, out, action, e0 + el, lane, s_pv + el * H, s_gr + el * H, s_nv + el * H, auto_reset);
     }
 }
 
@@ -683,7 +730,7 @@ static inline int pick_group(int M)
 }
 
 // host launcher (called from c_abi.cu)
-extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, cudaStream_t stream)
+extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, int auto_reset, cudaStream_t stream)
 {
     const int H = P->cfg.human_num;
     const int M = H - 1 + (P->cfg.robot_visible ? 1 : 0);
@@ -695,10 +742,10 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     const size_t smem = (size_t)E * H * (16 + 16 + 8 + 4) + STEP_THREADS * 16;
     const int grid = (P->n_envs + E - 1) / E;
     switch (G) {
-    case 4: crowd_step_kernel<4><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E); break;
-    case 8: crowd_step_kernel<8><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E); break;
-    case 16: crowd_step_kernel<16><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E); break;
-    default: crowd_step_kernel<32><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E); break;
+    case 4: crowd_step_kernel<4><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    case 8: crowd_step_kernel<8><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    case 16: crowd_step_kernel<16><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    default: crowd_step_kernel<32><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
     }
     return (int)cudaGetLastError();
 }

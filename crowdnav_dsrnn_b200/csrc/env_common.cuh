@@ -12,6 +12,11 @@
 //   rob_x   float4[N]    theta, desiredVelocity[0], potential, episode_return
 //   rob_acc float2[N]    last_acceleration
 //   ctr     int4  [N]    step_count, scenario_counter, case_counter, current_scenario
+// Spare episodes (crowd_reset.cu): the initial state of every env's NEXT episode is generated ahead of time, off the
+// critical path, and swapped in by the step kernel when the episode ends:
+//   sp_pv / sp_gr / sp_th  [N*H], sp_rob_pv / sp_rob_gr [N], sp_theta [N]   the spawned humans and robot
+//   sp_meta int4[N]        valid, case_counter and scenario_counter the spare was generated for, scenario
+//   need_spare / need_sync uint8[N], sync_count int[4]   work flags for the refill and the synchronous fall-back
 // Humans of one env are contiguous, envs are contiguous: a CTA that owns E
 // consecutive envs reads E*H consecutive float4 (fully coalesced 16 B accesses).
 #pragma once
@@ -27,6 +32,13 @@ struct EnvArrays {
     float4 *rob_pv, *rob_gr, *rob_x;
     float2 *rob_acc;
     int4 *ctr;
+    float4 *sp_pv, *sp_gr;
+    float *sp_th;
+    float4 *sp_rob_pv, *sp_rob_gr;
+    float *sp_theta;
+    int4 *sp_meta;
+    uint8_t *need_spare, *need_sync;
+    int *sync_count;
 };
 
 struct EnvParams {
@@ -58,6 +70,16 @@ static inline size_t cn_carve(EnvArrays *a, void *base, int n, int H)
     CN_TAKE(rob_x, float4, n);
     CN_TAKE(rob_acc, float2, n);
     CN_TAKE(ctr, int4, n);
+    CN_TAKE(sp_pv, float4, nh);
+    CN_TAKE(sp_gr, float4, nh);
+    CN_TAKE(sp_th, float, nh);
+    CN_TAKE(sp_rob_pv, float4, n);
+    CN_TAKE(sp_rob_gr, float4, n);
+    CN_TAKE(sp_theta, float, n);
+    CN_TAKE(sp_meta, int4, n);
+    CN_TAKE(need_spare, uint8_t, n);
+    CN_TAKE(need_sync, uint8_t, n);
+    CN_TAKE(sync_count, int, 4);
 #undef CN_TAKE
     return off;
 }
@@ -130,6 +152,43 @@ __device__ __forceinline__ bool detect_visible_d(int kinematics, double p1x, dou
     if (d != d) return false;
     d = d < -1.0 ? -1.0 : (d > 1.0 ? 1.0 : d);
     return fabs(acos(d)) <= fov / 2.0;
+}
+
+// observation right after a reset (one warp per env, lane i <-> human i); used by the reset kernel and by the step
+// kernel when it swaps a spare episode in
+__device__ __forceinline__ void write_reset_obs(const EnvParams &P, const CnObsOut &obs, int e, int lane, int H,
+                                                float4 rpv, float4 rgr, float theta, bool reset_flag)
+{
+    // generate_ob (crowd_sim_dict.py:72-103) from the state in HBM; reset_flag picks the (15,15,0,0,0.3) belief
+    const CnConfig &cfg = P.cfg;
+    bool vis = false;
+    if (lane < H) {
+        const size_t hi = (size_t)e * H + lane;
+        const float4 hpv = P.a.hum_pv[hi];
+        if (cfg.robot_fov >= 2.0 * CN_PI) vis = !((double)hpv.x - (double)rpv.x == 0.0 && (double)hpv.y - (double)rpv.y == 0.0);
+        else vis = detect_visible_d(cfg.kinematics, rpv.x, rpv.y, rpv.z, rpv.w, theta, hpv.x, hpv.y, cfg.robot_fov);
+        float4 bel;
+        if (vis) { bel = hpv; P.a.hum_br[hi] = P.a.hum_gr[hi].z; }
+        else if (reset_flag) { bel = make_float4(15.0f, 15.0f, 0.0f, 0.0f); P.a.hum_br[hi] = 0.3f; }
+        else {
+            bel = P.a.hum_bel[hi];
+            bel.x = (float)((double)bel.x + (double)bel.z * cfg.time_step);
+            bel.y = (float)((double)bel.y + (double)bel.w * cfg.time_step);
+        }
+        P.a.hum_bel[hi] = bel;
+        if (obs.spatial_edges)
+            reinterpret_cast<float2 *>(obs.spatial_edges)[hi] =
+                make_float2((float)((double)bel.x - (double)rpv.x), (float)((double)bel.y - (double)rpv.y));
+    }
+    const unsigned vis_bits = __ballot_sync(0xffffffffu, vis);
+    if (lane < 7 && obs.robot_node) {
+        const float v = lane == 0 ? rpv.x : lane == 1 ? rpv.y : lane == 2 ? rgr.z : lane == 3 ? rgr.x
+                      : lane == 4 ? rgr.y : lane == 5 ? rgr.w : theta;
+        obs.robot_node[(size_t)e * 7 + lane] = v;
+    } else if (lane >= 7 && lane < 9 && obs.temporal_edges) {
+        obs.temporal_edges[(size_t)e * 2 + (lane - 7)] = lane == 7 ? rpv.z : rpv.w;
+    }
+    if (lane == 0 && obs.visible_mask) obs.visible_mask[e] = vis_bits;
 }
 
 // create_agent_attributes (crowd_sim/envs/crowd_sim.py:296-357) from 6 uniforms

@@ -112,6 +112,11 @@ class CrowdEngine:
         self.launches += self.lib.cn_env_last_launches(self.handle)
         return b
 
+    def join(self):
+        """Make the current stream wait for the spare-episode refill forked by the last reset()/step() (the library joins it
+        by itself at the next call; an explicit join is needed at the end of a CUDA-graph capture)."""
+        _lib.check(self.lib.cn_env_join(self.handle, self._stream()), "cn_env_join")
+
     def observe(self):
         self.cur ^= 1
         b = self.bufs[self.cur]

@@ -1,5 +1,5 @@
-"""CUDA-graph rollout: one deterministic rollout step (`Policy.act` -> `CrowdVecEnv.step`, i.e. train.py:243-261 /
-evaluation.py:119-134 without the host round trips) captured once and replayed.
+"""CUDA-graph rollout: one deterministic rollout step (`CrowdVecEnv.step` -> `Policy.act` on the new observation, i.e. the
+loop of train.py:243-261 / evaluation.py:119-134 without the host round trips) captured once and replayed.
 
 At small batches (BASELINE.json configs[0]/[1]: 16 / 1024 envs) a step is ~15 kernel launches of a few microseconds
 each, so the eager loop is bound by launch latency; a graph replay submits the whole step with one call.  Two graphs are
@@ -19,20 +19,27 @@ class GraphedRollout(object):
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
         self.sets = [dict(h_node=z(n, 1, 128), h_edge=z(n, H + 1, 256), masks=z(n, 1), value=z(n, 1), mean=z(n, 2)) for _ in range(2)]
         cur = eng.cur
-        if hx is not None:
-            self.sets[cur]["h_node"].copy_(hx["human_node_rnn"].reshape(n, 1, 128))
-            self.sets[cur]["h_edge"].copy_(hx["human_human_edge_rnn"].reshape(n, H + 1, 256))
-        if masks is not None:
-            self.sets[cur]["masks"].copy_(masks.reshape(n, 1))
         assert obs["robot_node"].data_ptr() == eng.bufs[cur].robot_node.data_ptr(), "obs must be the engine's current buffer"
-        self.parity = cur                 # which set holds the inputs of the next step
+        hx0 = {"human_node_rnn": z(n, 1, 128) if hx is None else hx["human_node_rnn"].reshape(n, 1, 128),
+               "human_human_edge_rnn": z(n, H + 1, 256) if hx is None else hx["human_human_edge_rnn"].reshape(n, H + 1, 256)}
+        m0 = z(n, 1) if masks is None else masks.reshape(n, 1)
+        self.parity = cur                 # graph p steps the env out of buffer p (action = sets[p]["mean"]) into buffer p ^ 1
         self.graphs = [None, None]
         self.steps = 0
         self.launches_per_step = 0
-        # eager warm-up of both parities (lazy handle / workspace creation must not happen inside a capture)
+        # A captured step is: crowd step (+ swap-in of spare episodes, fork of their refill) -> masks -> forward on the new
+        # observation -> join of the refill, so the spawn of the next episodes runs beside the forward.  The forward of the
+        # FIRST observation therefore happens here, eagerly; it leaves the action in sets[cur] and the hidden state in
+        # sets[cur ^ 1], where graph `cur` expects them.
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), torch.no_grad():
+            a, b = self.sets[cur], self.sets[cur ^ 1]
+            eng.join()
+            b["masks"].copy_(m0)
+            policy.cuda_forward(obs, hx0, m0, need_features=False,
+                                out=dict(h_node=b["h_node"], h_edge=b["h_edge"], value=a["value"], mean=a["mean"]))
+            # eager warm-up of both parities (lazy handle / workspace creation must not happen inside a capture)
             l0 = eng.launches + policy.gpu_launches
             self._one_step(self.parity)
             self.launches_per_step = eng.launches + policy.gpu_launches - l0
@@ -50,13 +57,13 @@ class GraphedRollout(object):
 
     def _one_step(self, p):
         eng, a, b = self.eng, self.sets[p], self.sets[p ^ 1]
-        src = eng.bufs[p]
         with torch.no_grad():
-            self.policy.cuda_forward(src.obs(), {"human_node_rnn": a["h_node"], "human_human_edge_rnn": a["h_edge"]},
-                                     a["masks"], need_features=False,
-                                     out=dict(h_node=b["h_node"], h_edge=b["h_edge"], value=a["value"], mean=a["mean"]))
             dst = eng.step(a["mean"], auto_reset=True)            # flips eng.cur to p ^ 1 and writes bufs[p ^ 1]
             torch.sub(1.0, dst.done.to(torch.float32).unsqueeze(1), out=b["masks"])
+            self.policy.cuda_forward(dst.obs(), {"human_node_rnn": b["h_node"], "human_human_edge_rnn": b["h_edge"]},
+                                     b["masks"], need_features=False,
+                                     out=dict(h_node=a["h_node"], h_edge=a["h_edge"], value=b["value"], mean=b["mean"]))
+            eng.join()
         return dst
 
     def step(self):
@@ -69,5 +76,6 @@ class GraphedRollout(object):
         return self.eng.bufs[self.parity]
 
     def hidden(self):
+        """(hidden state, masks) that belong to the observation of the last step() -- what the next `act` would be given."""
         s = self.sets[self.parity]
         return {"human_node_rnn": s["h_node"], "human_human_edge_rnn": s["h_edge"]}, s["masks"]

@@ -167,6 +167,12 @@ int cn_env_reset(CnEnv *env, const uint8_t *mask_dev, const CnObsOut *obs, void 
 /* CrowdSimDict.step on every env; action_dev [N,2] float32 raw policy output (clip_action is applied inside).
  * auto_reset != 0 reproduces the vec-env worker: done envs are reset and return the reset observation. */
 int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut *out, int auto_reset, void *stream);
+/* cn_env_reset / cn_env_step(auto_reset) also start generating the NEXT episode of the envs that were reset ("spare
+ * episodes": the rejection-sampling spawn of the following reset, crowd_sim.py:359-393) on an internal stream that forks
+ * from `stream`, so that the step kernel can swap a finished episode for its spare without waiting for the spawn.  The
+ * next cn_env_* call joins that work automatically; cn_env_join makes `stream` wait for it explicitly (needed at the end
+ * of a CUDA-graph capture, and before the caller frees or reads the state buffer on another stream). */
+int cn_env_join(CnEnv *env, void *stream);
 int cn_env_set_state(CnEnv *env, const CnStateView *view, void *stream);
 int cn_env_get_state(CnEnv *env, const CnStateView *view, void *stream);
 /* regenerate the observation from the current state without stepping (generate_ob(reset=True) semantics) */
