@@ -128,3 +128,37 @@ def test_rollout_tracks_oracle(kw, steps):
     assert np.abs(st["humans"] - ost.humans).max() <= 1e-4
     assert np.abs(st["robot"] - ost.robot).max() <= 1e-4
     assert n_done > 0
+
+
+def test_spare_and_fallback_resets_track_oracle():
+    """Episodes that end are replaced by their pre-generated spare episode inside the step kernel; envs whose counters
+    were changed behind the spares' back (cn_env_set_state) must fall back to the synchronous reset.  Both paths in one
+    batch, in lock-step with the oracle's plain reset."""
+    n = 512
+    cfg_obj = _cfg(human_num=5)
+    eng = G.make_engine(cfg_obj, n, seed=11)
+    cfg = eng.cfg
+    eng.reset()
+    ost = crowd_oracle.OracleState(n, cfg.human_num)
+    crowd_oracle.reset(cfg, ost, n_threads=8)
+    st = eng.get_state()
+    st["counters"][::2, 2] += 7                      # case_counter of the even envs: their spares are now stale
+    st["counters"][::4, 1] += 1                      # scenario_counter of every fourth env as well
+    eng.set_state(counters=st["counters"])
+    ost.counters[:] = st["counters"].cpu().numpy()
+    rng = np.random.default_rng(9)
+    n_done = np.zeros(n, dtype=np.int64)
+    for t in range(150):
+        act = rng.normal(0, 0.7, (n, 2)).astype(np.float32)
+        buf = eng.step(torch.from_numpy(act).cuda(), auto_reset=True)
+        oout = crowd_oracle.step(cfg, ost, act, auto_reset=True, n_threads=8)
+        out = G.buf_to_numpy(buf)
+        assert np.array_equal(out["done"], oout.done), "step %d" % t
+        assert np.array_equal(out["event"], oout.event), "step %d" % t
+        assert np.abs(out["spatial_edges"] - oout.spatial_edges).max() <= 1e-4, "step %d" % t
+        n_done += out["done"].astype(np.int64)
+    stf = G.state_to_numpy(eng.get_state())
+    assert np.array_equal(stf["counters"], ost.counters)
+    assert np.abs(stf["humans"] - ost.humans).max() <= 1e-4
+    # even envs: fall-back at their first reset, spares afterwards; odd envs: spares only
+    assert (n_done[::2] >= 1).sum() > 100 and (n_done[1::2] >= 1).sum() > 100 and (n_done >= 2).sum() > 20
