@@ -351,7 +351,8 @@ def run_ours(args, wl):
         "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (3-pass split bf16, fp32 accumulate)", "bf16": "bf16", "fp16": "fp16 (fp32 accumulate)"}[args.precision],
         "data": "synthetic scenarios (device reset, counter-based RNG); weights of the shipped checkpoint %s" % wl["weights"],
-        "config": {"workload": wl["label"], "human_num": H, "envs_per_gpu": N, "global_envs": N * world,
+        "config": {"workload": wl["label"] if N == wl["envs_per_gpu"] else wl["label"] + " (overridden: %d envs/GPU)" % N,
+                   "human_num": H, "envs_per_gpu": N, "global_envs": N * world,
                    "parallelism": "env-sharded x%d, no data-path collective" % world, "precision": args.precision,
                    "l2": "inputs larger than L2 (hidden state %.0f MB + env state %.0f MB per step vs 126 MB L2)" % (
                        N * (H + 1) * 256 * 4 * 2 / 1e6, N * step_bytes(H) / 1e6),
