@@ -738,6 +738,11 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     // envs per CTA: ~2 rounds of ORCA groups per CTA, at most 64 (s_rob_* capacity), at least 8 (one tail warp each)
     int E = (2 * (STEP_THREADS / G) + H - 1) / H;
     E = E < 8 ? 8 : (E > 64 ? 64 : E);
+    // small batches (BASELINE configs[0], [1]): a CTA is a latency chain of ~E*H/groups solves plus one tail per warp, and
+    // there are not enough CTAs to fill the GPU anyway -- spread the envs over at least ~4 CTAs per SM
+    static int num_sms = 0;
+    if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    if (num_sms > 0 && P->n_envs < E * 4 * num_sms) { E = P->n_envs / (4 * num_sms); E = E < 1 ? 1 : E; }
     if (const char *dbg = getenv("CN_STEP_ENVS_PER_CTA")) { const int v = atoi(dbg); if (v >= 1 && v <= 64) E = v; }   // tuning knob
     const size_t smem = (size_t)E * H * (16 + 16 + 8 + 4) + STEP_THREADS * 16;
     const int grid = (P->n_envs + E - 1) / E;
