@@ -8,7 +8,7 @@ CrowdSim.configure (crowd_sim/envs/crowd_sim.py:93-246) and Agent.__init__
 import ctypes as C
 import math
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_HUMANS = 32
 MAX_SCENARIOS = 8
 STEP_TABLE_WORDS = 128
@@ -70,7 +70,8 @@ class CnObsOut(C.Structure):
 
 class CnStepOut(C.Structure):
     _fields_ = [("obs", CnObsOut), ("reward", _fp), ("done", _fp), ("event", _fp), ("scenario", _fp),
-                ("info", _fp), ("episode_return", _fp), ("episode_length", _fp), ("goal_changed", _fp)]
+                ("info", _fp), ("episode_return", _fp), ("episode_length", _fp), ("goal_changed", _fp),
+                ("not_done", _fp)]
 
 
 DSRNN_WEIGHT_FIELDS = [

@@ -623,6 +623,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
         P.a.ctr[e] = ctr;
         out.reward[e] = (float)reward;
         out.done[e] = (uint8_t)done;
+        if (out.not_done) out.not_done[e] = done ? 0.0f : 1.0f;
         out.event[e] = event;
         if (out.scenario) out.scenario[e] = ctr.w;
         if (out.episode_return) out.episode_return[e] = rx.w;

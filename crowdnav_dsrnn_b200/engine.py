@@ -36,11 +36,12 @@ class StepBuffers:
         self.episode_return = torch.zeros(n, **f32)
         self.episode_length = torch.zeros(n, dtype=torch.int32, device=device)
         self.goal_changed = torch.zeros(n, dtype=torch.int32, device=device)
+        self.not_done = torch.ones(n, 1, **f32)            # 1 - done: the masks of the next Policy.act
         self.obs_struct = abi.CnObsOut(_ptr(self.robot_node), _ptr(self.temporal_edges), _ptr(self.spatial_edges),
                                        _ptr(self.visible_mask))
         self.step_struct = abi.CnStepOut(self.obs_struct, _ptr(self.reward), _ptr(self.done), _ptr(self.event),
                                          _ptr(self.scenario), _ptr(self.info), _ptr(self.episode_return),
-                                         _ptr(self.episode_length), _ptr(self.goal_changed))
+                                         _ptr(self.episode_length), _ptr(self.goal_changed), _ptr(self.not_done))
 
     def obs(self):
         return {"robot_node": self.robot_node, "temporal_edges": self.temporal_edges,

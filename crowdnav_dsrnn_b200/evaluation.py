@@ -61,7 +61,7 @@ def evaluate_batched(actor_critic, config, device, episodes=None, seed=None, det
         length = torch.where(first, buf.episode_length, length)
         ret = torch.where(first, buf.episode_return, ret)
         finished |= first
-        masks = (1.0 - done.to(torch.float32)).unsqueeze(1)
+        masks = buf.not_done                                        # 1 - done, written by the step kernel
         if bool(finished.all()):
             break
     venv.close()

@@ -59,7 +59,7 @@ class GraphedRollout(object):
         eng, a, b = self.eng, self.sets[p], self.sets[p ^ 1]
         with torch.no_grad():
             dst = eng.step(a["mean"], auto_reset=True)            # flips eng.cur to p ^ 1 and writes bufs[p ^ 1]
-            torch.sub(1.0, dst.done.to(torch.float32).unsqueeze(1), out=b["masks"])
+            b["masks"] = dst.not_done                             # 1 - done, written by the step kernel itself
             self.policy.cuda_forward(dst.obs(), {"human_node_rnn": b["h_node"], "human_human_edge_rnn": b["h_edge"]},
                                      b["masks"], need_features=False,
                                      out=dict(h_node=a["h_node"], h_edge=a["h_edge"], value=b["value"], mean=b["mean"]))

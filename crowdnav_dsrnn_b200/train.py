@@ -75,8 +75,7 @@ def train(config, device=None, num_updates=None, output_dir=None, actor_critic=N
                                   ((buf.event == abi.EV_COLLISION).to(torch.float64) * d).sum(),
                                   ((buf.event == abi.EV_TIMEOUT).to(torch.float64) * d).sum(), d.sum(),
                                   (buf.episode_return.to(torch.float64) * d).sum()])
-            masks = 1.0 - done.to(torch.float32)
-            rollouts.insert(obs, hx, action, log_prob, value, reward, masks, None)
+            rollouts.insert(obs, hx, action, log_prob, value, reward, buf.not_done, None)     # masks = 1 - done
         next_value = actor_critic.get_value(rollouts.obs_at(-1), dict(rollouts.hidden_at(-1)), rollouts.masks[-1]).detach()
         rollouts.compute_returns(next_value, config.ppo.use_gae, config.reward.gamma, config.ppo.gae_lambda,
                                  config.training.use_proper_time_limits)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CN_ABI_VERSION 1
+#define CN_ABI_VERSION 2
 #define CN_MAX_HUMANS 32          /* one 32-lane group per ORCA solve */
 #define CN_MAX_SCENARIOS 8
 #define CN_STEP_TABLE_WORDS 128   /* bit table over step indices: up to 4096 steps per episode */
@@ -136,6 +136,7 @@ typedef struct CnStepOut {
     float *episode_return;  /* [N] valid where done */
     int32_t *episode_length;/* [N] valid where done */
     uint32_t *goal_changed; /* [N] bit i: human i was given a new goal after this step (may be NULL) */
+    float *not_done;        /* [N] 1.0f - done: the `masks` of the next Policy.act (train.py:279), may be NULL */
 } CnStepOut;
 
 /* columns of CnStepOut.info (step_info keys, crowd_sim.py:973-1030) */
