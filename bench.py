@@ -255,6 +255,7 @@ def run_ours(args, wl):
         launches = args.steps * roll.launches_per_step
         obs = buf.obs()
         hx, masks = roll.hidden()
+        roll.close()
         hx = {k: v.clone() for k, v in hx.items()}
         masks = masks.clone()
     clocks = sampler.stop() if rank == 0 else None

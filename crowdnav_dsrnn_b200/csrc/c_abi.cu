@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include "env_common.cuh"
 #include "dsrnn.cuh"
@@ -26,7 +27,7 @@ static int fail(int code, const char *fmt, ...)
 
 extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, int auto_reset, cudaStream_t stream);
 extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, int mode, cudaStream_t stream);
-enum { CN_RESET_LIVE = 0, CN_RESET_SPARE = 1, CN_RESET_SYNC = 2 };   // crowd_reset.cu
+enum { CN_RESET_LIVE = 0, CN_RESET_SPARE = 1, CN_RESET_SYNC = 2, CN_RESET_SPARE_LIST = 3 };   // crowd_reset.cu
 extern "C" int cn_launch_crowd_observe(const EnvParams *P, const CnObsOut *obs, cudaStream_t stream);
 extern "C" int cn_launch_state_convert(const EnvParams *P, const CnStateView *v, int dir, cudaStream_t stream);
 
@@ -85,11 +86,11 @@ static int join_refill(CnEnv *env, cudaStream_t s)
 }
 
 // generate the next episode of every env flagged in need_spare, concurrently with whatever the caller enqueues next
-static int fork_refill(CnEnv *env, cudaStream_t s)
+static int fork_refill(CnEnv *env, cudaStream_t s, int mode = CN_RESET_SPARE_LIST)
 {
     CN_CUDA(cudaEventRecord(env->ev_fork, s));
     CN_CUDA(cudaStreamWaitEvent(env->side, env->ev_fork, 0));
-    CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, nullptr, nullptr, CN_RESET_SPARE, env->side));
+    CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, nullptr, nullptr, mode, env->side));
     CN_CUDA(cudaEventRecord(env->ev_spare, env->side));
     env->refill_pending = true;
     return CN_OK;
@@ -172,6 +173,15 @@ extern "C" int cn_env_destroy(CnEnv *env)
     return CN_OK;
 }
 
+extern "C" int cn_env_refill(CnEnv *env, void *stream)
+{
+    if (!env) return fail(CN_ERR_ARG, "env is NULL");
+    CN_CUDA(cudaSetDevice(env->device));
+    int rc = join_refill(env, (cudaStream_t)stream);      // never two refills in flight
+    if (rc != CN_OK) return rc;
+    return fork_refill(env, (cudaStream_t)stream);
+}
+
 extern "C" int cn_env_join(CnEnv *env, void *stream)
 {
     if (!env) return fail(CN_ERR_ARG, "env is NULL");
@@ -196,7 +206,7 @@ extern "C" int cn_env_reset(CnEnv *env, const uint8_t *mask_dev, const CnObsOut 
     rc = join_refill(env, (cudaStream_t)stream);
     if (rc != CN_OK) return rc;
     CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, obs, mask_dev, CN_RESET_LIVE, (cudaStream_t)stream));
-    rc = fork_refill(env, (cudaStream_t)stream);       // the next episodes of the envs that were just reset
+    rc = fork_refill(env, (cudaStream_t)stream, CN_RESET_SPARE);       // the next episodes of the envs that were just reset
     if (rc != CN_OK) return rc;
     env->last_launches = 2;
     return CN_OK;
@@ -210,6 +220,11 @@ extern "C" int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut 
     if (rc != CN_OK) return rc;
     if (!out->reward || !out->done || !out->event) return fail(CN_ERR_ARG, "CnStepOut needs reward, done and event");
     CN_CUDA(cudaSetDevice(env->device));
+    {   // development switches for timing experiments (never set in tests / bench): 1 = no auto-reset at all, 2 = no spare refill
+        static const int dbg = getenv("CN_DEBUG_RESET") ? atoi(getenv("CN_DEBUG_RESET")) : 0;
+        if (dbg == 1) auto_reset = 0;
+        if (dbg == 2 && auto_reset) auto_reset = 3;
+    }
     rc = join_refill(env, (cudaStream_t)stream);        // the step kernel reads (and consumes) the spares
     if (rc != CN_OK) return rc;
     env->timer.begin((cudaStream_t)stream);
@@ -220,9 +235,12 @@ extern "C" int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut 
         // finished episodes were replaced by their spares inside the step kernel; the fall-back handles the envs whose
         // spare was missing (normally none: it exits at once), the refill runs beside the caller's next kernels
         CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, &out->obs, nullptr, CN_RESET_SYNC, (cudaStream_t)stream));
-        rc = fork_refill(env, (cudaStream_t)stream);
-        if (rc != CN_OK) return rc;
-        env->last_launches = 3;
+        env->last_launches = 2;
+        if (auto_reset == 1) {                         // 2: the caller (or the forward, cn_dsrnn_set_refill_env) starts the refill
+            rc = fork_refill(env, (cudaStream_t)stream);
+            if (rc != CN_OK) return rc;
+            env->last_launches = 3;
+        }
     }
     return CN_OK;
 }
@@ -326,6 +344,13 @@ extern "C" int cn_dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnD
 }
 
 extern "C" int cn_dsrnn_last_launches(const CnDsrnn *m) { return m ? dsrnn_last_launches(m) : 0; }
+extern "C" int cn_dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env)
+{
+    if (!m) return fail(CN_ERR_ARG, "model is NULL");
+    dsrnn_set_refill_env(m, env);
+    return CN_OK;
+}
+
 extern "C" int cn_dsrnn_enable_timing(CnDsrnn *m, int enable)
 {
     if (!m) return fail(CN_ERR_ARG, "model is NULL");

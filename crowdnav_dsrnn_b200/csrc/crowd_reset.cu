@@ -36,7 +36,9 @@ __device__ __forceinline__ int cta_first_ok(bool ok, int *s_vote)
 //                      counters the next reset will see; runs on a side stream, off the critical path
 // mode CN_RESET_SYNC   fall-back of the step kernel: envs flagged in need_sync (their spare was missing or stale, e.g.
 //                      after cn_env_set_state changed the counters); exits at once when sync_count is 0
-enum { CN_RESET_LIVE = 0, CN_RESET_SPARE = 1, CN_RESET_SYNC = 2 };
+// mode CN_RESET_SPARE_LIST  like CN_RESET_SPARE for the envs in refill_list (appended by the step kernel / the fall-back):
+//                      a small grid instead of one (mostly idle) CTA per env
+enum { CN_RESET_LIVE = 0, CN_RESET_SPARE = 1, CN_RESET_SYNC = 2, CN_RESET_SPARE_LIST = 3 };
 
 __global__ void __launch_bounds__(RESET_THREADS)
 crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnObsOut obs,
@@ -51,16 +53,23 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
     const CnConfig &cfg = P.cfg;
     const int H = cfg.human_num;
     const int tid = threadIdx.x, lane = threadIdx.x & 31;
-    const bool spare = mode == CN_RESET_SPARE;
+    const bool spare = mode == CN_RESET_SPARE || mode == CN_RESET_SPARE_LIST;
+    const int *list = nullptr;
+    int limit = P.n_envs;
     if (mode == CN_RESET_SYNC) {
         if (P.a.sync_count[0] == 0) return;
         mask = P.a.need_sync;
+    } else if (mode == CN_RESET_SPARE_LIST) {
+        list = P.a.refill_list;
+        limit = P.a.sync_count[2];
+        mask = nullptr;
     } else if (spare) {
         mask = P.a.need_spare;
     }
     float4 *dst_pv = spare ? P.a.sp_pv : P.a.hum_pv, *dst_gr = spare ? P.a.sp_gr : P.a.hum_gr;
     float *dst_th = spare ? P.a.sp_th : P.a.hum_th;
-    for (int e = blockIdx.x; e < P.n_envs; e += gridDim.x) {      // one env per CTA except in the fall-back mode
+    for (int it = blockIdx.x; it < limit; it += gridDim.x) {      // one env per CTA in the full-grid modes
+    const int e = list ? list[it] : it;
     if (mask && !mask[e]) continue;
 #ifdef RESET_PROFILE
     const long long pt0 = clock64();
@@ -234,8 +243,12 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
                 P.a.rob_x[e] = rx;
                 P.a.ctr[e] = ctr;
                 P.a.sp_meta[e] = make_int4(0, 0, 0, 0);     // the counters moved on: whatever spare there was is stale
-                P.a.need_spare[e] = 1;
-                if (mode == CN_RESET_SYNC) P.a.need_sync[e] = 0;
+                if (mode == CN_RESET_SYNC) {
+                    P.a.need_sync[e] = 0;
+                    P.a.refill_list[atomicAdd(&P.a.sync_count[2], 1)] = e;
+                } else {
+                    P.a.need_spare[e] = 1;
+                }
             }
         }
     }
@@ -244,6 +257,9 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
     if (mode == CN_RESET_SYNC) {          // the last CTA to finish re-arms the counter for the next step
         __threadfence();
         if (tid == 0 && atomicAdd(&P.a.sync_count[1], 1) == (int)gridDim.x - 1) { P.a.sync_count[0] = 0; P.a.sync_count[1] = 0; }
+    } else if (mode == CN_RESET_SPARE_LIST) {
+        __threadfence();
+        if (tid == 0 && atomicAdd(&P.a.sync_count[3], 1) == (int)gridDim.x - 1) { P.a.sync_count[2] = 0; P.a.sync_count[3] = 0; }
     }
 }
 
@@ -315,7 +331,8 @@ extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, co
 {
     CnObsOut none = {};
     // the fall-back normally finds nothing to do: a small grid that strides over the envs keeps its launch cheap
-    const int grid = mode == CN_RESET_SYNC ? (P->n_envs < 592 ? P->n_envs : 592) : P->n_envs;
+    const int small = mode == CN_RESET_SPARE_LIST ? 1184 : 592;
+    const int grid = (mode == CN_RESET_SYNC || mode == CN_RESET_SPARE_LIST) ? (P->n_envs < small ? P->n_envs : small) : P->n_envs;
     crowd_reset_kernel<<<grid, RESET_THREADS, 0, stream>>>(*P, obs ? *obs : none, mask, mode);
     return (int)cudaGetLastError();
 }

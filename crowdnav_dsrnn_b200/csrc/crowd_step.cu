@@ -378,7 +378,7 @@ __device__ __noinline__ void swap_in_spare(const EnvParams &P, const CnStepOut &
             P.a.rob_x[e] = nx;
             P.a.ctr[e] = ctr;
             P.a.sp_meta[e] = make_int4(0, 0, 0, 0);
-            P.a.need_spare[e] = 1;
+            P.a.refill_list[atomicAdd(&P.a.sync_count[2], 1)] = e;
         }
     } else if (lane == 0) {
         P.a.need_sync[e] = 1;

@@ -13,4 +13,5 @@ const char *dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnDsrnnIO
                           void *workspace, cudaStream_t stream);
 int dsrnn_last_launches(const CnDsrnn *m);
 void dsrnn_enable_timing(CnDsrnn *m, int enable);
+void dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env);
 float dsrnn_time_ms(CnDsrnn *m, int *count);

@@ -32,6 +32,7 @@ struct CnDsrnn {
     void *tc_state;   // packed bf16 weights of the tensor-core edge stage (dsrnn_edge_tc.cu)
     void *node_state = nullptr;   // packed weights of the fused node / heads kernel (dsrnn_node_tc.cu)
     bool unfused_node = false;    // CN_NODE_UNFUSED=1: one launch per layer (development A/B switch)
+    CnEnv *refill_env = nullptr;  // cn_dsrnn_set_refill_env: start this env's spare-episode refill beside the attention kernel
     bool timing;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;   // events around the edge stage
     int num_sms;
@@ -475,6 +476,7 @@ const char *dsrnn_update_weights(CnDsrnn *m, const CnDsrnnWeights *w, cudaStream
 }
 
 int dsrnn_last_launches(const CnDsrnn *m) { return m->last_launches; }
+void dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env) { m->refill_env = env; }
 
 // one linear layer, on CUDA cores (fp32) or tensor cores (bf16x3 / bf16)
 struct LinearRun {
@@ -544,6 +546,9 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
         TcLinearCall q = call(io->h_edge_out, 256, N, ws.qt, 256, ACT_NONE);
         q.rows_per_env = 1; q.env_stride_rows = H + 1; q.first_row = 0;
         run(m->att_qt, m->att_wc, m->att_bc, q, 256, 256);
+        // the attention kernel is bandwidth-bound with a small footprint: the one place in this forward where the env's
+        // spare-episode refill (crowd_reset.cu) can share the SMs instead of waiting for them or making others wait
+        if (m->refill_env && cn_env_refill(m->refill_env, s) != CN_OK) return "cn_env_refill (refill hook) failed";
         attention_kernel<<<(N + 3) / 4, 128, 0, s>>>(io->h_edge_out, ws.qt, ws.cat, N, H);
         ++launches;
     }

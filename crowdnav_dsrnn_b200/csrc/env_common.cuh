@@ -16,7 +16,8 @@
 // critical path, and swapped in by the step kernel when the episode ends:
 //   sp_pv / sp_gr / sp_th  [N*H], sp_rob_pv / sp_rob_gr [N], sp_theta [N]   the spawned humans and robot
 //   sp_meta int4[N]        valid, case_counter and scenario_counter the spare was generated for, scenario
-//   need_spare / need_sync uint8[N], sync_count int[4]   work flags for the refill and the synchronous fall-back
+//   need_spare / need_sync uint8[N], sync_count int[4], refill_list int[N]   work flags / list for the refill and the
+//                          synchronous fall-back
 // Humans of one env are contiguous, envs are contiguous: a CTA that owns E
 // consecutive envs reads E*H consecutive float4 (fully coalesced 16 B accesses).
 #pragma once
@@ -38,7 +39,8 @@ struct EnvArrays {
     float *sp_theta;
     int4 *sp_meta;
     uint8_t *need_spare, *need_sync;
-    int *sync_count;
+    int *sync_count;          // [0] envs flagged in need_sync, [1] CTAs done (sync), [2] entries of refill_list, [3] CTAs done (refill)
+    int *refill_list;         // envs whose spare was consumed by the last step (compact: the refill launches a small grid)
 };
 
 struct EnvParams {
@@ -80,6 +82,7 @@ static inline size_t cn_carve(EnvArrays *a, void *base, int n, int H)
     CN_TAKE(need_spare, uint8_t, n);
     CN_TAKE(need_sync, uint8_t, n);
     CN_TAKE(sync_count, int, 4);
+    CN_TAKE(refill_list, int, n);
 #undef CN_TAKE
     return off;
 }

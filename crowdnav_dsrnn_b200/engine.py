@@ -78,6 +78,10 @@ class CrowdEngine:
 
     def close(self):
         if getattr(self, "handle", None):
+            for ref in self.__dict__.pop("_refill_policies", []):      # forwards must not call into a destroyed env
+                policy = ref()
+                if policy is not None and policy.__dict__.get("_refill_engine") is self:
+                    policy.start_refill_of(None)
             self.lib.cn_env_destroy(self.handle)
             self.handle = None
 
@@ -100,16 +104,17 @@ class CrowdEngine:
         self.launches += self.lib.cn_env_last_launches(self.handle)
         return b
 
-    def step(self, action, auto_reset=True):
-        """CrowdSimDict.step on every env; action [N,2] float32 on the device."""
+    def step(self, action, auto_reset=True, defer_refill=False):
+        """CrowdSimDict.step on every env; action [N,2] float32 on the device.  `defer_refill`: the spare-episode refill is
+        started by the next forward (Policy.start_refill_of) instead of right behind the step kernel."""
         if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous():
             action = action.to(device=self.device, dtype=torch.float32).contiguous()
         if action.numel() != 2 * self.n:
             raise ValueError("action must have shape [%d, 2]" % self.n)
         self.cur ^= 1
         b = self.bufs[self.cur]
-        _lib.check(self.lib.cn_env_step(self.handle, _ptr(action), C.byref(b.step_struct), int(bool(auto_reset)),
-                                        self._stream()), "cn_env_step")
+        mode = (2 if defer_refill else 1) if auto_reset else 0
+        _lib.check(self.lib.cn_env_step(self.handle, _ptr(action), C.byref(b.step_struct), mode, self._stream()), "cn_env_step")
         self.launches += self.lib.cn_env_last_launches(self.handle)
         return b
 

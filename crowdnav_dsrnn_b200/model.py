@@ -15,6 +15,7 @@ with differentiable torch ops over the T x N rollout chunk.
 """
 import ctypes as C
 import math
+import weakref
 
 import torch
 import torch.nn as nn
@@ -182,6 +183,9 @@ class Policy(nn.Module):
             handle = C.c_void_p()
             _lib.check(lib.cn_dsrnn_create(C.byref(w), index, stream, C.byref(handle)), "cn_dsrnn_create")
             self._handle = handle
+            hook = self.__dict__.get("_refill_engine")
+            if hook is not None:
+                _lib.check(lib.cn_dsrnn_set_refill_env(handle, hook.handle), "cn_dsrnn_set_refill_env")
         else:
             _lib.check(lib.cn_dsrnn_update_weights(self._handle, C.byref(w), stream), "cn_dsrnn_update_weights")
         self._weights_key = key
@@ -195,6 +199,16 @@ class Policy(nn.Module):
                 _lib.load().cn_dsrnn_destroy(handle)
         except Exception:  # noqa: BLE001
             pass
+
+    def start_refill_of(self, engine):
+        """Let every forward start `engine`'s spare-episode refill beside its attention kernel (pair with
+        `engine.step(..., defer_refill=True)`; used by rollout.GraphedRollout).  `engine=None` clears the hook."""
+        self.__dict__["_refill_engine"] = engine
+        if engine is not None:
+            engine.__dict__.setdefault("_refill_policies", []).append(weakref.ref(self))
+        if self._handle is not None:
+            _lib.check(_lib.load().cn_dsrnn_set_refill_env(self._handle, engine.handle if engine is not None else None),
+                       "cn_dsrnn_set_refill_env")
 
     def cuda_forward(self, inputs, rnn_hxs, masks, need_features=True, out=None):
         """One rollout-step forward on the GPU. Returns (value[N,1], mean[N,2], features[N,256]|None, h_node, h_edge).

@@ -39,6 +39,8 @@ class GraphedRollout(object):
             b["masks"].copy_(m0)
             policy.cuda_forward(obs, hx0, m0, need_features=False,
                                 out=dict(h_node=b["h_node"], h_edge=b["h_edge"], value=a["value"], mean=a["mean"]))
+            eng.join()
+            policy.start_refill_of(eng)        # from here on the forward starts the refill of the step before it
             # eager warm-up of both parities (lazy handle / workspace creation must not happen inside a capture)
             l0 = eng.launches + policy.gpu_launches
             self._one_step(self.parity)
@@ -58,7 +60,7 @@ class GraphedRollout(object):
     def _one_step(self, p):
         eng, a, b = self.eng, self.sets[p], self.sets[p ^ 1]
         with torch.no_grad():
-            dst = eng.step(a["mean"], auto_reset=True)            # flips eng.cur to p ^ 1 and writes bufs[p ^ 1]
+            dst = eng.step(a["mean"], auto_reset=True, defer_refill=True)   # flips eng.cur to p ^ 1, writes bufs[p ^ 1]
             b["masks"] = dst.not_done                             # 1 - done, written by the step kernel itself
             self.policy.cuda_forward(dst.obs(), {"human_node_rnn": b["h_node"], "human_human_edge_rnn": b["h_edge"]},
                                      b["masks"], need_features=False,
@@ -74,6 +76,11 @@ class GraphedRollout(object):
         self.eng.cur = self.parity
         self.steps += 1
         return self.eng.bufs[self.parity]
+
+    def close(self):
+        """Detach the forward from the env: eager `act` / `step` calls behave as usual afterwards."""
+        self.policy.start_refill_of(None)
+        self.eng.join()
 
     def hidden(self):
         """(hidden state, masks) that belong to the observation of the last step() -- what the next `act` would be given."""

@@ -174,6 +174,9 @@ int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut *out, int a
  * next cn_env_* call joins that work automatically; cn_env_join makes `stream` wait for it explicitly (needed at the end
  * of a CUDA-graph capture, and before the caller frees or reads the state buffer on another stream). */
 int cn_env_join(CnEnv *env, void *stream);
+/* Start the refill at the current position of `stream` (what cn_env_step does by itself unless it was called with
+ * auto_reset == 2 = "reset, but somebody else starts the refill"). */
+int cn_env_refill(CnEnv *env, void *stream);
 int cn_env_set_state(CnEnv *env, const CnStateView *view, void *stream);
 int cn_env_get_state(CnEnv *env, const CnStateView *view, void *stream);
 /* regenerate the observation from the current state without stepping (generate_ob(reset=True) semantics) */
@@ -227,6 +230,11 @@ int cn_dsrnn_update_weights(CnDsrnn *m, const CnDsrnnWeights *w, void *stream);
 size_t cn_dsrnn_workspace_bytes(int n_envs, int human_num);
 int cn_dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnDsrnnIO *io, int precision,
                      void *workspace_dev, size_t workspace_bytes, void *stream);
+/* A rollout that runs the forward right after the env step can let the FORWARD start the env's spare-episode refill, at
+ * the point where it hurts least: next to the bandwidth-bound attention kernel (the refill's CTAs cannot share an SM with
+ * the persistent tensor-core kernels, whose register / shared-memory footprint is a whole SM).  Pair
+ * cn_dsrnn_set_refill_env(m, env) with cn_env_step(..., auto_reset = 2, ...); env == NULL clears it. */
+int cn_dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env);
 /* number of kernels the last forward / step call launched (bench.py's gpu_launches claim) */
 int cn_dsrnn_last_launches(const CnDsrnn *m);
 int cn_env_last_launches(const CnEnv *env);
