@@ -237,8 +237,9 @@ def run_ours(args, wl):
         barrier()
         launches = eng.launches + policy.gpu_launches - launches0
     else:
-        # the timed loop replays the rollout step (forward -> action -> crowd step -> reset) as a CUDA graph: the kernels
-        # and the data flow are those of the eager loop (tests/test_gpu_rollout_graph.py), only the launch path differs
+        # the timed loop replays the rollout step (crowd step incl. swap-in of spare episodes -> forward on the new observation,
+        # with the refill of the consumed spares forked beside the attention kernel) as a CUDA graph: the kernels and the
+        # data flow are those of the eager loop (tests/test_gpu_rollout_graph.py), only the launch path differs
         roll = GraphedRollout(policy, venv, obs, hx, masks)
         for _ in range(max(3, args.warmup)):
             roll.step()
