@@ -158,6 +158,18 @@ class Policy(nn.Module):
         sd = dict(self.named_parameters())
         return [sd[abi.DSRNN_STATE_DICT_KEYS[f]] for f in abi.DSRNN_WEIGHT_FIELDS]
 
+    _TRANSIENT = ("_handle", "_weights_key", "_workspace", "_workspace_key", "_param_list", "_gauss_cache", "_refill_engine")
+
+    def __getstate__(self):                     # copy.deepcopy / torch.save(policy): library handles and caches stay behind
+        state = dict(self.__dict__)
+        for k in self._TRANSIENT:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.__dict__.update(_handle=None, _weights_key=None, _workspace=None)
+
     def _apply(self, fn, *args, **kwargs):      # .to() / .cuda() / .float(): forget the cached parameter list
         self.__dict__.pop("_param_list", None)
         return super()._apply(fn, *args, **kwargs)

@@ -116,3 +116,21 @@ def test_evaluate_actions_matches_reference_forward_on_cpu():
     assert (logp - t("ref_log_prob")).abs().max() < 1e-4
     assert (hx2["human_human_edge_rnn"] - t("ref_h_edge")).abs().max() < 1e-5
     assert value.requires_grad and math.isfinite(float(ent))
+
+
+def test_policy_can_be_pickled_and_deep_copied():
+    """train.py's resume path loads a pickled actor_critic (train.py:170-172): library handles and caches must stay behind."""
+    import copy
+    import io
+
+    obs, act = crowd_spaces(5)
+    p = Policy(obs.spaces, act, base="srnn", base_kwargs=Config())
+    p.__dict__["_param_list"] = p._weight_tensors()          # as after a forward
+    q = copy.deepcopy(p)
+    buf = io.BytesIO()
+    torch.save(p, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    for other in (q, r):
+        assert other._handle is None and "_param_list" not in other.__dict__
+        assert all(torch.equal(a, b) for a, b in zip(p.state_dict().values(), other.state_dict().values()))
