@@ -548,7 +548,10 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
         run(m->att_qt, m->att_wc, m->att_bc, q, 256, 256);
         // the attention kernel is bandwidth-bound with a small footprint: the one place in this forward where the env's
         // spare-episode refill (crowd_reset.cu) can share the SMs instead of waiting for them or making others wait
-        if (m->refill_env && cn_env_refill(m->refill_env, s) != CN_OK) return "cn_env_refill (refill hook) failed";
+        if (m->refill_env) {
+            if (cn_env_refill(m->refill_env, s) != CN_OK) return "cn_env_refill (refill hook) failed";
+            ++launches;
+        }
         attention_kernel<<<(N + 3) / 4, 128, 0, s>>>(io->h_edge_out, ws.qt, ws.cat, N, H);
         ++launches;
     }
