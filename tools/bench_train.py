@@ -26,10 +26,14 @@ def main():
     ap.add_argument("--humans", type=int, default=20)
     ap.add_argument("--updates", type=int, default=3)
     ap.add_argument("--per-pass", type=int, default=1024)
+    ap.add_argument("--tf32", action="store_true", help="TF32 tensor cores for the torch GEMMs of the update (fwd + bwd)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if args.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = Config()
