@@ -3,14 +3,21 @@
 // The edge GRUs of the DS-RNN (HumanHumanEdgeRNN.forward, srnn_model.py:201-215; one GRU(64->256) step on
 // N temporal + N*H spatial edge rows) are one tall GEMM per weight set:
 //     [e | m*h]  (rows x 320)   x   [W_ih | W_hh]^T  (320 x 768)      e = ReLU(W_enc x + b)  (K = 2, computed in place)
-// followed by the gate non-linearities.  One persistent CTA per SM walks 128-row tiles:
-//   warps 0-7  stage the tile's A operand straight from the fp32 hidden state in HBM (masking, fp32 -> split bf16
-//              hi/lo, 128B-swizzled K-major smem image), then act as the epilogue: tcgen05.ld the accumulators of a
-//              64-hidden-unit column tile (n_i | r | z | n_h, 256 TMEM columns), apply sigmoid/tanh/blend and store h'.
-//   warp 8     streams the pre-swizzled bf16 weight images (24 KB chunks) with cp.async.bulk into a 2-slot smem ring.
-//   warp 9     owns TMEM (512 columns = 2 accumulator buffers) and issues tcgen05.mma.kind::f16 (M=128, N=192, K=16).
+// followed by the gate non-linearities.  Persistent CTA PAIRS (cluster of 2, tcgen05.mma.cta_group::2: M = 256 = 128 rows per
+// CTA, the weight operand split between the two CTAs) walk 256-row tile pairs; 20 warps per CTA, setmaxnreg budgets:
+//   warps 0-7   epilogue: tcgen05.ld the accumulators of a 64-hidden-unit column tile (n_i | r | z | n_h, 256 TMEM columns,
+//               double-buffered), h_prev back out of the staged A image, gates with 5 MUFU per element, 256-bit stores of h',
+//               tcgen05.st zeroes n_h for the next column tile.
+//   warps 8-15  stage the tile's A operand straight from the fp32 hidden state in HBM (masking, fp32 -> split bf16 hi/lo,
+//               128B-swizzled K-major smem image, 160 KB).  The loads of the next tile are issued before waiting for the MMAs
+//               of the current one; the image is handed over in three pieces (k-block 0 | 1-2 | 3-4).
+//   warp 16     streams this CTA's half (96 of 192 rows, 12 KB) of the pre-swizzled weight chunks with
+//               cp.async.bulk.tensor .cta_group::2 into a 5-slot ring; both CTAs' copies complete on the leader's mbarrier.
+//   warp 17     (leader CTA) issues every tcgen05.mma (N = 192, K = 16) and the multicast tcgen05.commit's; TMEM (512 columns)
+//               is allocated for the pair by this warp of both CTAs.
 // Precision: CN_PREC_BF16X3 runs A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (fp32 accumulate in TMEM, ~2^-16 relative operand
-// error); CN_PREC_BF16 runs the first pass only.
+// error); CN_PREC_BF16 / CN_PREC_FP16 run one pass.
+// Development aids: -DEDGE_PROFILE adds per-role clock64 counters (tools/edge_profile.py) and CN_EDGE_DEBUG what-if switches.
 #include <cuda.h>
 #include <cstdlib>
 #include <new>

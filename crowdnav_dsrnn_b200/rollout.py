@@ -1,8 +1,8 @@
 """CUDA-graph rollout: one deterministic rollout step (`CrowdVecEnv.step` -> `Policy.act` on the new observation, i.e. the
 loop of train.py:243-261 / evaluation.py:119-134 without the host round trips) captured once and replayed.
 
-At small batches (BASELINE.json configs[0]/[1]: 16 / 1024 envs) a step is ~15 kernel launches of a few microseconds
-each, so the eager loop is bound by launch latency; a graph replay submits the whole step with one call.  Two graphs are
+At small batches (BASELINE.json configs[0]/[1]: 16 / 1024 envs) a step is 7 kernel launches of a few microseconds
+each (plus the host-side bookkeeping of `act`), so the eager loop is bound by launch latency; a graph replay submits the whole step with one call.  Two graphs are
 captured because every buffer is ping-ponged (the engine double-buffers its outputs, the hidden state and masks
 alternate between two static sets): graph 0 reads set 0 and writes set 1, graph 1 the reverse.
 """
