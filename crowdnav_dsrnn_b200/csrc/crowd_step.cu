@@ -22,7 +22,9 @@
 #include "env_common.cuh"
 
 #define ORCA_EPS 0.00001f
+#ifndef STEP_THREADS
 #define STEP_THREADS 256
+#endif
 #ifndef STEP_MIN_BLOCKS
 #define STEP_MIN_BLOCKS 4
 #endif
