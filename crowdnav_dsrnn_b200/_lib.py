@@ -11,7 +11,8 @@ import subprocess
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrowdnav_b200.so")
+# CROWDNAV_B200_LIB: another build of the same library (A/B timing of kernel variants inside one process launch)
+LIB_PATH = os.environ.get("CROWDNAV_B200_LIB") or os.path.join(_HERE, "libcrowdnav_b200.so")
 
 # every function include/crowdnav_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
