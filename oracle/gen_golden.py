@@ -51,7 +51,9 @@ def flat_cfg(ref_cfg, n_envs):
     return abi.flatten_config(ref_cfg, n_envs, phase="train")
 
 
-def run_case(name, over, n_envs, seed):
+def reference_vs_oracle(over, n_envs, seed):
+    """Run the reference's own step and the C oracle on the same seeded injected states; returns (inputs, reference outputs,
+    comparison report).  Used by run_case (fixtures) and by tests/test_oracle_live_reference.py (fresh seeds)."""
     over = dict(COMMON, **over)
     ref_cfg = ref_harness.make_reference_config(**over)
     cfg = flat_cfg(ref_cfg, n_envs)
@@ -84,8 +86,12 @@ def run_case(name, over, n_envs, seed):
         getattr(st, f)[...] = inp[f]
     out = crowd_oracle.step(cfg, st, inp["action"], auto_reset=False)
 
-    rep = compare(ref, out, st, H)
-    print(f"[{name}] N={n_envs} H={H}: " + ", ".join(f"{k}={v}" for k, v in rep.items()))
+    return over, inp, ref, compare(ref, out, st, H)
+
+
+def run_case(name, over, n_envs, seed):
+    over, inp, ref, rep = reference_vs_oracle(over, n_envs, seed)
+    print(f"[{name}] N={n_envs}: " + ", ".join(f"{k}={v}" for k, v in rep.items()))
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     np.savez_compressed(
         os.path.join(GOLDEN_DIR, f"step_{name}.npz"),
