@@ -61,7 +61,7 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
         mask = P.a.need_sync;
     } else if (mode == CN_RESET_SPARE_LIST) {
         list = P.a.refill_list;
-        limit = P.a.sync_count[2];
+        limit = min(P.a.sync_count[2], P.n_envs);
         mask = nullptr;
     } else if (spare) {
         mask = P.a.need_spare;
@@ -245,7 +245,8 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
                 P.a.sp_meta[e] = make_int4(0, 0, 0, 0);     // the counters moved on: whatever spare there was is stale
                 if (mode == CN_RESET_SYNC) {
                     P.a.need_sync[e] = 0;
-                    P.a.refill_list[atomicAdd(&P.a.sync_count[2], 1)] = e;
+                    const int slot = atomicAdd(&P.a.sync_count[2], 1);
+                    if (slot < P.n_envs) P.a.refill_list[slot] = e;
                 } else {
                     P.a.need_spare[e] = 1;
                 }

@@ -380,7 +380,10 @@ __device__ __noinline__ void swap_in_spare(const EnvParams &P, const CnStepOut &
             P.a.rob_x[e] = nx;
             P.a.ctr[e] = ctr;
             P.a.sp_meta[e] = make_int4(0, 0, 0, 0);
-            P.a.refill_list[atomicAdd(&P.a.sync_count[2], 1)] = e;
+            // (the list holds n_envs entries: if nobody ran the refill for many steps the surplus is dropped and those envs
+            //  simply take the synchronous fall-back at their next reset)
+            const int slot = atomicAdd(&P.a.sync_count[2], 1);
+            if (slot < P.n_envs) P.a.refill_list[slot] = e;
         }
     } else if (lane == 0) {
         P.a.need_sync[e] = 1;
