@@ -49,7 +49,9 @@ def synthetic_rollout(policy, storage, seed):
     return next_value
 
 
-def main():
+def reference_run(rollout_seed=99, act_seed=7, perm_seed=PERM_SEED):
+    """Run the reference's own storage + PPO.update on a synthetic rollout; returns the fixture dict (inputs, returns in all
+    four modes, normalised advantages, losses, per-parameter change digests)."""
     from . import ref_harness, ref_import
 
     ref_import.install_shims()
@@ -68,8 +70,8 @@ def main():
         policy.load_state_dict(torch.load(os.path.join(ref_import.REFERENCE_ROOT, "data/example_model/checkpoints/27776.pt"),
                                           map_location="cpu"))
         storage = SRNNRolloutStorage(T, N, spaces, act_space, 128, 256, recurrent_cell_type="GRU")
-        torch.manual_seed(7)
-        next_value = synthetic_rollout(policy, storage, seed=99)
+        torch.manual_seed(act_seed)
+        next_value = synthetic_rollout(policy, storage, seed=rollout_seed)
         storage.compute_returns(next_value, tag.startswith("gae"), cfg.reward.gamma, cfg.ppo.gae_lambda, proper)
         out["returns_" + tag] = storage.returns.numpy().copy()
         if tag != "gae":
@@ -88,7 +90,7 @@ def main():
         before = {k: v.detach().clone() for k, v in policy.state_dict().items()}
         adv = storage.returns[:-1] - storage.value_preds[:-1]
         out["advantages"] = ((adv - adv.mean()) / (adv.std() + 1e-5)).numpy().copy()
-        torch.manual_seed(PERM_SEED)
+        torch.manual_seed(perm_seed)
         losses = agent.update(storage)
         out["losses"] = np.asarray(losses, dtype=np.float64)
         names = sorted(before)
@@ -100,8 +102,13 @@ def main():
             out["delta_stats_%02d" % i] = np.asarray([float(delta.norm()), float(delta.sum()), float(delta.abs().max())])
         out["hyper"] = np.asarray([cfg.ppo.clip_param, cfg.ppo.epoch, cfg.ppo.num_mini_batch, cfg.ppo.value_loss_coef,
                                    cfg.ppo.entropy_coef, cfg.training.lr, cfg.training.eps, cfg.training.max_grad_norm,
-                                   cfg.reward.gamma, cfg.ppo.gae_lambda, PERM_SEED], dtype=np.float64)
-        print("losses", losses)
+                                   cfg.reward.gamma, cfg.ppo.gae_lambda, perm_seed], dtype=np.float64)
+    return out
+
+
+def main():
+    out = reference_run()
+    print("losses", out["losses"])
     path = os.path.join(GOLDEN_DIR, "ppo_update_h5.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -52,3 +52,25 @@ def test_dsrnn_restatement_matches_reference_policy_on_fresh_inputs(ckpt, H, see
     assert float((mine["action_mean"] - action.reshape(mine["action_mean"].shape)).abs().max()) <= 1e-4
     assert float((mine["h_edge"] - hx["human_human_edge_rnn"].reshape(mine["h_edge"].shape)).abs().max()) <= 1e-5
     assert float((mine["h_node"] - hx["human_node_rnn"].reshape(mine["h_node"].shape)).abs().max()) <= 1e-5
+
+
+def test_ppo_update_matches_reference_on_a_fresh_rollout():
+    """The PPO update path against the reference's own SRNNRolloutStorage + PPO.update on a rollout / permutation that is not
+    the committed fixture (tests/test_ppo_update.py holds the helpers)."""
+    import torch
+
+    import test_ppo_update as T
+    from crowdnav_dsrnn_b200.ppo import PPO
+    from oracle import gen_golden_ppo
+
+    g = gen_golden_ppo.reference_run(rollout_seed=1234, act_seed=21, perm_seed=777)
+    hyper = g["hyper"]
+    torch.set_num_threads(4)
+    policy = T._policy()
+    before = {k: v.detach().clone() for k, v in policy.state_dict().items()}
+    st = T._storage(g)
+    st.compute_returns(torch.from_numpy(g["next_value"]), True, float(hyper[8]), float(hyper[9]), False)
+    agent = PPO(policy, float(hyper[0]), int(hyper[1]), int(hyper[2]), float(hyper[3]), float(hyper[4]), lr=float(hyper[5]),
+                eps=float(hyper[6]), max_grad_norm=float(hyper[7]))
+    torch.manual_seed(int(hyper[10]))
+    T._check_update(g, policy, before, agent.update(st))
