@@ -77,3 +77,13 @@ def test_oracle_is_not_imported_by_the_product():
     code = "import sys; import crowdnav_dsrnn_b200.envs, crowdnav_dsrnn_b200.model, crowdnav_dsrnn_b200.crowd_sim_dict; " \
            "assert not [m for m in sys.modules if m.split('.')[0] == 'oracle']"
     subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+
+
+def test_graft_entry_build_runs():
+    """The driver's "does it build" check: __graft_entry__.build() must make + load the library and the C oracle."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+
+    pkg = __graft_entry__.build()
+    assert pkg.__name__ == "crowdnav_dsrnn_b200"
+    assert os.path.exists(_lib.LIB_PATH)
