@@ -117,9 +117,14 @@ __device__ __forceinline__ void lp3_group(const GroupOps<G> &g, const Line &ln, 
                                           float &rx, float &ry)
 {
     float distance = 0.0f;
+    // RVO2 walks the lines from `begin` and re-solves at every line that is penetrated by more than `distance`; between two
+    // such lines neither the velocity nor `distance` changes, so every lane tests its own line and a ballot names the next one
     for (int i = begin; i < n; ++i) {
+        const unsigned pen = g.ballot(g.gl >= i && g.gl < n && det2(ln.dx, ln.dy, ln.px - rx, ln.py - ry) > distance);
+        if (pen == 0u) break;
+        i = __ffs(pen) - 1;
         const float kpx = g.shfl(ln.px, i), kpy = g.shfl(ln.py, i), kdx = g.shfl(ln.dx, i), kdy = g.shfl(ln.dy, i);
-        if (det2(kdx, kdy, kpx - rx, kpy - ry) > distance) {
+        {
             Line pl; pl.px = pl.py = pl.dx = pl.dy = 0.0f;
             bool pvalid = false;
             if (g.gl < i) {
@@ -258,6 +263,183 @@ __device__ __forceinline__ float2 orca_group(const CnConfig &cfg, const GroupOps
     float rx, ry;
     const int fail = lp2_group<G>(g, ln, valid, max_speed, prefx, prefy, false, rx, ry);
     if (fail >= 0) lp3_group<G>(g, ln, n, fail, max_speed, rx, ry);
+    return make_float2(rx, ry);
+}
+
+// ---------------------------------------------------------------------------------------------- phase A, sequential form
+// One THREAD per human: the RVO2 solve exactly as the library runs it (computeNeighbors -> computeNewVelocity ->
+// linearProgram2 [-> linearProgram3]), the thread's half-planes kept in shared memory in rank order, slot-major
+// (`line a of thread t` = lines[a * stride + t]: conflict-free when the warp is converged).  Used for crowds of more
+// than 16 neighbours, where the incremental LP is a long dependent chain and a 32-lane group mostly runs it with one
+// useful lane: 32 humans share every issued instruction instead of one.  Same arithmetic, same order -> same bits as
+// the group form and oracle/orca_core.h.
+struct SmemLines {
+    const float4 *p; int stride;
+    __device__ __forceinline__ Line operator()(int a) const { const float4 t = p[a * stride]; return Line{t.x, t.y, t.z, t.w}; }
+};
+
+template <class LA>
+__device__ __forceinline__ bool lp1_seq(const LA &L, int k, float radius, float optx, float opty, bool dir_opt, float &rx, float &ry)
+{
+    const Line lk = L(k);
+    const float dp = lk.px * lk.dx + lk.py * lk.dy;
+    const float disc = dp * dp + radius * radius - (lk.px * lk.px + lk.py * lk.py);
+    if (disc < 0.0f) return false;
+    const float sq = sqrtf(disc);
+    float t_left = -dp - sq, t_right = -dp + sq;
+    // no early exit inside the loop: t_left only grows and t_right only shrinks, so testing once at the end decides the
+    // same way as RVO2's per-line test, and the iterations stay independent (four divisions in flight per thread)
+    bool fail = false;
+#pragma unroll 4
+    for (int j = 0; j < k; ++j) {
+        const Line lj = L(j);
+        const float den = det2(lk.dx, lk.dy, lj.dx, lj.dy);
+        const float num = det2(lj.dx, lj.dy, lk.px - lj.px, lk.py - lj.py);
+        if (fabsf(den) <= ORCA_EPS) fail |= num < 0.0f;
+        else {
+            const float t = num / den;
+            if (den >= 0.0f) { if (t < t_right) t_right = t; }
+            else             { if (t_left < t) t_left = t; }
+        }
+    }
+    if (fail || t_left > t_right) return false;
+    float t;
+    if (dir_opt) t = (optx * lk.dx + opty * lk.dy > 0.0f) ? t_right : t_left;
+    else {
+        t = lk.dx * (optx - lk.px) + lk.dy * (opty - lk.py);
+        if (t < t_left) t = t_left; else if (t > t_right) t = t_right;
+    }
+    rx = lk.px + t * lk.dx; ry = lk.py + t * lk.dy;
+    return true;
+}
+
+// returns the index of the first line that cannot be satisfied, or n
+template <class LA>
+__device__ __forceinline__ int lp2_seq(const LA &L, int n, float radius, float optx, float opty, bool dir_opt, float &rx, float &ry)
+{
+    if (dir_opt) { rx = radius * optx; ry = radius * opty; }
+    else if (optx * optx + opty * opty > radius * radius) {
+        const float inv = 1.0f / sqrtf(optx * optx + opty * opty);
+        rx = radius * (optx * inv); ry = radius * (opty * inv);
+    } else { rx = optx; ry = opty; }
+    for (int i = 0; i < n; ++i) {
+        const Line li = L(i);
+        if (det2(li.dx, li.dy, li.px - rx, li.py - ry) > 0.0f) {
+            const float tx = rx, ty = ry;
+            if (!lp1_seq(L, i, radius, optx, opty, dir_opt, rx, ry)) { rx = tx; ry = ty; return i; }
+        }
+    }
+    return n;
+}
+
+// neighbour slot k of human i: the other humans in index order, then the robot (orca.py:99-115); invisible ones are
+// replaced by the dummy agent (crowd_sim.py:161-163, 1119-1153)
+struct Neighbour { float x, y, vx, vy, rad; };
+__device__ __forceinline__ Neighbour fetch_neighbour(const CnConfig &cfg, int i, int k, int H, float4 me, double my_th, bool limited,
+                                                     const float4 *s_pv, const float4 *s_gr, float4 rob_pv, float rob_radius)
+{
+    Neighbour o;
+    double raw_r, dummy_r;
+    if (k < H - 1) {
+        const int j = k + (k >= i ? 1 : 0);
+        const float4 p = s_pv[j];
+        o.x = p.x; o.y = p.y; o.vx = p.z; o.vy = p.w; raw_r = (double)s_gr[j].z; dummy_r = cfg.human_radius;
+    } else {
+        o.x = rob_pv.x; o.y = rob_pv.y; o.vx = rob_pv.z; o.vy = rob_pv.w; raw_r = (double)rob_radius; dummy_r = cfg.robot_radius;
+    }
+    if (limited && !detect_visible_d(cfg.kinematics, me.x, me.y, me.z, me.w, my_th, o.x, o.y, cfg.human_fov)) {
+        raw_r = dummy_r; o.x = 7.0f; o.y = 7.0f; o.vx = 0.0f; o.vy = 0.0f;
+    }
+    o.rad = (float)(raw_r + 0.01 + (double)cfg.orca_safety_space);
+    return o;
+}
+
+// computeNewVelocity's half-plane against one neighbour (RVO2 Agent.cpp, restated in oracle/orca_core.h)
+__device__ __forceinline__ float4 orca_half_plane(const CnConfig &cfg, float4 me, float radius, const Neighbour &o)
+{
+    Line ln;
+    const float rpx = o.x - me.x, rpy = o.y - me.y;
+    const float rvx = me.z - o.vx, rvy = me.w - o.vy;
+    const float dsq = rpx * rpx + rpy * rpy;
+    const float R = radius + o.rad;
+    const float R2 = R * R;
+    float ux, uy;
+    if (dsq > R2) {
+        const float inv_tau = 1.0f / cfg.orca_time_horizon;
+        const float wx = rvx - inv_tau * rpx, wy = rvy - inv_tau * rpy;
+        const float wl2 = wx * wx + wy * wy;
+        const float dp1 = wx * rpx + wy * rpy;
+        if (dp1 < 0.0f && dp1 * dp1 > R2 * wl2) {
+            const float wl = sqrtf(wl2);
+            const float inv = 1.0f / wl;
+            const float uwx = wx * inv, uwy = wy * inv;
+            ln.dx = uwy; ln.dy = -uwx;
+            const float sc = R * inv_tau - wl;
+            ux = sc * uwx; uy = sc * uwy;
+        } else {
+            const float leg = sqrtf(dsq - R2);
+            const float inv = 1.0f / dsq;
+            if (det2(rpx, rpy, wx, wy) > 0.0f) {
+                ln.dx = (rpx * leg - rpy * R) * inv; ln.dy = (rpx * R + rpy * leg) * inv;
+            } else {
+                ln.dx = -((rpx * leg + rpy * R) * inv); ln.dy = -((-rpx * R + rpy * leg) * inv);
+            }
+            const float dp2 = rvx * ln.dx + rvy * ln.dy;
+            ux = dp2 * ln.dx - rvx; uy = dp2 * ln.dy - rvy;
+        }
+    } else {
+        const float inv_dt = 1.0f / (float)cfg.time_step;
+        const float wx = rvx - inv_dt * rpx, wy = rvy - inv_dt * rpy;
+        const float wl = sqrtf(wx * wx + wy * wy);
+        const float inv = 1.0f / wl;
+        const float uwx = wx * inv, uwy = wy * inv;
+        ln.dx = uwy; ln.dy = -uwx;
+        const float sc = R * inv_dt - wl;
+        ux = sc * uwx; uy = sc * uwy;
+    }
+    return make_float4(me.z + 0.5f * ux, me.w + 0.5f * uy, ln.dx, ln.dy);
+}
+
+// One human's ORCA solve by one thread up to linearProgram2.  lines / keys: this thread's column of the slot-major shared
+// arrays.  fail < n_lines: the LP is infeasible from line `fail` on and the caller hands the human to linearProgram3.
+__device__ __forceinline__ float2 orca_thread(const CnConfig &cfg, int i, int H, const float4 *s_pv, const float4 *s_gr,
+                                              const float *s_th, float2 pref, float4 rob_pv, float rob_radius,
+                                              float4 *lines, int *keys, int stride, int &n_lines, int &fail)
+{
+    const float4 me = s_pv[i];
+    const float4 me_g = s_gr[i];
+    const float radius = (float)((double)me_g.z + 0.01 + (double)cfg.orca_safety_space);
+    const float max_speed = me_g.w;
+    const int M = H - 1 + (cfg.robot_visible ? 1 : 0);
+    const bool limited = cfg.human_fov < 2.0 * CN_PI;
+    const double my_th = (limited && cfg.kinematics != CN_HOLONOMIC) ? (double)s_th[i] : 0.0;
+    const float range_sq = cfg.orca_neighbor_dist * cfg.orca_neighbor_dist;
+
+    // computeNeighbors: everyone strictly inside neighborDist; the sort key is the bit pattern of distSq (>= +0)
+    int n = 0;
+    for (int k = 0; k < M; ++k) {
+        const Neighbour o = fetch_neighbour(cfg, i, k, H, me, my_th, limited, s_pv, s_gr, rob_pv, rob_radius);
+        const float ddx = me.x - o.x, ddy = me.y - o.y;
+        const float dist_sq = ddx * ddx + ddy * ddy;
+        const bool in = dist_sq < range_sq;
+        keys[k * stride] = in ? __float_as_int(dist_sq) : 0x7fffffff;
+        n += in ? 1 : 0;
+    }
+    // rank = number of in-range neighbours that sort before this one in (distSq, index) order = RVO2's stable insertion
+    for (int k = 0; k < M; ++k) {
+        const int key = keys[k * stride];
+        if (key == 0x7fffffff) continue;
+        int rank = 0;
+        for (int j = 0; j < k; ++j) rank += (keys[j * stride] <= key) ? 1 : 0;
+        for (int j = k + 1; j < M; ++j) rank += (keys[j * stride] < key) ? 1 : 0;
+        const Neighbour o = fetch_neighbour(cfg, i, k, H, me, my_th, limited, s_pv, s_gr, rob_pv, rob_radius);
+        lines[rank * stride] = orca_half_plane(cfg, me, radius, o);
+    }
+
+    float rx, ry;
+    const SmemLines L{lines, stride};
+    fail = lp2_seq(L, n, max_speed, pref.x, pref.y, false, rx, ry);
+    n_lines = n;
     return make_float2(rx, ry);
 }
 
@@ -730,6 +912,110 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
     }
 }
 
+// The sequential form of phase A (thread per human) around the same staging and phase B.
+// dynamic smem: E*H*(float4 pv + float4 gr + float2 nv + float th) + S * M * (float4 line + int key), S = solver threads
+#ifndef STEP_SEQ_MIN_BLOCKS
+#define STEP_SEQ_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(STEP_THREADS, STEP_SEQ_MIN_BLOCKS)
+crowd_step_seq_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnStepOut out,
+                      const float *__restrict__ action, int E, int S, int auto_reset)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const CnConfig &cfg = P.cfg;
+    const int H = cfg.human_num;
+    const int M = H - 1 + (cfg.robot_visible ? 1 : 0);
+    const int e0 = blockIdx.x * E;
+    const int ne = min(E, P.n_envs - e0);
+    const int EH = E * H;
+    float4 *s_pv = reinterpret_cast<float4 *>(smem_raw);
+    float4 *s_gr = s_pv + EH;
+    float4 *s_lines = s_gr + EH;
+    float2 *s_nv = reinterpret_cast<float2 *>(s_lines + S * M);
+    int *s_keys = reinterpret_cast<int *>(s_nv + EH);
+    float *s_th = reinterpret_cast<float *>(s_keys + S * M);
+    __shared__ float4 s_rob_pv[64];
+    __shared__ float2 s_rob_rt[64];   // radius, theta
+    __shared__ int s_fail[STEP_THREADS];   // queue of humans for linearProgram3: thread | n << 8 | first failed line << 16
+    __shared__ int s_ctl[3];
+
+    const size_t base = (size_t)e0 * H;
+    const bool need_th = cfg.human_fov < 2.0 * CN_PI && cfg.kinematics != CN_HOLONOMIC;
+    for (int k = threadIdx.x; k < ne * H; k += STEP_THREADS) {
+        const float4 pv = P.a.hum_pv[base + k], gr = P.a.hum_gr[base + k];
+        s_pv[k] = pv;
+        s_gr[k] = gr;
+        s_nv[k] = preferred_velocity(pv, gr);
+        if (need_th) s_th[k] = P.a.hum_th[base + k];
+    }
+    if (cfg.robot_visible) {
+        for (int k = threadIdx.x; k < ne; k += STEP_THREADS) {
+            s_rob_pv[k] = P.a.rob_pv[e0 + k];
+            s_rob_rt[k] = make_float2(P.a.rob_gr[e0 + k].z, P.a.rob_x[e0 + k].x);
+        }
+    }
+    __syncthreads();
+
+    // phase A: thread t < S solves human task0 + t up to linearProgram2.  Humans whose LP is infeasible (common in dense
+    // crowds: ~1 in 8 at H = 20) are finished with the lane-parallel linearProgram3 by whole warps -- run by their own
+    // thread they would hold the CTA at the barrier for tens of microseconds.  The two run CONCURRENTLY: solver threads
+    // push (thread, n, fail) records into a shared-memory queue, and every warp that has no solver thread left (the
+    // spare warps from the start, the solver warps as they finish) pops records until the queue is closed and drained.
+    const int lane = threadIdx.x & 31;
+    volatile int *vctl = s_ctl;
+    volatile int *vfail = s_fail;
+    for (int task0 = 0; task0 < ne * H; task0 += S) {
+        const int todo = min(S, ne * H - task0);
+        const int solver_warps = (todo + 31) >> 5;
+        s_fail[threadIdx.x] = -1;
+        if (threadIdx.x < 3) s_ctl[threadIdx.x] = 0;       // records pushed | records popped | solver warps finished
+        __syncthreads();
+        if (threadIdx.x < todo) {
+            const int task = task0 + threadIdx.x;
+            const int el = task / H, i = task - el * H;
+            const float4 rob = cfg.robot_visible ? s_rob_pv[el] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float rr = cfg.robot_visible ? s_rob_rt[el].x : 0.f;
+            int n, fail;
+            s_nv[task] = orca_thread(cfg, i, H, s_pv + el * H, s_gr + el * H, s_th + el * H, s_nv[task], rob, rr,
+                                     s_lines + threadIdx.x, s_keys + threadIdx.x, S, n, fail);
+            if (fail < n) {
+                const int slot = atomicAdd(&s_ctl[0], 1);
+                __threadfence_block();                       // lines and the LP2 result before the record
+                vfail[slot] = (int)threadIdx.x | (n << 8) | (fail << 16);
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x >> 5) < solver_warps && lane == 0) { __threadfence_block(); atomicAdd(&s_ctl[2], 1); }
+        GroupOps<32> g;
+        g.gl = lane; g.gbase = 0; g.gmask = 0xffffffffu;
+        for (;;) {
+            int rec = -1;
+            if (lane == 0) {
+                const int slot = atomicAdd(&s_ctl[1], 1);
+                for (;;) {
+                    if (slot < STEP_THREADS) rec = vfail[slot];
+                    if (rec >= 0) break;
+                    if (vctl[2] >= solver_warps && slot >= vctl[0]) { rec = -2; break; }     // closed and drained
+                    __nanosleep(40);
+                }
+            }
+            rec = __shfl_sync(0xffffffffu, rec, 0);
+            if (rec < 0) break;
+            const int owner = rec & 0xff, n = (rec >> 8) & 0xff, fail = rec >> 16, t = task0 + owner;
+            Line ln; ln.px = ln.py = ln.dx = ln.dy = 0.0f;
+            if (g.gl < n) { const float4 v = s_lines[g.gl * S + owner]; ln.px = v.x; ln.py = v.y; ln.dx = v.z; ln.dy = v.w; }
+            float2 r = s_nv[t];
+            lp3_group<32>(g, ln, n, fail, s_gr[t].w, r.x, r.y);
+            if (g.gl == 0) s_nv[t] = r;
+        }
+        __syncthreads();
+    }
+
+    // phase B: one warp per env
+    for (int el = threadIdx.x >> 5; el < ne; el += STEP_THREADS / 32)
+        env_tail(P, out, action, e0 + el, lane, s_pv + el * H, s_gr + el * H, s_nv + el * H, auto_reset);
+}
+
 static inline int pick_group(int M)
 {
     return M <= 4 ? 4 : (M <= 8 ? 8 : (M <= 16 ? 16 : 32));
@@ -741,13 +1027,37 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     const int H = P->cfg.human_num;
     const int M = H - 1 + (P->cfg.robot_visible ? 1 : 0);
     const int G = pick_group(M < 1 ? 1 : M);
+    static int num_sms = 0;
+    if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    // CN_STEP_SEQ=1: the thread-per-human form of phase A.  Same bits; measured at 16384 envs x 20 humans it executes 30 %
+    // fewer instructions than the group form but is latency-bound at the ~15 solver warps per SM its 400 B of shared memory
+    // per human allow, so it is no faster (0.49-0.53 vs 0.51 ms, profiles/README.md) and stays a development switch.
+    bool seq = false;
+    if (const char *dbg = getenv("CN_STEP_SEQ")) seq = atoi(dbg) != 0 && M >= 1 && M <= 32;
+    if (seq) {
+        int E = STEP_THREADS / H;           // one solve per thread
+        E = E < 1 ? 1 : (E > 64 ? 64 : E);
+        if (num_sms > 0 && P->n_envs < E * 2 * num_sms) { E = P->n_envs / (2 * num_sms); E = E < 1 ? 1 : E; }
+        if (const char *dbg = getenv("CN_STEP_ENVS_PER_CTA")) { const int v = atoi(dbg); if (v >= 1 && v <= 64) E = v; }
+        int S = (E * H + 31) & ~31;         // solver threads per pass = columns of the slot-major line / key arrays
+        S = S > STEP_THREADS ? STEP_THREADS : S;
+        const size_t smem = (size_t)E * H * (16 + 16 + 8 + 4) + (size_t)S * M * (16 + 4);
+        static bool attr_set = false;
+        if (!attr_set) {
+            const cudaError_t rc = cudaFuncSetAttribute(crowd_step_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (rc != cudaSuccess) return (int)rc;
+            attr_set = true;
+        }
+        if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+        const int grid = (P->n_envs + E - 1) / E;
+        crowd_step_seq_kernel<<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, S, auto_reset);
+        return (int)cudaGetLastError();
+    }
     // envs per CTA: ~2 rounds of ORCA groups per CTA, at most 64 (s_rob_* capacity), at least 8 (one tail warp each)
     int E = (2 * (STEP_THREADS / G) + H - 1) / H;
     E = E < 8 ? 8 : (E > 64 ? 64 : E);
     // small batches (BASELINE configs[0], [1]): a CTA is a latency chain of ~E*H/groups solves plus one tail per warp, and
     // there are not enough CTAs to fill the GPU anyway -- spread the envs over at least ~4 CTAs per SM
-    static int num_sms = 0;
-    if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
     if (num_sms > 0 && P->n_envs < E * 4 * num_sms) { E = P->n_envs / (4 * num_sms); E = E < 1 ? 1 : E; }
     if (const char *dbg = getenv("CN_STEP_ENVS_PER_CTA")) { const int v = atoi(dbg); if (v >= 1 && v <= 64) E = v; }   // tuning knob
     const size_t smem = (size_t)E * H * (16 + 16 + 8 + 4) + STEP_THREADS * 16;
