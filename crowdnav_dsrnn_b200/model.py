@@ -33,6 +33,76 @@ def _orthogonal(module, gain=1.0):
     return module
 
 
+class _MaskedGruSequence(torch.autograd.Function):
+    """h_t = GRUCell(x_t, m_t * h_{t-1}) for t < T over R independent rows, returned as [T, R, hidden].
+
+    The training-time form of one DS-RNN recurrent unit (srnn_model.py:53-104 applies the masks by cutting the sequence at
+    every step where any env finished -- with thousands of envs that is every step).  One autograd node for the whole
+    sequence instead of ~6 per step: the input projection of all T steps is one GEMM, the weight gradients are ONE
+    [3h, T*R] x [T*R, k] GEMM each at the end of the backward (per-step weight-gradient GEMMs have a 768 x 320 output and
+    fill 60 of 148 SMs), only `h W_hh^T`, the gate kernel and their transposes run per step.  On CUDA the gate math is
+    ATen's fused GRU cell pair; elsewhere (CPU tests) the same formulas in plain torch.
+    """
+
+    @staticmethod
+    def forward(ctx, x, h0, m, w_ih, w_hh, b_ih, b_hh):
+        T, R, hid = x.shape[0], x.shape[1], h0.shape[1]
+        fused = x.is_cuda
+        gi = torch.matmul(x, w_ih.t())                       # [T, R, 3h]; the cell adds both biases
+        hs = x.new_empty(T, R, hid)
+        hm = x.new_empty(T, R, hid)                          # masked previous state of every step
+        ws = x.new_empty(T, R, 5 * hid) if fused else x.new_empty(T, R, 4 * hid)
+        h = h0
+        w_hh_t = w_hh.t()
+        for t in range(T):
+            torch.mul(h, m[t], out=hm[t])
+            gh = torch.mm(hm[t], w_hh_t)
+            if fused:
+                h, w = torch.ops.aten._thnn_fused_gru_cell(gi[t], gh, hm[t], b_ih, b_hh)
+                ws[t].copy_(w)
+            else:
+                a, b = gi[t] + b_ih, gh + b_hh
+                r = torch.sigmoid(a[:, :hid] + b[:, :hid])
+                z = torch.sigmoid(a[:, hid:2 * hid] + b[:, hid:2 * hid])
+                hn = b[:, 2 * hid:]
+                n = torch.tanh(a[:, 2 * hid:] + r * hn)
+                h = n + z * (hm[t] - n)
+                ws[t].copy_(torch.cat([r, z, n, hn], 1))
+            hs[t].copy_(h)
+        ctx.save_for_backward(x, m, w_ih, w_hh, hm, ws)
+        ctx.fused = fused
+        return hs
+
+    @staticmethod
+    def backward(ctx, grad_hs):
+        x, m, w_ih, w_hh, hm, ws = ctx.saved_tensors
+        T, R, hid = hm.shape
+        dgi = x.new_empty(T, R, 3 * hid)
+        dgh = x.new_empty(T, R, 3 * hid)
+        dh = None
+        for t in range(T - 1, -1, -1):
+            g = grad_hs[t] if dh is None else grad_hs[t] + dh
+            if ctx.fused:
+                a, b, dhm, _, _ = torch.ops.aten._thnn_fused_gru_cell_backward(g.contiguous(), ws[t], True)
+                dgi[t].copy_(a)
+                dgh[t].copy_(b)
+            else:
+                r, z, n, hn = ws[t].split(hid, 1)
+                dpre_n = g * (1.0 - z) * (1.0 - n * n)
+                dpre_r = dpre_n * hn * r * (1.0 - r)
+                dpre_z = g * (hm[t] - n) * z * (1.0 - z)
+                dgi[t].copy_(torch.cat([dpre_r, dpre_z, dpre_n], 1))
+                dgh[t].copy_(torch.cat([dpre_r, dpre_z, dpre_n * r], 1))
+                dhm = g * z
+            dhm = torch.addmm(dhm, dgh[t], w_hh)
+            dh = dhm * m[t]
+        dgi2, dgh2 = dgi.view(T * R, 3 * hid), dgh.view(T * R, 3 * hid)
+        dx = torch.matmul(dgi, w_ih) if ctx.needs_input_grad[0] else None
+        dw_ih = torch.mm(dgi2.t(), x.reshape(T * R, -1))
+        dw_hh = torch.mm(dgh2.t(), hm.view(T * R, hid))
+        return dx, dh, None, dw_ih, dw_hh, dgi2.sum(0), dgh2.sum(0)
+
+
 class _EdgeRNN(nn.Module):
     """Parameter holder of HumanHumanEdgeRNN (srnn_model.py:176-215): Linear(2,64) + GRU(64,256)."""
 
@@ -141,6 +211,7 @@ class Policy(nn.Module):
             raise NotImplementedError("only Box action spaces are supported")
         self.dist = DiagGaussian(self.base.output_size, action_space.shape[0])
         self.precision = "bf16x3"   # contraction precision of the CUDA forward: "fp32" | "bf16x3" | "bf16"
+        self.sequence_impl = "batched"   # evaluate_actions: "batched" (whole [T, N] chunk at once) | "per_step"
         self._handle = None
         self._weights_key = None
         self._workspace = None
@@ -331,6 +402,45 @@ class Policy(nn.Module):
         return b.critic_linear(b.critic(y)), b.actor(y), h_n, torch.cat([o_t.unsqueeze(1), o_s], 1)
 
     def _torch_sequence_forward(self, inputs, rnn_hxs, masks):
+        """The whole [T, N] chunk at once.  The edge GRUs do not depend on the node RNN (srnn_model.py:464-480), so their
+        T steps run first as one `_MaskedGruSequence` each; the attention, the encoders and the heads have no recurrence
+        and are evaluated for all T*N samples in one batch; the node GRU is a second (small) masked sequence."""
+        if getattr(self, "sequence_impl", "batched") == "per_step":
+            return self._torch_sequence_forward_per_step(inputs, rnn_hxs, masks)
+        b = self.base
+        se = inputs["spatial_edges"]
+        H = se.shape[1]
+        N = rnn_hxs["human_node_rnn"].shape[0]
+        T = se.shape[0] // N
+        rn = inputs["robot_node"].reshape(T * N, 7)
+        te = inputs["temporal_edges"].reshape(T, N, 2)
+        se = se.reshape(T, N * H, 2)
+        mk = masks.reshape(T, N, 1)
+        h_node = rnn_hxs["human_node_rnn"].reshape(N, 128)
+        h_edge = rnn_hxs["human_human_edge_rnn"].reshape(N, H + 1, 256)
+
+        def seq(mod, x, h0, m):
+            return _MaskedGruSequence.apply(x, h0, m, mod.weight_ih_l0, mod.weight_hh_l0, mod.bias_ih_l0, mod.bias_hh_l0)
+
+        et, es = b.humanhumanEdgeRNN_temporal, b.humanhumanEdgeRNN_spatial
+        o_t = seq(et.gru, torch.relu(et.encoder_linear(te)), h_edge[:, 0], mk)                               # [T, N, 256]
+        mk_rows = mk.expand(T, N, H).reshape(T, N * H, 1)
+        o_s = seq(es.gru, torch.relu(es.encoder_linear(se)), h_edge[:, 1:].reshape(N * H, 256), mk_rows)    # [T, N*H, 256]
+        o_t2, o_s3 = o_t.view(T * N, 256), o_s.view(T * N, H, 256)
+        q = b.attn.temporal_edge_layer[0](o_t2)
+        k = b.attn.spatial_edge_layer[0](o_s3)
+        alpha = torch.softmax(torch.bmm(k, q.unsqueeze(-1)).squeeze(-1) * (H / math.sqrt(64.0)), dim=-1)
+        c = torch.bmm(alpha.unsqueeze(1), o_s3).squeeze(1)
+        enc = torch.relu(b.humanNodeRNN.encoder_linear(b.robot_linear(rn)))
+        emb = torch.relu(b.humanNodeRNN.edge_attention_embed(torch.cat([o_t2, c], -1)))
+        h_n = seq(b.humanNodeRNN.gru, torch.cat([enc, emb], -1).view(T, N, -1), h_node, mk)                 # [T, N, 128]
+        y = b.humanNodeRNN.output_linear(h_n.view(T * N, 128))
+        rnn_hxs["human_node_rnn"] = h_n[-1].unsqueeze(1)
+        rnn_hxs["human_human_edge_rnn"] = torch.cat([o_t[-1].unsqueeze(1), o_s[-1].view(N, H, 256)], 1)
+        return b.critic_linear(b.critic(y)), b.actor(y), rnn_hxs
+
+    def _torch_sequence_forward_per_step(self, inputs, rnn_hxs, masks):
+        """One autograd graph per rollout step (the first form of this path; kept as the cross-check of the batched one)."""
         se = inputs["spatial_edges"]
         H = se.shape[1]
         N = rnn_hxs["human_node_rnn"].shape[0]

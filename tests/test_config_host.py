@@ -118,6 +118,49 @@ def test_evaluate_actions_matches_reference_forward_on_cpu():
     assert value.requires_grad and math.isfinite(float(ent))
 
 
+def _sequence_case(dtype, device, n=6, H=5, T=7, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    obs_space, act_space = crowd_spaces(H)
+    policy = Policy(obs_space.spaces, act_space, base="srnn", base_kwargs=Config(human_num=H)).to(device=device, dtype=dtype)
+    mk = lambda *shape, scale=1.0: (torch.randn(*shape, generator=g) * scale).to(device=device, dtype=dtype)
+    obs = {"robot_node": mk(T * n, 1, 7), "temporal_edges": mk(T * n, 1, 2), "spatial_edges": mk(T * n, H, 2, scale=3.0)}
+    masks = (torch.rand(T * n, 1, generator=g) > 0.2).to(device=device, dtype=dtype)
+    action = mk(T * n, 2)
+    h0 = {"human_node_rnn": mk(n, 1, 128, scale=0.3), "human_human_edge_rnn": mk(n, H + 1, 256, scale=0.3)}
+    return policy, obs, masks, action, h0
+
+
+def sequence_impls_agree(dtype, device, tol):
+    """evaluate_actions over a [T, n] chunk: the batched form (one masked GRU sequence per recurrent unit, everything else
+    evaluated for all T*n samples at once) against the per-step autograd graph -- outputs, final hidden state, every
+    parameter gradient and the gradient with respect to the initial hidden state."""
+    policy, obs, masks, action, h0 = _sequence_case(dtype, device)
+    res = {}
+    for impl in ("per_step", "batched"):
+        policy.sequence_impl = impl
+        policy.zero_grad(set_to_none=True)
+        hx = {k: v.clone().requires_grad_(True) for k, v in h0.items()}
+        value, logp, _, out = policy.evaluate_actions(obs, dict(hx), masks, action)
+        weights = torch.linspace(0, 1, value.numel(), device=value.device, dtype=dtype).view_as(value)
+        ((value * weights).sum() + 0.3 * logp.sum() + 0.01 * out["human_human_edge_rnn"].sum()
+         + 0.02 * out["human_node_rnn"].sum()).backward()
+        grads = {k: q.grad.clone() for k, q in policy.named_parameters() if q.grad is not None}
+        res[impl] = (value.detach(), logp.detach(), out["human_human_edge_rnn"].detach(), out["human_node_rnn"].detach(),
+                     grads, [hx[k].grad.clone() for k in sorted(hx)])
+    a, b = res["per_step"], res["batched"]
+    for x, y in list(zip(a[:4], b[:4])) + list(zip(a[5], b[5])):
+        assert (x - y).abs().max().item() <= tol * max(1.0, x.abs().max().item())
+    assert sorted(a[4]) == sorted(b[4]) and len(a[4]) >= 40
+    for k in a[4]:
+        scale = max(a[4][k].abs().max().item(), 1e-3)
+        assert (a[4][k] - b[4][k]).abs().max().item() <= tol * scale, k
+
+
+def test_batched_sequence_forward_equals_per_step_graph_on_cpu():
+    sequence_impls_agree(torch.float64, "cpu", 1e-10)
+    sequence_impls_agree(torch.float32, "cpu", 2e-4)
+
+
 def test_policy_can_be_pickled_and_deep_copied():
     """train.py's resume path loads a pickled actor_critic (train.py:170-172): library handles and caches must stay behind."""
     import copy

@@ -74,3 +74,10 @@ def test_cuda_forward_tracks_optimizer_updates():
     vt, _, _, _ = policy.evaluate_actions(obs, hx(), masks, a1)
     assert (v1 - v0).abs().max() > 1e-3                    # the weights moved ...
     assert (v1 - vt.detach()).abs().max() < 1e-3 * max(1.0, float(vt.abs().max()))   # ... and CUDA and torch paths agree on them
+
+
+def test_batched_sequence_forward_equals_per_step_graph_on_gpu():
+    """On CUDA the masked GRU sequence uses ATen's fused GRU-cell pair for the gate math (forward and backward)."""
+    from test_config_host import sequence_impls_agree
+
+    sequence_impls_agree(torch.float32, DEV, 5e-4)

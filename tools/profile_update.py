@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--humans", type=int, default=20)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--tf32", action="store_true")
-    ap.add_argument("--fused", action="store_true", help="use the CUDA sequence kernels (Policy.sequence_impl='cuda')")
+    ap.add_argument("--per-step", action="store_true", help="the per-step autograd graph (Policy.sequence_impl='per_step')")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.backends.cuda.matmul.allow_tf32 = args.tf32
@@ -30,8 +30,8 @@ def main():
     cfg = Config(human_num=H)
     obs_space, act_space = crowd_spaces(H)
     policy = Policy(obs_space.spaces, act_space, base="srnn", base_kwargs=cfg).to(dev)
-    if args.fused:
-        policy.sequence_impl = "cuda"
+    if args.per_step:
+        policy.sequence_impl = "per_step"
     g = torch.Generator(device=dev).manual_seed(0)
     obs = {"robot_node": torch.randn(T * n, 1, 7, device=dev, generator=g),
            "temporal_edges": torch.randn(T * n, 1, 2, device=dev, generator=g),
@@ -55,8 +55,8 @@ def main():
         one_pass()
     e1.record()
     torch.cuda.synchronize()
-    print("pass of %d envs x %d humans x %d steps: %.2f ms (tf32=%s, fused=%s), peak mem %.2f GB" % (
-        n, H, T, e0.elapsed_time(e1) / 3, args.tf32, args.fused, torch.cuda.max_memory_allocated() / 2**30))
+    print("pass of %d envs x %d humans x %d steps: %.2f ms (tf32=%s, per_step=%s), peak mem %.2f GB" % (
+        n, H, T, e0.elapsed_time(e1) / 3, args.tf32, args.per_step, torch.cuda.max_memory_allocated() / 2**30))
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         one_pass()
