@@ -363,3 +363,30 @@ extern "C" int cn_dsrnn_time_ms(CnDsrnn *m, float *edge_stage_ms, int *n_forward
     *edge_stage_ms = dsrnn_time_ms(m, n_forwards);
     return CN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- training path (dsrnn_train.cu)
+extern "C" int cn_launch_gru_gates_forward(const float *gi, const float *gh, const float *hm, const float *b_ih, const float *b_hh,
+                                           const float *m_next, float *h_out, float *hm_next, float *ws, int R, int hid,
+                                           cudaStream_t stream);
+extern "C" int cn_launch_gru_gates_backward(const float *grad_h, const float *d_next, const float *m_next, const float *ws,
+                                            const float *hm, float *dgi, float *dgh, float *dhm, int R, int hid, cudaStream_t stream);
+
+extern "C" int cn_gru_gates_forward(const float *gi, const float *gh, const float *hm, const float *b_ih, const float *b_hh,
+                                    const float *m_next, float *h_out, float *hm_next, float *ws, int rows, int hid, void *stream)
+{
+    if (!gi || !gh || !hm || !b_ih || !b_hh || !h_out || !ws) return fail(CN_ERR_ARG, "cn_gru_gates_forward: NULL pointer");
+    const int rc = cn_launch_gru_gates_forward(gi, gh, hm, b_ih, b_hh, m_next, h_out, hm_next, ws, rows, hid, (cudaStream_t)stream);
+    if (rc == -1) return fail(CN_ERR_ARG, "cn_gru_gates_forward: rows %d / hid %d / alignment / hm_next without m_next", rows, hid);
+    if (rc != 0) return fail(CN_ERR_CUDA, "gru_gates_forward_kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    return CN_OK;
+}
+
+extern "C" int cn_gru_gates_backward(const float *grad_h, const float *d_next, const float *m_next, const float *ws, const float *hm,
+                                     float *dgi, float *dgh, float *dhm, int rows, int hid, void *stream)
+{
+    if (!grad_h || !ws || !hm || !dgi || !dgh || !dhm) return fail(CN_ERR_ARG, "cn_gru_gates_backward: NULL pointer");
+    const int rc = cn_launch_gru_gates_backward(grad_h, d_next, m_next, ws, hm, dgi, dgh, dhm, rows, hid, (cudaStream_t)stream);
+    if (rc == -1) return fail(CN_ERR_ARG, "cn_gru_gates_backward: rows %d / hid %d / alignment / d_next without m_next", rows, hid);
+    if (rc != 0) return fail(CN_ERR_CUDA, "gru_gates_backward_kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    return CN_OK;
+}

@@ -1,0 +1,115 @@
+// dsrnn_train.cu -- gate math of the masked GRU sequences of the PPO update (the reference's
+// training forward is srnn_model.py:53-104, one nn.GRU step per mask segment).  The recurrent GEMMs stay cuBLAS calls
+// made by the host (model.py `_MaskedGruSequence`); these two kernels are everything between them, fused so that a
+// step of the sequence is two launches in each direction (GEMM + gates) and nothing is copied:
+//   forward : gates -> h_t straight into the [T, R, hid] output, the gate values the backward needs into the [T, R, 4 hid]
+//             workspace, and the MASKED state of the next step (h_t * m_{t+1}, the next GEMM's operand);
+//   backward: g = dL/dh_t + m_{t+1} * dL/d(masked state of step t+1) formed in registers, then the gate gradients
+//             straight into the [T, R, 3 hid] buffers the single weight-gradient GEMMs read at the end.
+// HBM-bound, one thread per four hidden units (float4 everywhere): 17 floats of traffic per hidden unit forward, 20 backward.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float *p) { const float4 t = *reinterpret_cast<const float4 *>(p); return F4{{t.x, t.y, t.z, t.w}}; }
+__device__ __forceinline__ void st4(float *p, const F4 &a) { *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+
+__global__ void __launch_bounds__(256)
+gru_gates_forward_kernel(const float *__restrict__ gi, const float *__restrict__ gh, const float *__restrict__ hm,
+                         const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ m_next,
+                         float *__restrict__ h_out, float *__restrict__ hm_next, float *__restrict__ ws, int R, int hid)
+{
+    const int q = hid >> 2;                                     // float4 columns per row
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)R * q) return;
+    const int row = (int)(idx / q), c = (int)(idx - (size_t)row * q) << 2;
+    const float *gir = gi + (size_t)row * 3 * hid, *ghr = gh + (size_t)row * 3 * hid;
+    const F4 ir = ld4(gir + c), iz = ld4(gir + hid + c), in = ld4(gir + 2 * hid + c);
+    const F4 hr = ld4(ghr + c), hz = ld4(ghr + hid + c), hnn = ld4(ghr + 2 * hid + c);
+    const F4 bir = ld4(b_ih + c), biz = ld4(b_ih + hid + c), bin = ld4(b_ih + 2 * hid + c);
+    const F4 bhr = ld4(b_hh + c), bhz = ld4(b_hh + hid + c), bhn = ld4(b_hh + 2 * hid + c);
+    const F4 hp = ld4(hm + (size_t)row * hid + c);
+    F4 r, z, n, hn, h;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r.v[k] = sigmoidf_((ir.v[k] + bir.v[k]) + (hr.v[k] + bhr.v[k]));
+        z.v[k] = sigmoidf_((iz.v[k] + biz.v[k]) + (hz.v[k] + bhz.v[k]));
+        hn.v[k] = hnn.v[k] + bhn.v[k];
+        n.v[k] = tanhf((in.v[k] + bin.v[k]) + r.v[k] * hn.v[k]);
+        h.v[k] = n.v[k] + z.v[k] * (hp.v[k] - n.v[k]);
+    }
+    st4(h_out + (size_t)row * hid + c, h);
+    float *w = ws + (size_t)row * 4 * hid;
+    st4(w + c, r); st4(w + hid + c, z); st4(w + 2 * hid + c, n); st4(w + 3 * hid + c, hn);
+    if (hm_next) {
+        const float m = m_next[row];
+        F4 o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o.v[k] = h.v[k] * m;
+        st4(hm_next + (size_t)row * hid + c, o);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gru_gates_backward_kernel(const float *__restrict__ grad_h, const float *__restrict__ d_next, const float *__restrict__ m_next,
+                          const float *__restrict__ ws, const float *__restrict__ hm, float *__restrict__ dgi,
+                          float *__restrict__ dgh, float *__restrict__ dhm, int R, int hid)
+{
+    const int q = hid >> 2;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)R * q) return;
+    const int row = (int)(idx / q), c = (int)(idx - (size_t)row * q) << 2;
+    F4 g = ld4(grad_h + (size_t)row * hid + c);
+    if (d_next) {
+        const float m = m_next[row];
+        const F4 d = ld4(d_next + (size_t)row * hid + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g.v[k] = g.v[k] + d.v[k] * m;
+    }
+    const float *w = ws + (size_t)row * 4 * hid;
+    const F4 r = ld4(w + c), z = ld4(w + hid + c), n = ld4(w + 2 * hid + c), hn = ld4(w + 3 * hid + c);
+    const F4 hp = ld4(hm + (size_t)row * hid + c);
+    F4 pr, pz, pn, pnr, dh;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pn.v[k] = g.v[k] * (1.0f - z.v[k]) * (1.0f - n.v[k] * n.v[k]);
+        pr.v[k] = pn.v[k] * hn.v[k] * r.v[k] * (1.0f - r.v[k]);
+        pz.v[k] = g.v[k] * (hp.v[k] - n.v[k]) * z.v[k] * (1.0f - z.v[k]);
+        pnr.v[k] = pn.v[k] * r.v[k];
+        dh.v[k] = g.v[k] * z.v[k];
+    }
+    float *a = dgi + (size_t)row * 3 * hid, *b = dgh + (size_t)row * 3 * hid;
+    st4(a + c, pr); st4(a + hid + c, pz); st4(a + 2 * hid + c, pn);
+    st4(b + c, pr); st4(b + hid + c, pz); st4(b + 2 * hid + c, pnr);
+    st4(dhm + (size_t)row * hid + c, dh);
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+// host launchers (called from c_abi.cu); return a cudaError_t as int, -1 for bad arguments
+extern "C" int cn_launch_gru_gates_forward(const float *gi, const float *gh, const float *hm, const float *b_ih, const float *b_hh,
+                                           const float *m_next, float *h_out, float *hm_next, float *ws, int R, int hid,
+                                           cudaStream_t stream)
+{
+    if (R < 1 || hid < 4 || (hid & 3) || !aligned16(gi) || !aligned16(gh) || !aligned16(hm) || !aligned16(b_ih) || !aligned16(b_hh) ||
+        !aligned16(h_out) || !aligned16(ws) || (hm_next && !aligned16(hm_next)) || (hm_next && !m_next)) return -1;
+    const size_t n = (size_t)R * (hid >> 2);
+    gru_gates_forward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gi, gh, hm, b_ih, b_hh, m_next, h_out, hm_next, ws, R, hid);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cn_launch_gru_gates_backward(const float *grad_h, const float *d_next, const float *m_next, const float *ws,
+                                            const float *hm, float *dgi, float *dgh, float *dhm, int R, int hid, cudaStream_t stream)
+{
+    if (R < 1 || hid < 4 || (hid & 3) || !aligned16(grad_h) || (d_next && (!aligned16(d_next) || !m_next)) || !aligned16(ws) ||
+        !aligned16(hm) || !aligned16(dgi) || !aligned16(dgh) || !aligned16(dhm)) return -1;
+    const size_t n = (size_t)R * (hid >> 2);
+    gru_gates_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_h, d_next, m_next, ws, hm, dgi, dgh, dhm, R, hid);
+    return (int)cudaGetLastError();
+}

@@ -40,37 +40,46 @@ class _MaskedGruSequence(torch.autograd.Function):
     every step where any env finished -- with thousands of envs that is every step).  One autograd node for the whole
     sequence instead of ~6 per step: the input projection of all T steps is one GEMM, the weight gradients are ONE
     [3h, T*R] x [T*R, k] GEMM each at the end of the backward (per-step weight-gradient GEMMs have a 768 x 320 output and
-    fill 60 of 148 SMs), only `h W_hh^T`, the gate kernel and their transposes run per step.  On CUDA the gate math is
-    ATen's fused GRU cell pair; elsewhere (CPU tests) the same formulas in plain torch.
+    fill 60 of 148 SMs), only `h W_hh^T`, the gate kernel and their transposes run per step: two launches per step in each
+    direction.  On CUDA the gate math is the library's `cn_gru_gates_forward / _backward` (csrc/dsrnn_train.cu), which also
+    apply the masks and write straight into the [T, ...] buffers; elsewhere (CPU tests) the same formulas in plain torch.
     """
 
     @staticmethod
     def forward(ctx, x, h0, m, w_ih, w_hh, b_ih, b_hh):
         T, R, hid = x.shape[0], x.shape[1], h0.shape[1]
-        fused = x.is_cuda
-        gi = torch.matmul(x, w_ih.t())                       # [T, R, 3h]; the cell adds both biases
+        cuda = x.is_cuda and x.dtype is torch.float32
+        gi = torch.matmul(x, w_ih.t())                       # [T, R, 3h]; the gate math adds both biases
         hs = x.new_empty(T, R, hid)
         hm = x.new_empty(T, R, hid)                          # masked previous state of every step
-        ws = x.new_empty(T, R, 5 * hid) if fused else x.new_empty(T, R, 4 * hid)
-        h = h0
+        ws = x.new_empty(T, R, 4 * hid)                      # r | z | n | W_hn hm + b_hn of every step
+        m = m.contiguous()
         w_hh_t = w_hh.t()
-        for t in range(T):
-            torch.mul(h, m[t], out=hm[t])
-            gh = torch.mm(hm[t], w_hh_t)
-            if fused:
-                h, w = torch.ops.aten._thnn_fused_gru_cell(gi[t], gh, hm[t], b_ih, b_hh)
-                ws[t].copy_(w)
-            else:
-                a, b = gi[t] + b_ih, gh + b_hh
+        torch.mul(h0, m[0], out=hm[0])
+        if cuda:
+            lib = _lib.load()
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            b_ih, b_hh = b_ih.contiguous(), b_hh.contiguous()
+            for t in range(T):
+                gh = torch.mm(hm[t], w_hh_t)
+                last = t == T - 1
+                _lib.check(lib.cn_gru_gates_forward(_ptr(gi[t]), _ptr(gh), _ptr(hm[t]), _ptr(b_ih), _ptr(b_hh),
+                                                    None if last else _ptr(m[t + 1]), _ptr(hs[t]),
+                                                    None if last else _ptr(hm[t + 1]), _ptr(ws[t]), R, hid, stream),
+                           "cn_gru_gates_forward")
+        else:                                                # CPU tests / float64 checks: the same formulas in torch
+            for t in range(T):
+                a, b = gi[t] + b_ih, torch.mm(hm[t], w_hh_t) + b_hh
                 r = torch.sigmoid(a[:, :hid] + b[:, :hid])
                 z = torch.sigmoid(a[:, hid:2 * hid] + b[:, hid:2 * hid])
                 hn = b[:, 2 * hid:]
                 n = torch.tanh(a[:, 2 * hid:] + r * hn)
-                h = n + z * (hm[t] - n)
-                ws[t].copy_(torch.cat([r, z, n, hn], 1))
-            hs[t].copy_(h)
+                hs[t] = n + z * (hm[t] - n)
+                ws[t] = torch.cat([r, z, n, hn], 1)
+                if t + 1 < T:
+                    torch.mul(hs[t], m[t + 1], out=hm[t + 1])
         ctx.save_for_backward(x, m, w_ih, w_hh, hm, ws)
-        ctx.fused = fused
+        ctx.cuda = cuda
         return hs
 
     @staticmethod
@@ -79,28 +88,32 @@ class _MaskedGruSequence(torch.autograd.Function):
         T, R, hid = hm.shape
         dgi = x.new_empty(T, R, 3 * hid)
         dgh = x.new_empty(T, R, 3 * hid)
-        dh = None
-        for t in range(T - 1, -1, -1):
-            g = grad_hs[t] if dh is None else grad_hs[t] + dh
-            if ctx.fused:
-                a, b, dhm, _, _ = torch.ops.aten._thnn_fused_gru_cell_backward(g.contiguous(), ws[t], True)
-                dgi[t].copy_(a)
-                dgh[t].copy_(b)
-            else:
+        d_next = None                                        # dL/d(masked state of step t+1)
+        if ctx.cuda:
+            lib = _lib.load()
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            grad_hs = grad_hs.contiguous()
+            dhm = x.new_empty(R, hid)
+            for t in range(T - 1, -1, -1):
+                _lib.check(lib.cn_gru_gates_backward(_ptr(grad_hs[t]), _ptr(d_next), None if d_next is None else _ptr(m[t + 1]),
+                                                     _ptr(ws[t]), _ptr(hm[t]), _ptr(dgi[t]), _ptr(dgh[t]), _ptr(dhm), R, hid, stream),
+                           "cn_gru_gates_backward")
+                d_next = torch.addmm(dhm, dgh[t], w_hh)
+        else:
+            for t in range(T - 1, -1, -1):
+                g = grad_hs[t] if d_next is None else grad_hs[t] + d_next * m[t + 1]
                 r, z, n, hn = ws[t].split(hid, 1)
                 dpre_n = g * (1.0 - z) * (1.0 - n * n)
                 dpre_r = dpre_n * hn * r * (1.0 - r)
                 dpre_z = g * (hm[t] - n) * z * (1.0 - z)
-                dgi[t].copy_(torch.cat([dpre_r, dpre_z, dpre_n], 1))
-                dgh[t].copy_(torch.cat([dpre_r, dpre_z, dpre_n * r], 1))
-                dhm = g * z
-            dhm = torch.addmm(dhm, dgh[t], w_hh)
-            dh = dhm * m[t]
+                dgi[t] = torch.cat([dpre_r, dpre_z, dpre_n], 1)
+                dgh[t] = torch.cat([dpre_r, dpre_z, dpre_n * r], 1)
+                d_next = torch.addmm(g * z, dgh[t], w_hh)
         dgi2, dgh2 = dgi.view(T * R, 3 * hid), dgh.view(T * R, 3 * hid)
         dx = torch.matmul(dgi, w_ih) if ctx.needs_input_grad[0] else None
         dw_ih = torch.mm(dgi2.t(), x.reshape(T * R, -1))
         dw_hh = torch.mm(dgh2.t(), hm.view(T * R, hid))
-        return dx, dh, None, dw_ih, dw_hh, dgi2.sum(0), dgh2.sum(0)
+        return dx, d_next * m[0], None, dw_ih, dw_hh, dgi2.sum(0), dgh2.sum(0)
 
 
 class _EdgeRNN(nn.Module):

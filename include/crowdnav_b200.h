@@ -247,6 +247,24 @@ int cn_dsrnn_time_ms(CnDsrnn *m, float *edge_stage_ms, int *n_forwards);
 int cn_env_enable_timing(CnEnv *env, int enable);
 int cn_env_time_ms(CnEnv *env, float *step_kernel_ms, int *n_steps);
 
+/*
+ * Training path (PPO update): the gate math of ONE step of a masked GRU sequence
+ * h_t = GRUCell(x_t, m_t * h_{t-1}) over R independent rows -- what nn.GRU does inside `_forward_gru`
+ * (srnn_model.py:53-104) between two mask boundaries, and its gradient.  The recurrent GEMMs are the caller's
+ * (cuBLAS); gate order r|z|n as in torch.nn.GRU.  All pointers are device float32, 16-byte aligned, hid % 4 == 0.
+ *
+ * forward:  gi = x_t W_ih^T, gh = hm W_hh^T [R,3 hid] (no biases), hm = m_t * h_{t-1} [R,hid], b_ih / b_hh [3 hid]
+ *           -> h_out [R,hid]; ws [R,4 hid] = r | z | n | (W_hn hm + b_hn) for the backward;
+ *              hm_next = m_next[row] * h_out (the next step's masked state) when hm_next != NULL.
+ * backward: g = grad_h + (d_next ? m_next[row] * d_next : 0), where d_next = dL/d(hm of step t+1)
+ *           -> dgi, dgh [R,3 hid] (gradients of gi and gh; bias gradients are their column sums), dhm = g * z
+ *              (the direct part of dL/d(hm); the caller adds dgh W_hh).
+ */
+int cn_gru_gates_forward(const float *gi, const float *gh, const float *hm, const float *b_ih, const float *b_hh,
+                         const float *m_next, float *h_out, float *hm_next, float *ws, int rows, int hid, void *stream);
+int cn_gru_gates_backward(const float *grad_h, const float *d_next, const float *m_next, const float *ws, const float *hm,
+                          float *dgi, float *dgh, float *dhm, int rows, int hid, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
