@@ -81,3 +81,47 @@ def test_batched_sequence_forward_equals_per_step_graph_on_gpu():
     from test_config_host import sequence_impls_agree
 
     sequence_impls_agree(torch.float32, DEV, 5e-4)
+
+
+@pytest.mark.parametrize("rows,hid", [(1, 128), (77, 256), (4099, 256)])
+def test_gru_gate_kernels_match_torch_reference(rows, hid):
+    """cn_gru_gates_forward / _backward through the C ABI against the same step written with torch fp32 ops + autograd."""
+    import ctypes as C
+
+    from crowdnav_dsrnn_b200 import _lib
+
+    lib = _lib.load()
+    ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    g = torch.Generator(device="cpu").manual_seed(rows + hid)
+    mk = lambda *shape: torch.randn(*shape, generator=g).to(DEV)
+    gi, gh, h_prev = mk(rows, 3 * hid).requires_grad_(True), mk(rows, 3 * hid).requires_grad_(True), mk(rows, hid)
+    b_ih, b_hh = mk(3 * hid), mk(3 * hid)
+    m_t = (torch.rand(rows, 1, generator=g) > 0.3).float().to(DEV)
+    m_next = (torch.rand(rows, 1, generator=g) > 0.3).float().to(DEV)
+    hm = (h_prev * m_t).requires_grad_(True)
+    # torch reference of the step (gate order r|z|n, torch.nn.GRU)
+    a, b = gi + b_ih, gh + b_hh
+    r = torch.sigmoid(a[:, :hid] + b[:, :hid])
+    z = torch.sigmoid(a[:, hid:2 * hid] + b[:, hid:2 * hid])
+    n = torch.tanh(a[:, 2 * hid:] + r * b[:, 2 * hid:])
+    h_ref = n + z * (hm - n)
+    grad_h, d_next = mk(rows, hid), mk(rows, hid)
+    h_ref.backward(grad_h + d_next * m_next)
+    stream = C.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
+    h_out, hm_next, ws = torch.empty(rows, hid, device=DEV), torch.empty(rows, hid, device=DEV), torch.empty(rows, 4 * hid, device=DEV)
+    _lib.check(lib.cn_gru_gates_forward(ptr(gi.detach()), ptr(gh.detach()), ptr(hm.detach()), ptr(b_ih), ptr(b_hh), ptr(m_next),
+                                        ptr(h_out), ptr(hm_next), ptr(ws), rows, hid, stream), "cn_gru_gates_forward")
+    dgi, dgh, dhm = torch.empty(rows, 3 * hid, device=DEV), torch.empty(rows, 3 * hid, device=DEV), torch.empty(rows, hid, device=DEV)
+    _lib.check(lib.cn_gru_gates_backward(ptr(grad_h), ptr(d_next), ptr(m_next), ptr(ws), ptr(hm.detach()), ptr(dgi), ptr(dgh),
+                                         ptr(dhm), rows, hid, stream), "cn_gru_gates_backward")
+    torch.cuda.synchronize()
+    tol = 2e-5      # fp32 with fused multiply-adds and libdevice expf / tanhf vs ATen's
+    for got, want in ((h_out, h_ref.detach()), (hm_next, h_ref.detach() * m_next), (ws[:, :hid], r.detach()),
+                      (ws[:, hid:2 * hid], z.detach()), (ws[:, 2 * hid:3 * hid], n.detach()), (dgi, gi.grad), (dgh, gh.grad),
+                      (dhm, hm.grad)):
+        assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+    # bad arguments are refused, not launched
+    assert lib.cn_gru_gates_forward(ptr(gi.detach()), ptr(gh.detach()), ptr(hm.detach()), ptr(b_ih), ptr(b_hh), None, ptr(h_out),
+                                    ptr(hm_next), ptr(ws), rows, hid, stream) == -1
+    assert lib.cn_gru_gates_backward(ptr(grad_h), ptr(d_next), ptr(m_next), ptr(ws), ptr(hm.detach()), ptr(dgi), ptr(dgh), ptr(dhm),
+                                     rows, 6, stream) == -1
