@@ -6,7 +6,8 @@
 //             workspace, and the MASKED state of the next step (h_t * m_{t+1}, the next GEMM's operand);
 //   backward: g = dL/dh_t + m_{t+1} * dL/d(masked state of step t+1) formed in registers, then the gate gradients
 //             straight into the [T, R, 3 hid] buffers the single weight-gradient GEMMs read at the end.
-// HBM-bound, one thread per four hidden units (float4 everywhere): 17 floats of traffic per hidden unit forward, 20 backward.
+// HBM-bound, one thread per four hidden units (float4 everywhere): 13 floats of traffic per hidden unit forward, 14 backward
+// (52 / 56 B; measured 38 / 42 us for 20480 rows x 256 = 7.1 / 7.0 TB/s, profiles/r1_ncu_gate_kernels.txt).
 #include <cuda_runtime.h>
 #include <stdint.h>
 

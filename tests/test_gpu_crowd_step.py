@@ -14,6 +14,17 @@ import gpu_helpers as G
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["group", "thread"])
+def phase_a_form(request, monkeypatch):
+    """Every case runs with both forms of the kernel's ORCA phase: one lane group per human (the default) and one thread
+    per human (CN_STEP_SEQ=1, read by the launcher at every call) -- they must give the same bits."""
+    if request.param == "thread":
+        monkeypatch.setenv("CN_STEP_SEQ", "1")
+    else:
+        monkeypatch.delenv("CN_STEP_SEQ", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("name", STEP_CASES)
 def test_step_matches_reference_golden_and_oracle(name):
     d, cfg_obj, cfg, n = load_step_case(name)
