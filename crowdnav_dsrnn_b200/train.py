@@ -58,8 +58,12 @@ def train(config, device=None, num_updates=None, output_dir=None, actor_critic=N
     out_dir = output_dir if output_dir is not None else config.training.output_dir
     if rank == 0 and out_dir:
         os.makedirs(os.path.join(out_dir, "checkpoints"), exist_ok=True)
-    # device-side episode statistics: [success, collision, timeout, episodes, return sum]
+    # device-side episode statistics: [success, collision, timeout, episodes, return sum], reduced ONCE per update from the
+    # per-step event / done / episode-return records (three small copies per step instead of ~20 reduction launches)
     stats = torch.zeros(5, dtype=torch.float64, device=device)
+    ev_rec = torch.zeros(T, N, dtype=torch.int32, device=device)
+    done_rec = torch.zeros(T, N, dtype=torch.bool, device=device)
+    ret_rec = torch.zeros(T, N, dtype=torch.float32, device=device)
     history = []
     start = time.time()
     for j in range(num_updates):
@@ -70,12 +74,15 @@ def train(config, device=None, num_updates=None, output_dir=None, actor_critic=N
             value, action, log_prob, hx = actor_critic.act(rollouts.obs_at(step), dict(rollouts.hidden_at(step)),
                                                            rollouts.masks[step])
             obs, reward, done, buf = envs.step_device(action)
-            d = done.to(torch.float64)
-            stats += torch.stack([((buf.event == abi.EV_REACH_GOAL).to(torch.float64) * d).sum(),
-                                  ((buf.event == abi.EV_COLLISION).to(torch.float64) * d).sum(),
-                                  ((buf.event == abi.EV_TIMEOUT).to(torch.float64) * d).sum(), d.sum(),
-                                  (buf.episode_return.to(torch.float64) * d).sum()])
+            ev_rec[step].copy_(buf.event.view(N))
+            done_rec[step].copy_(done.view(N))
+            ret_rec[step].copy_(buf.episode_return.view(N))
             rollouts.insert(obs, hx, action, log_prob, value, reward, buf.not_done, None)     # masks = 1 - done
+        d = done_rec.to(torch.float64)
+        stats.copy_(torch.stack([((ev_rec == abi.EV_REACH_GOAL) & done_rec).sum().double(),
+                                 ((ev_rec == abi.EV_COLLISION) & done_rec).sum().double(),
+                                 ((ev_rec == abi.EV_TIMEOUT) & done_rec).sum().double(), d.sum(),
+                                 (ret_rec.to(torch.float64) * d).sum()]))
         next_value = actor_critic.get_value(rollouts.obs_at(-1), dict(rollouts.hidden_at(-1)), rollouts.masks[-1]).detach()
         rollouts.compute_returns(next_value, config.ppo.use_gae, config.reward.gamma, config.ppo.gae_lambda,
                                  config.training.use_proper_time_limits)
