@@ -33,6 +33,26 @@ def _orthogonal(module, gain=1.0):
     return module
 
 
+# GEMM arithmetic of the masked GRU sequences' recurrent products (PPO update): "fp32" = torch's fp32 matmul (SIMT, or TF32
+# when torch.backends.cuda.matmul.allow_tf32 is set), "bf16x3" = split-bf16 3-pass on the tensor cores with fp32 accumulation
+# (A_hi B_hi + A_lo B_hi + A_hi B_lo, operand error ~2^-16: the rollout kernels' precision), CUDA only.
+SEQUENCE_GEMM = "fp32"
+
+
+def _split_bf16(a):
+    hi = a.to(torch.bfloat16)
+    return hi, torch.sub(a, hi).to(torch.bfloat16)
+
+
+def _mm_bf16x3(a, b_hi, b_lo, add=None):
+    """a [M,K] fp32 times (b_hi + b_lo) [K,N] (bf16 pair), fp32 result (+ add)."""
+    a_hi, a_lo = _split_bf16(a)
+    f32 = torch.float32
+    out = torch.mm(a_hi, b_hi, out_dtype=f32) if add is None else torch.addmm(add, a_hi, b_hi, out_dtype=f32)
+    out = torch.addmm(out, a_lo, b_hi, out_dtype=f32)
+    return torch.addmm(out, a_hi, b_lo, out_dtype=f32)
+
+
 class _MaskedGruSequence(torch.autograd.Function):
     """h_t = GRUCell(x_t, m_t * h_{t-1}) for t < T over R independent rows, returned as [T, R, hidden].
 
@@ -60,8 +80,11 @@ class _MaskedGruSequence(torch.autograd.Function):
             lib = _lib.load()
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
             b_ih, b_hh = b_ih.contiguous(), b_hh.contiguous()
+            x3 = SEQUENCE_GEMM == "bf16x3"
+            if x3:
+                wt_hi, wt_lo = _split_bf16(w_hh_t.contiguous())
             for t in range(T):
-                gh = torch.mm(hm[t], w_hh_t)
+                gh = _mm_bf16x3(hm[t], wt_hi, wt_lo) if x3 else torch.mm(hm[t], w_hh_t)
                 last = t == T - 1
                 _lib.check(lib.cn_gru_gates_forward(_ptr(gi[t]), _ptr(gh), _ptr(hm[t]), _ptr(b_ih), _ptr(b_hh),
                                                     None if last else _ptr(m[t + 1]), _ptr(hs[t]),
@@ -80,6 +103,7 @@ class _MaskedGruSequence(torch.autograd.Function):
                     torch.mul(hs[t], m[t + 1], out=hm[t + 1])
         ctx.save_for_backward(x, m, w_ih, w_hh, hm, ws)
         ctx.cuda = cuda
+        ctx.x3 = cuda and SEQUENCE_GEMM == "bf16x3"
         return hs
 
     @staticmethod
@@ -94,11 +118,13 @@ class _MaskedGruSequence(torch.autograd.Function):
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
             grad_hs = grad_hs.contiguous()
             dhm = x.new_empty(R, hid)
+            if ctx.x3:
+                w_hi, w_lo = _split_bf16(w_hh)
             for t in range(T - 1, -1, -1):
                 _lib.check(lib.cn_gru_gates_backward(_ptr(grad_hs[t]), _ptr(d_next), None if d_next is None else _ptr(m[t + 1]),
                                                      _ptr(ws[t]), _ptr(hm[t]), _ptr(dgi[t]), _ptr(dgh[t]), _ptr(dhm), R, hid, stream),
                            "cn_gru_gates_backward")
-                d_next = torch.addmm(dhm, dgh[t], w_hh)
+                d_next = _mm_bf16x3(dgh[t], w_hi, w_lo, add=dhm) if ctx.x3 else torch.addmm(dhm, dgh[t], w_hh)
         else:
             for t in range(T - 1, -1, -1):
                 g = grad_hs[t] if d_next is None else grad_hs[t] + d_next * m[t + 1]
@@ -112,7 +138,15 @@ class _MaskedGruSequence(torch.autograd.Function):
         dgi2, dgh2 = dgi.view(T * R, 3 * hid), dgh.view(T * R, 3 * hid)
         dx = torch.matmul(dgi, w_ih) if ctx.needs_input_grad[0] else None
         dw_ih = torch.mm(dgi2.t(), x.reshape(T * R, -1))
-        dw_hh = torch.mm(dgh2.t(), hm.view(T * R, hid))
+        if ctx.x3:
+            b_hi, b_lo = _split_bf16(hm.view(T * R, hid))
+            a_hi, a_lo = _split_bf16(dgh2)
+            f32 = torch.float32
+            dw_hh = torch.mm(a_hi.t(), b_hi, out_dtype=f32)
+            dw_hh = torch.addmm(dw_hh, a_lo.t(), b_hi, out_dtype=f32)
+            dw_hh = torch.addmm(dw_hh, a_hi.t(), b_lo, out_dtype=f32)
+        else:
+            dw_hh = torch.mm(dgh2.t(), hm.view(T * R, hid))
         return dx, d_next * m[0], None, dw_ih, dw_hh, dgi2.sum(0), dgh2.sum(0)
 
 

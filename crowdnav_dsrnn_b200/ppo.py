@@ -43,7 +43,7 @@ def normalized_advantages(rollouts, group=None):
 
 class PPO:
     def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef, lr=None, eps=None,
-                 max_grad_norm=None, use_clipped_value_loss=True, group=None, max_envs_per_pass=None, tf32=False):
+                 max_grad_norm=None, use_clipped_value_loss=True, group=None, max_envs_per_pass=None, tf32=False, bf16x3=False):
         self.actor_critic = actor_critic
         self.clip_param = clip_param
         self.ppo_epoch = ppo_epoch
@@ -54,7 +54,8 @@ class PPO:
         self.use_clipped_value_loss = use_clipped_value_loss
         self.group = group
         self.max_envs_per_pass = max_envs_per_pass
-        self.tf32 = bool(tf32)         # TF32 tensor cores for the fp32 GEMMs of the update's forward + backward (-20 % update time)
+        self.tf32 = bool(tf32)         # TF32 tensor cores for the fp32 GEMMs of the update's forward + backward
+        self.bf16x3 = bool(bf16x3)     # split-bf16 3-pass tensor-core GEMMs (fp32-level accuracy) for the recurrent products
         self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, eps=eps)
         self.perm_fn = None            # tests / reproducibility: callable(num_processes) -> env permutation
         self.allreduce_calls = 0
@@ -92,12 +93,17 @@ class PPO:
 
     # ------------------------------------------------------------------ reference interface
     def update(self, rollouts):
-        prev = torch.backends.cuda.matmul.allow_tf32
+        from . import model as _model
+
+        prev, prev_gemm = torch.backends.cuda.matmul.allow_tf32, _model.SEQUENCE_GEMM
         torch.backends.cuda.matmul.allow_tf32 = prev or self.tf32
+        if self.bf16x3:
+            _model.SEQUENCE_GEMM = "bf16x3"
         try:
             return self._update(rollouts)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
+            _model.SEQUENCE_GEMM = prev_gemm
 
     def _update(self, rollouts):
         advantages = normalized_advantages(rollouts, self.group)

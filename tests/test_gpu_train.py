@@ -125,3 +125,12 @@ def test_gru_gate_kernels_match_torch_reference(rows, hid):
                                     ptr(hm_next), ptr(ws), rows, hid, stream) == -1
     assert lib.cn_gru_gates_backward(ptr(grad_h), ptr(d_next), ptr(m_next), ptr(ws), ptr(hm.detach()), ptr(dgi), ptr(dgh), ptr(dhm),
                                      rows, 6, stream) == -1
+
+
+def test_bf16x3_recurrent_gemms_keep_fp32_level_accuracy(monkeypatch):
+    """PPO(bf16x3=True): the recurrent products of the masked GRU sequences as split-bf16 3-pass tensor-core GEMMs."""
+    from crowdnav_dsrnn_b200 import model as model_mod
+    from test_config_host import sequence_impls_agree
+
+    monkeypatch.setattr(model_mod, "SEQUENCE_GEMM", "bf16x3")      # only the batched form reads it; per_step stays fp32
+    sequence_impls_agree(torch.float32, DEV, 1e-3)

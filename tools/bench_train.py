@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--updates", type=int, default=3)
     ap.add_argument("--per-pass", type=int, default=1024)
     ap.add_argument("--tf32", action="store_true", help="TF32 tensor cores for the torch GEMMs of the update (fwd + bwd)")
+    ap.add_argument("--bf16x3", action="store_true", help="split-bf16 3-pass tensor-core GEMMs for the recurrent products of the update")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -55,11 +56,12 @@ def main():
         return out
 
     ppo_mod.PPO.update = timed
-    train_mod.train(cfg, dev, num_updates=1, output_dir=None, log=None, max_envs_per_pass=args.per_pass)   # warm-up
+    train_mod.train(cfg, dev, num_updates=1, output_dir=None, log=None, max_envs_per_pass=args.per_pass, bf16x3_update=args.bf16x3)   # warm-up
     spent["update"] = 0.0
     torch.cuda.synchronize()
     t0 = time.time()
-    _, hist = train_mod.train(cfg, dev, num_updates=args.updates, output_dir=None, log=None, max_envs_per_pass=args.per_pass)
+    _, hist = train_mod.train(cfg, dev, num_updates=args.updates, output_dir=None, log=None, max_envs_per_pass=args.per_pass,
+                               bf16x3_update=args.bf16x3)
     torch.cuda.synchronize()
     wall = time.time() - t0
     steps = args.updates * args.envs * world * cfg.ppo.num_steps

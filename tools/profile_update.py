@@ -22,10 +22,14 @@ def main():
     ap.add_argument("--humans", type=int, default=20)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--tf32", action="store_true")
+    ap.add_argument("--bf16x3", action="store_true", help="model.SEQUENCE_GEMM = 'bf16x3'")
     ap.add_argument("--per-step", action="store_true", help="the per-step autograd graph (Policy.sequence_impl='per_step')")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.backends.cuda.matmul.allow_tf32 = args.tf32
+    if args.bf16x3:
+        from crowdnav_dsrnn_b200 import model as model_mod
+        model_mod.SEQUENCE_GEMM = "bf16x3"
     n, H, T = args.envs, args.humans, args.steps
     cfg = Config(human_num=H)
     obs_space, act_space = crowd_spaces(H)
@@ -55,8 +59,8 @@ def main():
         one_pass()
     e1.record()
     torch.cuda.synchronize()
-    print("pass of %d envs x %d humans x %d steps: %.2f ms (tf32=%s, per_step=%s), peak mem %.2f GB" % (
-        n, H, T, e0.elapsed_time(e1) / 3, args.tf32, args.per_step, torch.cuda.max_memory_allocated() / 2**30))
+    print("pass of %d envs x %d humans x %d steps: %.2f ms (tf32=%s, per_step=%s, bf16x3=%s), peak mem %.2f GB" % (
+        n, H, T, e0.elapsed_time(e1) / 3, args.tf32, args.per_step, args.bf16x3, torch.cuda.max_memory_allocated() / 2**30))
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         one_pass()
