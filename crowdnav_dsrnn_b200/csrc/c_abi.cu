@@ -390,3 +390,13 @@ extern "C" int cn_gru_gates_backward(const float *grad_h, const float *d_next, c
     if (rc != 0) return fail(CN_ERR_CUDA, "gru_gates_backward_kernel: %s", cudaGetErrorString((cudaError_t)rc));
     return CN_OK;
 }
+
+extern "C" int cn_launch_split_bf16(const float *a, void *hi, void *lo, size_t n, cudaStream_t stream);
+extern "C" int cn_split_bf16(const float *a, void *hi, void *lo, size_t n, void *stream)
+{
+    if (!a || !hi || !lo) return fail(CN_ERR_ARG, "cn_split_bf16: NULL pointer");
+    const int rc = cn_launch_split_bf16(a, hi, lo, n, (cudaStream_t)stream);
+    if (rc == -1) return fail(CN_ERR_ARG, "cn_split_bf16: n %zu must be a positive multiple of 4, a 16-byte and hi / lo 8-byte aligned", n);
+    if (rc != 0) return fail(CN_ERR_CUDA, "split_bf16_kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    return CN_OK;
+}

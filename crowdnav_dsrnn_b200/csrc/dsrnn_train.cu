@@ -9,6 +9,7 @@
 // HBM-bound, one thread per four hidden units (float4 everywhere): 13 floats of traffic per hidden unit forward, 14 backward
 // (52 / 56 B; measured 38 / 42 us for 20480 rows x 256 = 7.1 / 7.0 TB/s, profiles/r1_ncu_gate_kernels.txt).
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace {
@@ -89,6 +90,24 @@ gru_gates_backward_kernel(const float *__restrict__ grad_h, const float *__restr
     st4(dhm + (size_t)row * hid + c, dh);
 }
 
+// a = hi + lo with hi = bf16(a), lo = bf16(a - hi): the operand pair of a split-bf16 3-pass GEMM (error ~2^-16 relative)
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float *__restrict__ a, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, size_t n4)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4 *>(a)[i];
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[k] = __float2bfloat16_rn(x[k]);
+        l[k] = __float2bfloat16_rn(x[k] - __bfloat162float(h[k]));
+    }
+    reinterpret_cast<uint2 *>(hi)[i] = *reinterpret_cast<const uint2 *>(h);
+    reinterpret_cast<uint2 *>(lo)[i] = *reinterpret_cast<const uint2 *>(l);
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -112,5 +131,13 @@ extern "C" int cn_launch_gru_gates_backward(const float *grad_h, const float *d_
         !aligned16(hm) || !aligned16(dgi) || !aligned16(dgh) || !aligned16(dhm)) return -1;
     const size_t n = (size_t)R * (hid >> 2);
     gru_gates_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_h, d_next, m_next, ws, hm, dgi, dgh, dhm, R, hid);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cn_launch_split_bf16(const float *a, void *hi, void *lo, size_t n, cudaStream_t stream)
+{
+    if (n == 0 || (n & 3) || !aligned16(a) || (reinterpret_cast<uintptr_t>(hi) & 7u) || (reinterpret_cast<uintptr_t>(lo) & 7u)) return -1;
+    const size_t n4 = n >> 2;
+    split_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(a, static_cast<__nv_bfloat16 *>(hi), static_cast<__nv_bfloat16 *>(lo), n4);
     return (int)cudaGetLastError();
 }

@@ -40,17 +40,30 @@ SEQUENCE_GEMM = "fp32"
 
 
 def _split_bf16(a):
-    hi = a.to(torch.bfloat16)
-    return hi, torch.sub(a, hi).to(torch.bfloat16)
+    """a (fp32, CUDA) -> (hi, lo) bf16 with a ~= hi + lo to 2^-16 relative; one pass over a (cn_split_bf16)."""
+    a = a.contiguous()
+    hi = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    lo = torch.empty_like(hi)
+    if a.numel() % 4 == 0 and a.numel() > 0:
+        stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+        _lib.check(_lib.load().cn_split_bf16(_ptr(a), _ptr(hi), _ptr(lo), a.numel(), stream), "cn_split_bf16")
+    else:                                                    # sizes the kernel does not take (never on the DS-RNN shapes)
+        hi = a.to(torch.bfloat16)
+        lo = torch.sub(a, hi).to(torch.bfloat16)
+    return hi, lo
 
 
-def _mm_bf16x3(a, b_hi, b_lo, add=None):
-    """a [M,K] fp32 times (b_hi + b_lo) [K,N] (bf16 pair), fp32 result (+ add)."""
-    a_hi, a_lo = _split_bf16(a)
+def _mm3(a_hi, a_lo, b_hi, b_lo, add=None):
+    """(a_hi + a_lo) [M,K] times (b_hi + b_lo) [K,N] (bf16 pairs) without the lo*lo term, fp32 accumulation and result (+ add)."""
     f32 = torch.float32
     out = torch.mm(a_hi, b_hi, out_dtype=f32) if add is None else torch.addmm(add, a_hi, b_hi, out_dtype=f32)
     out = torch.addmm(out, a_lo, b_hi, out_dtype=f32)
     return torch.addmm(out, a_hi, b_lo, out_dtype=f32)
+
+
+def _mm_bf16x3(a, b_hi, b_lo, add=None):
+    a_hi, a_lo = _split_bf16(a)
+    return _mm3(a_hi, a_lo, b_hi, b_lo, add)
 
 
 class _MaskedGruSequence(torch.autograd.Function):
@@ -69,7 +82,11 @@ class _MaskedGruSequence(torch.autograd.Function):
     def forward(ctx, x, h0, m, w_ih, w_hh, b_ih, b_hh):
         T, R, hid = x.shape[0], x.shape[1], h0.shape[1]
         cuda = x.is_cuda and x.dtype is torch.float32
-        gi = torch.matmul(x, w_ih.t())                       # [T, R, 3h]; the gate math adds both biases
+        x3 = cuda and SEQUENCE_GEMM == "bf16x3"
+        if x3:
+            gi = _mm_bf16x3(x.reshape(T * R, -1), *_split_bf16(w_ih.t())).view(T, R, 3 * hid)
+        else:
+            gi = torch.matmul(x, w_ih.t())                   # [T, R, 3h]; the gate math adds both biases
         hs = x.new_empty(T, R, hid)
         hm = x.new_empty(T, R, hid)                          # masked previous state of every step
         ws = x.new_empty(T, R, 4 * hid)                      # r | z | n | W_hn hm + b_hn of every step
@@ -80,9 +97,8 @@ class _MaskedGruSequence(torch.autograd.Function):
             lib = _lib.load()
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
             b_ih, b_hh = b_ih.contiguous(), b_hh.contiguous()
-            x3 = SEQUENCE_GEMM == "bf16x3"
             if x3:
-                wt_hi, wt_lo = _split_bf16(w_hh_t.contiguous())
+                wt_hi, wt_lo = _split_bf16(w_hh_t)
             for t in range(T):
                 gh = _mm_bf16x3(hm[t], wt_hi, wt_lo) if x3 else torch.mm(hm[t], w_hh_t)
                 last = t == T - 1
@@ -103,7 +119,7 @@ class _MaskedGruSequence(torch.autograd.Function):
                     torch.mul(hs[t], m[t + 1], out=hm[t + 1])
         ctx.save_for_backward(x, m, w_ih, w_hh, hm, ws)
         ctx.cuda = cuda
-        ctx.x3 = cuda and SEQUENCE_GEMM == "bf16x3"
+        ctx.x3 = x3
         return hs
 
     @staticmethod
@@ -136,16 +152,16 @@ class _MaskedGruSequence(torch.autograd.Function):
                 dgh[t] = torch.cat([dpre_r, dpre_z, dpre_n * r], 1)
                 d_next = torch.addmm(g * z, dgh[t], w_hh)
         dgi2, dgh2 = dgi.view(T * R, 3 * hid), dgh.view(T * R, 3 * hid)
-        dx = torch.matmul(dgi, w_ih) if ctx.needs_input_grad[0] else None
-        dw_ih = torch.mm(dgi2.t(), x.reshape(T * R, -1))
         if ctx.x3:
-            b_hi, b_lo = _split_bf16(hm.view(T * R, hid))
+            a_hi, a_lo = _split_bf16(dgi2)
+            dx = _mm3(a_hi, a_lo, *_split_bf16(w_ih)).view(T, R, -1) if ctx.needs_input_grad[0] else None
+            dw_ih = _mm3(a_hi.t(), a_lo.t(), *_split_bf16(x.reshape(T * R, -1)))
             a_hi, a_lo = _split_bf16(dgh2)
-            f32 = torch.float32
-            dw_hh = torch.mm(a_hi.t(), b_hi, out_dtype=f32)
-            dw_hh = torch.addmm(dw_hh, a_lo.t(), b_hi, out_dtype=f32)
-            dw_hh = torch.addmm(dw_hh, a_hi.t(), b_lo, out_dtype=f32)
+            dw_hh = _mm3(a_hi.t(), a_lo.t(), *_split_bf16(hm.view(T * R, hid)))
+            del a_hi, a_lo
         else:
+            dx = torch.matmul(dgi, w_ih) if ctx.needs_input_grad[0] else None
+            dw_ih = torch.mm(dgi2.t(), x.reshape(T * R, -1))
             dw_hh = torch.mm(dgh2.t(), hm.view(T * R, hid))
         return dx, d_next * m[0], None, dw_ih, dw_hh, dgi2.sum(0), dgh2.sum(0)
 

@@ -264,6 +264,10 @@ int cn_gru_gates_forward(const float *gi, const float *gh, const float *hm, cons
                          const float *m_next, float *h_out, float *hm_next, float *ws, int rows, int hid, void *stream);
 int cn_gru_gates_backward(const float *grad_h, const float *d_next, const float *m_next, const float *ws, const float *hm,
                           float *dgi, float *dgh, float *dhm, int rows, int hid, void *stream);
+/* a[n] float32 -> hi[n], lo[n] bfloat16 with hi = bf16(a), lo = bf16(a - hi): the operand pair of the split-bf16 3-pass
+ * tensor-core products (A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulation) the update can use for its recurrent GEMMs
+ * (same arithmetic as the rollout's CN_PREC_BF16X3).  n % 4 == 0. */
+int cn_split_bf16(const float *a, void *hi, void *lo, size_t n, void *stream);
 
 #ifdef __cplusplus
 }

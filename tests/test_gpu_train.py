@@ -132,5 +132,9 @@ def test_bf16x3_recurrent_gemms_keep_fp32_level_accuracy(monkeypatch):
     from crowdnav_dsrnn_b200 import model as model_mod
     from test_config_host import sequence_impls_agree
 
+    a = torch.randn(1000, 260, device=DEV) * torch.logspace(-3, 3, 260, device=DEV)
+    hi, lo = model_mod._split_bf16(a)                               # cn_split_bf16
+    assert hi.dtype is torch.bfloat16 and torch.equal(hi, a.to(torch.bfloat16))
+    assert ((hi.float() + lo.float() - a).abs() <= a.abs() * 2.0 ** -16).all()
     monkeypatch.setattr(model_mod, "SEQUENCE_GEMM", "bf16x3")      # only the batched form reads it; per_step stays fp32
     sequence_impls_agree(torch.float32, DEV, 1e-3)
