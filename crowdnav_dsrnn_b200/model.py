@@ -57,8 +57,9 @@ def _mm3(a_hi, a_lo, b_hi, b_lo, add=None):
     """(a_hi + a_lo) [M,K] times (b_hi + b_lo) [K,N] (bf16 pairs) without the lo*lo term, fp32 accumulation and result (+ add)."""
     f32 = torch.float32
     out = torch.mm(a_hi, b_hi, out_dtype=f32) if add is None else torch.addmm(add, a_hi, b_hi, out_dtype=f32)
-    out = torch.addmm(out, a_lo, b_hi, out_dtype=f32)
-    return torch.addmm(out, a_hi, b_lo, out_dtype=f32)
+    torch.addmm(out, a_lo, b_hi, out_dtype=f32, out=out)         # accumulate in place: no copy of the fp32 result per pass
+    torch.addmm(out, a_hi, b_lo, out_dtype=f32, out=out)
+    return out
 
 
 def _mm_bf16x3(a, b_hi, b_lo, add=None):
