@@ -10,8 +10,10 @@ fallback; tensors must live on a B200.  Batch size and human count are read
 from the tensor shapes (the reference bakes them from config,
 srnn_model.py:361-363,410-418).
 
-Training path (`evaluate_actions`): the same math written
-with differentiable torch ops over the T x N rollout chunk.
+Training path (`evaluate_actions`): the same math over the
+T x N rollout chunk, differentiable: masked GRU sequences (`_MaskedGruSequence`:
+cuBLAS GEMMs + the library's gate kernels, csrc/dsrnn_train.cu) and batched
+torch ops for everything without a recurrence.
 """
 import ctypes as C
 import math

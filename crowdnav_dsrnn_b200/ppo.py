@@ -12,8 +12,10 @@ Added for the sharded rollout (BASELINE.json configs[4]: envs sharded over 1/2/4
 * `max_envs_per_pass`: a minibatch is processed in sub-chunks of whole env trajectories with gradient accumulation
   (same gradient, bounded activation memory: T=30 steps x 21 edges x 768 gate columns per env are kept for backward).
 
-The rollout forward (`Policy.act`) is the CUDA hot path; the differentiable sequence forward used here is the torch
-restatement in model.py (`Policy.evaluate_actions`), autograd does the backward.
+The rollout forward (`Policy.act`) is the CUDA hot path.  The differentiable sequence forward used here is
+`Policy.evaluate_actions` (model.py): the recurrent units run as masked GRU sequences -- one autograd node each, cuBLAS
+GEMMs (fp32, `tf32=True`, or split-bf16 3-pass with `bf16x3=True`) around the library's hand-written gate kernels
+(csrc/dsrnn_train.cu) -- and everything without a recurrence is evaluated for the whole [T, n] chunk in one batch.
 """
 import torch
 import torch.distributed as dist
