@@ -41,8 +41,8 @@ SYMBOLS = {
     "cn_dsrnn_time_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "cn_env_enable_timing": (C.c_int, [_P, C.c_int]),
     "cn_env_time_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
-    "cn_gru_gates_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
-    "cn_gru_gates_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "cn_gru_gates_forward": (C.c_int, [_P] * 11 + [C.c_int, C.c_int, _P]),
+    "cn_gru_gates_backward": (C.c_int, [_P] * 12 + [C.c_int, C.c_int, _P]),
     "cn_split_bf16": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
 }
 

@@ -366,27 +366,34 @@ extern "C" int cn_dsrnn_time_ms(CnDsrnn *m, float *edge_stage_ms, int *n_forward
 
 // ---------------------------------------------------------------------------------------------- training path (dsrnn_train.cu)
 extern "C" int cn_launch_gru_gates_forward(const float *gi, const float *gh, const float *hm, const float *b_ih, const float *b_hh,
-                                           const float *m_next, float *h_out, float *hm_next, float *ws, int R, int hid,
-                                           cudaStream_t stream);
+                                           const float *m_next, float *h_out, float *hm_next, float *ws, void *hm_next_hi,
+                                           void *hm_next_lo, int R, int hid, cudaStream_t stream);
 extern "C" int cn_launch_gru_gates_backward(const float *grad_h, const float *d_next, const float *m_next, const float *ws,
-                                            const float *hm, float *dgi, float *dgh, float *dhm, int R, int hid, cudaStream_t stream);
+                                            const float *hm, float *dgi, float *dgh, float *dhm, void *const *pairs, int R, int hid,
+                                            cudaStream_t stream);
 
 extern "C" int cn_gru_gates_forward(const float *gi, const float *gh, const float *hm, const float *b_ih, const float *b_hh,
-                                    const float *m_next, float *h_out, float *hm_next, float *ws, int rows, int hid, void *stream)
+                                    const float *m_next, float *h_out, float *hm_next, float *ws, void *hm_next_hi, void *hm_next_lo,
+                                    int rows, int hid, void *stream)
 {
     if (!gi || !gh || !hm || !b_ih || !b_hh || !h_out || !ws) return fail(CN_ERR_ARG, "cn_gru_gates_forward: NULL pointer");
-    const int rc = cn_launch_gru_gates_forward(gi, gh, hm, b_ih, b_hh, m_next, h_out, hm_next, ws, rows, hid, (cudaStream_t)stream);
-    if (rc == -1) return fail(CN_ERR_ARG, "cn_gru_gates_forward: rows %d / hid %d / alignment / hm_next without m_next", rows, hid);
+    const int rc = cn_launch_gru_gates_forward(gi, gh, hm, b_ih, b_hh, m_next, h_out, hm_next, ws, hm_next_hi, hm_next_lo, rows, hid,
+                                               (cudaStream_t)stream);
+    if (rc == -1) return fail(CN_ERR_ARG, "cn_gru_gates_forward: rows %d / hid %d / alignment / hm_next without m_next / half a bf16 pair", rows, hid);
     if (rc != 0) return fail(CN_ERR_CUDA, "gru_gates_forward_kernel: %s", cudaGetErrorString((cudaError_t)rc));
     return CN_OK;
 }
 
 extern "C" int cn_gru_gates_backward(const float *grad_h, const float *d_next, const float *m_next, const float *ws, const float *hm,
-                                     float *dgi, float *dgh, float *dhm, int rows, int hid, void *stream)
+                                     float *dgi, float *dgh, float *dhm, void *dgi_hi, void *dgi_lo, void *dgh_hi, void *dgh_lo,
+                                     int rows, int hid, void *stream)
 {
     if (!grad_h || !ws || !hm || !dgi || !dgh || !dhm) return fail(CN_ERR_ARG, "cn_gru_gates_backward: NULL pointer");
-    const int rc = cn_launch_gru_gates_backward(grad_h, d_next, m_next, ws, hm, dgi, dgh, dhm, rows, hid, (cudaStream_t)stream);
-    if (rc == -1) return fail(CN_ERR_ARG, "cn_gru_gates_backward: rows %d / hid %d / alignment / d_next without m_next", rows, hid);
+    void *pairs[4] = {dgi_hi, dgi_lo, dgh_hi, dgh_lo};
+    const bool any = dgi_hi || dgi_lo || dgh_hi || dgh_lo;
+    const int rc = cn_launch_gru_gates_backward(grad_h, d_next, m_next, ws, hm, dgi, dgh, dhm, any ? pairs : nullptr, rows, hid,
+                                                (cudaStream_t)stream);
+    if (rc == -1) return fail(CN_ERR_ARG, "cn_gru_gates_backward: rows %d / hid %d / alignment / d_next without m_next / incomplete bf16 pairs", rows, hid);
     if (rc != 0) return fail(CN_ERR_CUDA, "gru_gates_backward_kernel: %s", cudaGetErrorString((cudaError_t)rc));
     return CN_OK;
 }

@@ -19,11 +19,24 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 struct F4 { float v[4]; };
 __device__ __forceinline__ F4 ld4(const float *p) { const float4 t = *reinterpret_cast<const float4 *>(p); return F4{{t.x, t.y, t.z, t.w}}; }
 __device__ __forceinline__ void st4(float *p, const F4 &a) { *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+// a = hi + lo with hi = bf16(a), lo = bf16(a - hi): the operand pair of a split-bf16 3-pass GEMM (error ~2^-16 relative)
+__device__ __forceinline__ void st4_split(__nv_bfloat16 *hi, __nv_bfloat16 *lo, const F4 &a)
+{
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[k] = __float2bfloat16_rn(a.v[k]);
+        l[k] = __float2bfloat16_rn(a.v[k] - __bfloat162float(h[k]));
+    }
+    *reinterpret_cast<uint2 *>(hi) = *reinterpret_cast<const uint2 *>(h);
+    *reinterpret_cast<uint2 *>(lo) = *reinterpret_cast<const uint2 *>(l);
+}
 
 __global__ void __launch_bounds__(256)
 gru_gates_forward_kernel(const float *__restrict__ gi, const float *__restrict__ gh, const float *__restrict__ hm,
                          const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ m_next,
-                         float *__restrict__ h_out, float *__restrict__ hm_next, float *__restrict__ ws, int R, int hid)
+                         float *__restrict__ h_out, float *__restrict__ hm_next, float *__restrict__ ws,
+                         __nv_bfloat16 *__restrict__ hm_next_hi, __nv_bfloat16 *__restrict__ hm_next_lo, int R, int hid)
 {
     const int q = hid >> 2;                                     // float4 columns per row
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,13 +66,16 @@ gru_gates_forward_kernel(const float *__restrict__ gi, const float *__restrict__
 #pragma unroll
         for (int k = 0; k < 4; ++k) o.v[k] = h.v[k] * m;
         st4(hm_next + (size_t)row * hid + c, o);
+        if (hm_next_hi) st4_split(hm_next_hi + (size_t)row * hid + c, hm_next_lo + (size_t)row * hid + c, o);
     }
 }
 
 __global__ void __launch_bounds__(256)
 gru_gates_backward_kernel(const float *__restrict__ grad_h, const float *__restrict__ d_next, const float *__restrict__ m_next,
                           const float *__restrict__ ws, const float *__restrict__ hm, float *__restrict__ dgi,
-                          float *__restrict__ dgh, float *__restrict__ dhm, int R, int hid)
+                          float *__restrict__ dgh, float *__restrict__ dhm, __nv_bfloat16 *__restrict__ dgi_hi,
+                          __nv_bfloat16 *__restrict__ dgi_lo, __nv_bfloat16 *__restrict__ dgh_hi, __nv_bfloat16 *__restrict__ dgh_lo,
+                          int R, int hid)
 {
     const int q = hid >> 2;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,55 +104,65 @@ gru_gates_backward_kernel(const float *__restrict__ grad_h, const float *__restr
     st4(a + c, pr); st4(a + hid + c, pz); st4(a + 2 * hid + c, pn);
     st4(b + c, pr); st4(b + hid + c, pz); st4(b + 2 * hid + c, pnr);
     st4(dhm + (size_t)row * hid + c, dh);
+    if (dgi_hi) {                                               // the same gradients as bf16 pairs for the 3-pass GEMMs
+        const size_t o = (size_t)row * 3 * hid + c;
+        st4_split(dgi_hi + o, dgi_lo + o, pr); st4_split(dgi_hi + o + hid, dgi_lo + o + hid, pz);
+        st4_split(dgi_hi + o + 2 * hid, dgi_lo + o + 2 * hid, pn);
+        st4_split(dgh_hi + o, dgh_lo + o, pr); st4_split(dgh_hi + o + hid, dgh_lo + o + hid, pz);
+        st4_split(dgh_hi + o + 2 * hid, dgh_lo + o + 2 * hid, pnr);
+    }
 }
 
-// a = hi + lo with hi = bf16(a), lo = bf16(a - hi): the operand pair of a split-bf16 3-pass GEMM (error ~2^-16 relative)
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float *__restrict__ a, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, size_t n4)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    const float4 v = reinterpret_cast<const float4 *>(a)[i];
-    const float x[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        h[k] = __float2bfloat16_rn(x[k]);
-        l[k] = __float2bfloat16_rn(x[k] - __bfloat162float(h[k]));
-    }
-    reinterpret_cast<uint2 *>(hi)[i] = *reinterpret_cast<const uint2 *>(h);
-    reinterpret_cast<uint2 *>(lo)[i] = *reinterpret_cast<const uint2 *>(l);
+    st4_split(hi + 4 * i, lo + 4 * i, ld4(a + 4 * i));
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
 }  // namespace
 
 // host launchers (called from c_abi.cu); return a cudaError_t as int, -1 for bad arguments
 extern "C" int cn_launch_gru_gates_forward(const float *gi, const float *gh, const float *hm, const float *b_ih, const float *b_hh,
-                                           const float *m_next, float *h_out, float *hm_next, float *ws, int R, int hid,
-                                           cudaStream_t stream)
+                                           const float *m_next, float *h_out, float *hm_next, float *ws, void *hm_next_hi,
+                                           void *hm_next_lo, int R, int hid, cudaStream_t stream)
 {
     if (R < 1 || hid < 4 || (hid & 3) || !aligned16(gi) || !aligned16(gh) || !aligned16(hm) || !aligned16(b_ih) || !aligned16(b_hh) ||
-        !aligned16(h_out) || !aligned16(ws) || (hm_next && !aligned16(hm_next)) || (hm_next && !m_next)) return -1;
+        !aligned16(h_out) || !aligned16(ws) || (hm_next && !aligned16(hm_next)) || (hm_next && !m_next) ||
+        ((hm_next_hi != nullptr) != (hm_next_lo != nullptr)) || (hm_next_hi && (!hm_next || !aligned8(hm_next_hi) || !aligned8(hm_next_lo))))
+        return -1;
     const size_t n = (size_t)R * (hid >> 2);
-    gru_gates_forward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gi, gh, hm, b_ih, b_hh, m_next, h_out, hm_next, ws, R, hid);
+    gru_gates_forward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gi, gh, hm, b_ih, b_hh, m_next, h_out, hm_next, ws,
+        static_cast<__nv_bfloat16 *>(hm_next_hi), static_cast<__nv_bfloat16 *>(hm_next_lo), R, hid);
     return (int)cudaGetLastError();
 }
 
 extern "C" int cn_launch_gru_gates_backward(const float *grad_h, const float *d_next, const float *m_next, const float *ws,
-                                            const float *hm, float *dgi, float *dgh, float *dhm, int R, int hid, cudaStream_t stream)
+                                            const float *hm, float *dgi, float *dgh, float *dhm, void *const *pairs, int R, int hid,
+                                            cudaStream_t stream)
 {
     if (R < 1 || hid < 4 || (hid & 3) || !aligned16(grad_h) || (d_next && (!aligned16(d_next) || !m_next)) || !aligned16(ws) ||
         !aligned16(hm) || !aligned16(dgi) || !aligned16(dgh) || !aligned16(dhm)) return -1;
+    __nv_bfloat16 *p[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (pairs) {
+        for (int k = 0; k < 4; ++k) {
+            if (!pairs[k] || !aligned8(pairs[k])) return -1;
+            p[k] = static_cast<__nv_bfloat16 *>(pairs[k]);
+        }
+    }
     const size_t n = (size_t)R * (hid >> 2);
-    gru_gates_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_h, d_next, m_next, ws, hm, dgi, dgh, dhm, R, hid);
+    gru_gates_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_h, d_next, m_next, ws, hm, dgi, dgh, dhm,
+                                                                               p[0], p[1], p[2], p[3], R, hid);
     return (int)cudaGetLastError();
 }
 
 extern "C" int cn_launch_split_bf16(const float *a, void *hi, void *lo, size_t n, cudaStream_t stream)
 {
-    if (n == 0 || (n & 3) || !aligned16(a) || (reinterpret_cast<uintptr_t>(hi) & 7u) || (reinterpret_cast<uintptr_t>(lo) & 7u)) return -1;
+    if (n == 0 || (n & 3) || !aligned16(a) || !aligned8(hi) || !aligned8(lo)) return -1;
     const size_t n4 = n >> 2;
     split_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(a, static_cast<__nv_bfloat16 *>(hi), static_cast<__nv_bfloat16 *>(lo), n4);
     return (int)cudaGetLastError();

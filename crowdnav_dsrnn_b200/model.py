@@ -85,7 +85,7 @@ class _MaskedGruSequence(torch.autograd.Function):
     def forward(ctx, x, h0, m, w_ih, w_hh, b_ih, b_hh):
         T, R, hid = x.shape[0], x.shape[1], h0.shape[1]
         cuda = x.is_cuda and x.dtype is torch.float32
-        x3 = cuda and SEQUENCE_GEMM == "bf16x3"
+        x3 = cuda and SEQUENCE_GEMM == "bf16x3" and (R * hid) % 4 == 0
         if x3:
             gi = _mm_bf16x3(x.reshape(T * R, -1), *_split_bf16(w_ih.t())).view(T, R, 3 * hid)
         else:
@@ -96,18 +96,25 @@ class _MaskedGruSequence(torch.autograd.Function):
         m = m.contiguous()
         w_hh_t = w_hh.t()
         torch.mul(h0, m[0], out=hm[0])
+        pairs = ()
         if cuda:
             lib = _lib.load()
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
             b_ih, b_hh = b_ih.contiguous(), b_hh.contiguous()
-            if x3:
+            if x3:                                           # bf16 hi/lo pair of every step's masked state, written by the gate kernel
                 wt_hi, wt_lo = _split_bf16(w_hh_t)
+                hm_hi = torch.empty(T, R, hid, dtype=torch.bfloat16, device=x.device)
+                hm_lo = torch.empty_like(hm_hi)
+                _lib.check(lib.cn_split_bf16(_ptr(hm[0]), _ptr(hm_hi[0]), _ptr(hm_lo[0]), R * hid, stream), "cn_split_bf16")
+                pairs = (hm_hi, hm_lo)
             for t in range(T):
-                gh = _mm_bf16x3(hm[t], wt_hi, wt_lo) if x3 else torch.mm(hm[t], w_hh_t)
+                gh = _mm3(hm_hi[t], hm_lo[t], wt_hi, wt_lo) if x3 else torch.mm(hm[t], w_hh_t)
                 last = t == T - 1
                 _lib.check(lib.cn_gru_gates_forward(_ptr(gi[t]), _ptr(gh), _ptr(hm[t]), _ptr(b_ih), _ptr(b_hh),
                                                     None if last else _ptr(m[t + 1]), _ptr(hs[t]),
-                                                    None if last else _ptr(hm[t + 1]), _ptr(ws[t]), R, hid, stream),
+                                                    None if last else _ptr(hm[t + 1]), _ptr(ws[t]),
+                                                    _ptr(hm_hi[t + 1]) if x3 and not last else None,
+                                                    _ptr(hm_lo[t + 1]) if x3 and not last else None, R, hid, stream),
                            "cn_gru_gates_forward")
         else:                                                # CPU tests / float64 checks: the same formulas in torch
             for t in range(T):
@@ -120,14 +127,14 @@ class _MaskedGruSequence(torch.autograd.Function):
                 ws[t] = torch.cat([r, z, n, hn], 1)
                 if t + 1 < T:
                     torch.mul(hs[t], m[t + 1], out=hm[t + 1])
-        ctx.save_for_backward(x, m, w_ih, w_hh, hm, ws)
+        ctx.save_for_backward(x, m, w_ih, w_hh, hm, ws, *pairs)
         ctx.cuda = cuda
         ctx.x3 = x3
         return hs
 
     @staticmethod
     def backward(ctx, grad_hs):
-        x, m, w_ih, w_hh, hm, ws = ctx.saved_tensors
+        x, m, w_ih, w_hh, hm, ws, *pairs = ctx.saved_tensors
         T, R, hid = hm.shape
         dgi = x.new_empty(T, R, 3 * hid)
         dgh = x.new_empty(T, R, 3 * hid)
@@ -139,11 +146,14 @@ class _MaskedGruSequence(torch.autograd.Function):
             dhm = x.new_empty(R, hid)
             if ctx.x3:
                 w_hi, w_lo = _split_bf16(w_hh)
+                bf = lambda: torch.empty(T, R, 3 * hid, dtype=torch.bfloat16, device=x.device)
+                dgi_hi, dgi_lo, dgh_hi, dgh_lo = bf(), bf(), bf(), bf()
             for t in range(T - 1, -1, -1):
+                extra = [_ptr(b[t]) for b in (dgi_hi, dgi_lo, dgh_hi, dgh_lo)] if ctx.x3 else [None] * 4
                 _lib.check(lib.cn_gru_gates_backward(_ptr(grad_hs[t]), _ptr(d_next), None if d_next is None else _ptr(m[t + 1]),
-                                                     _ptr(ws[t]), _ptr(hm[t]), _ptr(dgi[t]), _ptr(dgh[t]), _ptr(dhm), R, hid, stream),
-                           "cn_gru_gates_backward")
-                d_next = _mm_bf16x3(dgh[t], w_hi, w_lo, add=dhm) if ctx.x3 else torch.addmm(dhm, dgh[t], w_hh)
+                                                     _ptr(ws[t]), _ptr(hm[t]), _ptr(dgi[t]), _ptr(dgh[t]), _ptr(dhm), *extra,
+                                                     R, hid, stream), "cn_gru_gates_backward")
+                d_next = _mm3(dgh_hi[t], dgh_lo[t], w_hi, w_lo, add=dhm) if ctx.x3 else torch.addmm(dhm, dgh[t], w_hh)
         else:
             for t in range(T - 1, -1, -1):
                 g = grad_hs[t] if d_next is None else grad_hs[t] + d_next * m[t + 1]
@@ -156,12 +166,11 @@ class _MaskedGruSequence(torch.autograd.Function):
                 d_next = torch.addmm(g * z, dgh[t], w_hh)
         dgi2, dgh2 = dgi.view(T * R, 3 * hid), dgh.view(T * R, 3 * hid)
         if ctx.x3:
-            a_hi, a_lo = _split_bf16(dgi2)
+            a_hi, a_lo = dgi_hi.view(T * R, 3 * hid), dgi_lo.view(T * R, 3 * hid)
             dx = _mm3(a_hi, a_lo, *_split_bf16(w_ih)).view(T, R, -1) if ctx.needs_input_grad[0] else None
             dw_ih = _mm3(a_hi.t(), a_lo.t(), *_split_bf16(x.reshape(T * R, -1)))
-            a_hi, a_lo = _split_bf16(dgh2)
-            dw_hh = _mm3(a_hi.t(), a_lo.t(), *_split_bf16(hm.view(T * R, hid)))
-            del a_hi, a_lo
+            dw_hh = _mm3(dgh_hi.view(T * R, 3 * hid).t(), dgh_lo.view(T * R, 3 * hid).t(),
+                         pairs[0].view(T * R, hid), pairs[1].view(T * R, hid))
         else:
             dx = torch.matmul(dgi, w_ih) if ctx.needs_input_grad[0] else None
             dw_ih = torch.mm(dgi2.t(), x.reshape(T * R, -1))

@@ -259,11 +259,16 @@ int cn_env_time_ms(CnEnv *env, float *step_kernel_ms, int *n_steps);
  * backward: g = grad_h + (d_next ? m_next[row] * d_next : 0), where d_next = dL/d(hm of step t+1)
  *           -> dgi, dgh [R,3 hid] (gradients of gi and gh; bias gradients are their column sums), dhm = g * z
  *              (the direct part of dL/d(hm); the caller adds dgh W_hh).
+ * Optional bfloat16 hi/lo copies (NULL = off; cn_split_bf16 below describes the pair) of what the NEXT GEMMs read, so that
+ * the split-bf16 3-pass products need no separate pass over their operands: hm_next_hi/lo [R,hid] of hm_next;
+ * dgi_hi/lo, dgh_hi/lo [R,3 hid] of dgi and dgh (all four or none).
  */
 int cn_gru_gates_forward(const float *gi, const float *gh, const float *hm, const float *b_ih, const float *b_hh,
-                         const float *m_next, float *h_out, float *hm_next, float *ws, int rows, int hid, void *stream);
+                         const float *m_next, float *h_out, float *hm_next, float *ws, void *hm_next_hi, void *hm_next_lo,
+                         int rows, int hid, void *stream);
 int cn_gru_gates_backward(const float *grad_h, const float *d_next, const float *m_next, const float *ws, const float *hm,
-                          float *dgi, float *dgh, float *dhm, int rows, int hid, void *stream);
+                          float *dgi, float *dgh, float *dhm, void *dgi_hi, void *dgi_lo, void *dgh_hi, void *dgh_lo,
+                          int rows, int hid, void *stream);
 /* a[n] float32 -> hi[n], lo[n] bfloat16 with hi = bf16(a), lo = bf16(a - hi): the operand pair of the split-bf16 3-pass
  * tensor-core products (A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulation) the update can use for its recurrent GEMMs
  * (same arithmetic as the rollout's CN_PREC_BF16X3).  n % 4 == 0. */

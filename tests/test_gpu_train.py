@@ -110,10 +110,10 @@ def test_gru_gate_kernels_match_torch_reference(rows, hid):
     stream = C.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
     h_out, hm_next, ws = torch.empty(rows, hid, device=DEV), torch.empty(rows, hid, device=DEV), torch.empty(rows, 4 * hid, device=DEV)
     _lib.check(lib.cn_gru_gates_forward(ptr(gi.detach()), ptr(gh.detach()), ptr(hm.detach()), ptr(b_ih), ptr(b_hh), ptr(m_next),
-                                        ptr(h_out), ptr(hm_next), ptr(ws), rows, hid, stream), "cn_gru_gates_forward")
+                                        ptr(h_out), ptr(hm_next), ptr(ws), None, None, rows, hid, stream), "cn_gru_gates_forward")
     dgi, dgh, dhm = torch.empty(rows, 3 * hid, device=DEV), torch.empty(rows, 3 * hid, device=DEV), torch.empty(rows, hid, device=DEV)
     _lib.check(lib.cn_gru_gates_backward(ptr(grad_h), ptr(d_next), ptr(m_next), ptr(ws), ptr(hm.detach()), ptr(dgi), ptr(dgh),
-                                         ptr(dhm), rows, hid, stream), "cn_gru_gates_backward")
+                                         ptr(dhm), None, None, None, None, rows, hid, stream), "cn_gru_gates_backward")
     torch.cuda.synchronize()
     tol = 2e-5      # fp32 with fused multiply-adds and libdevice expf / tanhf vs ATen's
     for got, want in ((h_out, h_ref.detach()), (hm_next, h_ref.detach() * m_next), (ws[:, :hid], r.detach()),
@@ -122,9 +122,21 @@ def test_gru_gate_kernels_match_torch_reference(rows, hid):
         assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
     # bad arguments are refused, not launched
     assert lib.cn_gru_gates_forward(ptr(gi.detach()), ptr(gh.detach()), ptr(hm.detach()), ptr(b_ih), ptr(b_hh), None, ptr(h_out),
-                                    ptr(hm_next), ptr(ws), rows, hid, stream) == -1
+                                    ptr(hm_next), ptr(ws), None, None, rows, hid, stream) == -1
     assert lib.cn_gru_gates_backward(ptr(grad_h), ptr(d_next), ptr(m_next), ptr(ws), ptr(hm.detach()), ptr(dgi), ptr(dgh), ptr(dhm),
-                                     rows, 6, stream) == -1
+                                     None, None, None, None, rows, 6, stream) == -1
+    # the optional bf16 pairs are the split of the fp32 outputs
+    bf = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=DEV)
+    nh, nl = bf(rows, hid), bf(rows, hid)
+    _lib.check(lib.cn_gru_gates_forward(ptr(gi.detach()), ptr(gh.detach()), ptr(hm.detach()), ptr(b_ih), ptr(b_hh), ptr(m_next),
+                                        ptr(h_out), ptr(hm_next), ptr(ws), ptr(nh), ptr(nl), rows, hid, stream), "cn_gru_gates_forward")
+    pairs = [bf(rows, 3 * hid) for _ in range(4)]
+    _lib.check(lib.cn_gru_gates_backward(ptr(grad_h), ptr(d_next), ptr(m_next), ptr(ws), ptr(hm.detach()), ptr(dgi), ptr(dgh),
+                                         ptr(dhm), *[ptr(t) for t in pairs], rows, hid, stream), "cn_gru_gates_backward")
+    torch.cuda.synchronize()
+    for full, hi, lo in ((hm_next, nh, nl), (dgi, pairs[0], pairs[1]), (dgh, pairs[2], pairs[3])):
+        assert torch.equal(hi, full.to(torch.bfloat16))
+        assert ((hi.float() + lo.float() - full).abs() <= full.abs() * 2.0 ** -16 + 1e-38).all()
 
 
 def test_bf16x3_recurrent_gemms_keep_fp32_level_accuracy(monkeypatch):
