@@ -103,9 +103,10 @@ def test_advantages_and_generator_layout():
         list(st.recurrent_generator(adv, 7))
 
 
-@pytest.mark.parametrize("per_pass,keep", [(None, True), (2, False)])
-def test_update_matches_reference(per_pass, keep):
-    """Losses and every parameter's change after 5 epochs x 2 minibatches equal the reference's PPO.update."""
+@pytest.mark.parametrize("per_pass,keep,flags", [(None, True, {}), (2, False, {}), (2, False, {"tf32": True, "bf16x3": True})])
+def test_update_matches_reference(per_pass, keep, flags):
+    """Losses and every parameter's change after 5 epochs x 2 minibatches equal the reference's PPO.update.  (The GEMM
+    arithmetic switches only act on CUDA tensors; here they must be inert and restored after the update.)"""
     g = _golden()
     hyper = g["hyper"]
     torch.set_num_threads(4)
@@ -114,10 +115,13 @@ def test_update_matches_reference(per_pass, keep):
     st = _storage(g, keep_hidden_history=keep)
     st.compute_returns(torch.from_numpy(g["next_value"]), True, float(hyper[8]), float(hyper[9]), False)
     agent = PPO(policy, float(hyper[0]), int(hyper[1]), int(hyper[2]), float(hyper[3]), float(hyper[4]), lr=float(hyper[5]),
-                eps=float(hyper[6]), max_grad_norm=float(hyper[7]), max_envs_per_pass=per_pass)
+                eps=float(hyper[6]), max_grad_norm=float(hyper[7]), max_envs_per_pass=per_pass, **flags)
     torch.manual_seed(int(hyper[10]))          # the reference draws torch.randperm(N) per epoch from the CPU generator
+    tf32_before = torch.backends.cuda.matmul.allow_tf32
     losses = agent.update(st)
     _check_update(g, policy, before, losses)
+    from crowdnav_dsrnn_b200 import model as model_mod
+    assert model_mod.SEQUENCE_GEMM == "fp32" and torch.backends.cuda.matmul.allow_tf32 == tf32_before
     st.after_update()
     np.testing.assert_array_equal(st.obs["robot_node"][0].numpy(), g["obs_robot_node"][-1])
     np.testing.assert_array_equal(st.masks[0].numpy(), g["masks"][-1])
