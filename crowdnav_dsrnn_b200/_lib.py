@@ -44,6 +44,9 @@ SYMBOLS = {
     "cn_gru_gates_forward": (C.c_int, [_P] * 11 + [C.c_int, C.c_int, _P]),
     "cn_gru_gates_backward": (C.c_int, [_P] * 12 + [C.c_int, C.c_int, _P]),
     "cn_split_bf16": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
+    "cn_dsrnn_edge_sequence_step": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(abi.CnEdgeSeqStep), _P]),
+    "cn_gru_gates_backward_pairs": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "cn_gemm_bf16x3": (C.c_int, [C.POINTER(abi.CnGemm), C.c_int, _P]),
 }
 
 _LIB = None

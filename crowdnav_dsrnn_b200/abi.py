@@ -134,6 +134,25 @@ class CnDsrnnIO(C.Structure):
         "h_node_out", "h_edge_out", "value", "action_mean", "actor_features")]
 
 
+class CnEdgeSeqStep(C.Structure):
+    _fields_ = [("temporal_edges", _fp), ("spatial_edges", _fp), ("masks", _fp), ("h_in", _fp),
+                ("in_row_spatial", C.c_longlong), ("in_row_temporal", C.c_longlong),
+                ("out_row_spatial", C.c_longlong), ("out_row_temporal", C.c_longlong),
+                ("h_out", _fp), ("ws", _fp), ("hm_hi", _fp), ("hm_lo", _fp), ("e_hi", _fp), ("e_lo", _fp)]
+
+
+GEMM_MAX_PROBLEMS = 4
+
+
+class CnGemmOperand(C.Structure):
+    _fields_ = [("hi", _fp), ("lo", _fp), ("ld", C.c_longlong), ("mn_major", C.c_int), ("reserved", C.c_int)]
+
+
+class CnGemm(C.Structure):
+    _fields_ = [("a", CnGemmOperand), ("b", CnGemmOperand), ("c", _fp), ("ldc", C.c_longlong), ("bias", _fp),
+                ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("act", C.c_int), ("accumulate", C.c_int), ("split_k", C.c_int)]
+
+
 def step_tables(time_step, time_limit):
     """Replay the reference's float64 `global_time += time_step` accumulation
     (crowd_sim_dict.py:253) and return (timeout_step, goal_change_bits):

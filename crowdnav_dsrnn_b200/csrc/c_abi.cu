@@ -25,6 +25,22 @@ static int fail(int code, const char *fmt, ...)
         if (err__ != cudaSuccess) return fail(CN_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(err__)); \
     } while (0)
 
+// every entry point that owns a handle runs on the handle's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else prev = -1;                                  // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define CN_ON_DEVICE(dev)                                                               \
+    DeviceGuard guard__(dev);                                                           \
+    if (guard__.err != cudaSuccess) return fail(CN_ERR_CUDA, "cudaSetDevice(%d): %s", (int)(dev), cudaGetErrorString(guard__.err))
+
 extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, int auto_reset, cudaStream_t stream);
 extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, int mode, cudaStream_t stream);
 enum { CN_RESET_LIVE = 0, CN_RESET_SPARE = 1, CN_RESET_SYNC = 2, CN_RESET_SPARE_LIST = 3 };   // crowd_reset.cu
@@ -145,7 +161,11 @@ extern "C" int cn_env_create(const CnConfig *cfg, int n_envs, int device, void *
     env->device = device;
     env->last_launches = 0;
     cn_carve(&env->p.a, state_dev, n_envs, cfg->human_num);
-    CN_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) {
+        delete env;
+        return fail(CN_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.err));
+    }
     if (cudaStreamCreateWithFlags(&env->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&env->ev_spare, cudaEventDisableTiming) != cudaSuccess) {
@@ -176,7 +196,7 @@ extern "C" int cn_env_destroy(CnEnv *env)
 extern "C" int cn_env_refill(CnEnv *env, void *stream)
 {
     if (!env) return fail(CN_ERR_ARG, "env is NULL");
-    CN_CUDA(cudaSetDevice(env->device));
+    CN_ON_DEVICE(env->device);
     int rc = join_refill(env, (cudaStream_t)stream);      // never two refills in flight
     if (rc != CN_OK) return rc;
     return fork_refill(env, (cudaStream_t)stream);
@@ -185,7 +205,7 @@ extern "C" int cn_env_refill(CnEnv *env, void *stream)
 extern "C" int cn_env_join(CnEnv *env, void *stream)
 {
     if (!env) return fail(CN_ERR_ARG, "env is NULL");
-    CN_CUDA(cudaSetDevice(env->device));
+    CN_ON_DEVICE(env->device);
     return join_refill(env, (cudaStream_t)stream);
 }
 
@@ -202,7 +222,7 @@ extern "C" int cn_env_reset(CnEnv *env, const uint8_t *mask_dev, const CnObsOut 
     if (!env) return fail(CN_ERR_ARG, "env is NULL");
     int rc = check_obs(obs);
     if (rc != CN_OK) return rc;
-    CN_CUDA(cudaSetDevice(env->device));
+    CN_ON_DEVICE(env->device);
     rc = join_refill(env, (cudaStream_t)stream);
     if (rc != CN_OK) return rc;
     CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, obs, mask_dev, CN_RESET_LIVE, (cudaStream_t)stream));
@@ -219,12 +239,14 @@ extern "C" int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut 
     int rc = check_obs(&out->obs);
     if (rc != CN_OK) return rc;
     if (!out->reward || !out->done || !out->event) return fail(CN_ERR_ARG, "CnStepOut needs reward, done and event");
-    CN_CUDA(cudaSetDevice(env->device));
-    {   // development switches for timing experiments (never set in tests / bench): 1 = no auto-reset at all, 2 = no spare refill
+    CN_ON_DEVICE(env->device);
+#ifdef CN_DEBUG_SWITCHES
+    {   // development builds only (make NET_FLAGS=-DCN_DEBUG_SWITCHES): 1 = no auto-reset at all, 2 = no spare refill
         static const int dbg = getenv("CN_DEBUG_RESET") ? atoi(getenv("CN_DEBUG_RESET")) : 0;
         if (dbg == 1) auto_reset = 0;
         if (dbg == 2 && auto_reset) auto_reset = 3;
     }
+#endif
     rc = join_refill(env, (cudaStream_t)stream);        // the step kernel reads (and consumes) the spares
     if (rc != CN_OK) return rc;
     env->timer.begin((cudaStream_t)stream);
@@ -250,7 +272,7 @@ extern "C" int cn_env_observe(CnEnv *env, const CnObsOut *obs, void *stream)
     if (!env) return fail(CN_ERR_ARG, "env is NULL");
     int rc = check_obs(obs);
     if (rc != CN_OK) return rc;
-    CN_CUDA(cudaSetDevice(env->device));
+    CN_ON_DEVICE(env->device);
     CN_CUDA((cudaError_t)cn_launch_crowd_observe(&env->p, obs, (cudaStream_t)stream));
     env->last_launches = 1;
     return CN_OK;
@@ -259,7 +281,7 @@ extern "C" int cn_env_observe(CnEnv *env, const CnObsOut *obs, void *stream)
 static int convert(CnEnv *env, const CnStateView *view, int dir, void *stream)
 {
     if (!env || !view) return fail(CN_ERR_ARG, "env/view is NULL");
-    CN_CUDA(cudaSetDevice(env->device));
+    CN_ON_DEVICE(env->device);
     if (join_refill(env, (cudaStream_t)stream) != CN_OK) return CN_ERR_CUDA;      // the refill reads the counters
     CN_CUDA((cudaError_t)cn_launch_state_convert(&env->p, view, dir, (cudaStream_t)stream));
     env->last_launches = 1;
@@ -298,7 +320,7 @@ extern "C" int cn_dsrnn_create(const CnDsrnnWeights *w, int device, void *stream
     cudaDeviceProp prop;
     CN_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(CN_ERR_UNSUPPORTED, "libcrowdnav_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
-    CN_CUDA(cudaSetDevice(device));
+    CN_ON_DEVICE(device);
     CnDsrnn *m = nullptr;
     const char *msg = dsrnn_create(w, device, (cudaStream_t)stream, &m);
     if (msg) return fail(CN_ERR_CUDA, "dsrnn_create: %s", msg);
@@ -315,6 +337,7 @@ extern "C" int cn_dsrnn_destroy(CnDsrnn *m)
 extern "C" int cn_dsrnn_update_weights(CnDsrnn *m, const CnDsrnnWeights *w, void *stream)
 {
     if (!m || !w) return fail(CN_ERR_ARG, "model/weights is NULL");
+    CN_ON_DEVICE(dsrnn_device(m));
     const char *msg = dsrnn_update_weights(m, w, (cudaStream_t)stream);
     if (msg) return fail(CN_ERR_CUDA, "dsrnn_update_weights: %s", msg);
     return CN_OK;
@@ -338,6 +361,7 @@ extern "C" int cn_dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnD
         return fail(CN_ERR_ARG, "unknown precision %d", precision);
     const size_t need = dsrnn_workspace_bytes(n_envs, human_num);
     if (!workspace_dev || workspace_bytes < need) return fail(CN_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, need);
+    CN_ON_DEVICE(dsrnn_device(m));
     const char *msg = dsrnn_forward(m, n_envs, human_num, io, precision, workspace_dev, (cudaStream_t)stream);
     if (msg) return fail(CN_ERR_CUDA, "dsrnn_forward: %s", msg);
     return CN_OK;
@@ -405,5 +429,41 @@ extern "C" int cn_split_bf16(const float *a, void *hi, void *lo, size_t n, void 
     const int rc = cn_launch_split_bf16(a, hi, lo, n, (cudaStream_t)stream);
     if (rc == -1) return fail(CN_ERR_ARG, "cn_split_bf16: n %zu must be a positive multiple of 4, a 16-byte and hi / lo 8-byte aligned", n);
     if (rc != 0) return fail(CN_ERR_CUDA, "split_bf16_kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    return CN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- native PPO-update path
+extern "C" int cn_launch_gru_gates_backward_pairs(const float *grad_h, float *d, int d_live, const float *m_next, const float *ws,
+                                                  const float *h_prev, const float *m_cur, void *g_hi, void *g_lo, int R, int hid,
+                                                  cudaStream_t stream);
+const char *gemm_bf16x3_launch(const CnGemm *problems, int n_problems, cudaStream_t stream, int *items_out);
+
+extern "C" int cn_gru_gates_backward_pairs(const float *grad_h, float *d, int d_live, const float *m_next, const float *ws,
+                                           const float *h_prev, const float *m_cur, void *g_hi, void *g_lo, int rows, int hid, void *stream)
+{
+    if (!grad_h || !d || !ws || !g_hi || !g_lo) return fail(CN_ERR_ARG, "cn_gru_gates_backward_pairs: NULL pointer");
+    const int rc = cn_launch_gru_gates_backward_pairs(grad_h, d, d_live, m_next, ws, h_prev, m_cur, g_hi, g_lo, rows, hid, (cudaStream_t)stream);
+    if (rc == -1) return fail(CN_ERR_ARG, "cn_gru_gates_backward_pairs: rows %d / hid %d / alignment / live d without m_next / h_prev without m_cur", rows, hid);
+    if (rc != 0) return fail(CN_ERR_CUDA, "gru_gates_backward_pairs_kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    return CN_OK;
+}
+
+extern "C" int cn_gemm_bf16x3(const CnGemm *problems, int n_problems, void *stream)
+{
+    if (!problems) return fail(CN_ERR_ARG, "cn_gemm_bf16x3: problems is NULL");
+    const char *msg = gemm_bf16x3_launch(problems, n_problems, (cudaStream_t)stream, nullptr);
+    if (msg) return fail(CN_ERR_ARG, "cn_gemm_bf16x3: %s", msg);
+    return CN_OK;
+}
+
+extern "C" int cn_dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, const CnEdgeSeqStep *io, void *stream)
+{
+    if (!m || !io) return fail(CN_ERR_ARG, "model/io is NULL");
+    if (n_envs < 1 || human_num < 1 || human_num > CN_MAX_HUMANS) return fail(CN_ERR_ARG, "bad n_envs/human_num");
+    if (!io->temporal_edges || !io->spatial_edges || !io->masks || !io->h_in || !io->h_out || !io->ws || !io->hm_hi || !io->hm_lo ||
+        !io->e_hi || !io->e_lo) return fail(CN_ERR_ARG, "CnEdgeSeqStep has a NULL member");
+    CN_ON_DEVICE(dsrnn_device(m));
+    const char *msg = dsrnn_edge_sequence_step(m, n_envs, human_num, io, (cudaStream_t)stream);
+    if (msg) return fail(CN_ERR_CUDA, "dsrnn_edge_sequence_step: %s", msg);
     return CN_OK;
 }

@@ -12,6 +12,8 @@ size_t dsrnn_workspace_bytes(int n_envs, int human_num);
 const char *dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnDsrnnIO *io, int precision,
                           void *workspace, cudaStream_t stream);
 int dsrnn_last_launches(const CnDsrnn *m);
+int dsrnn_device(const CnDsrnn *m);
+const char *dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, const CnEdgeSeqStep *io, cudaStream_t stream);
 void dsrnn_enable_timing(CnDsrnn *m, int enable);
 void dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env);
 float dsrnn_time_ms(CnDsrnn *m, int *count);

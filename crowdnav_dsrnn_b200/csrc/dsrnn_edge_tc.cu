@@ -140,10 +140,19 @@ struct EdgeTcArgs {
     int three_pass;
     int fp16;          // single pass with FP16 operands (images part 2) instead of BF16
     int debug;         // EDGE_PROFILE builds: what-if switches (timing only, results are wrong), 0 otherwise
+    // training (one step of the masked GRU sequences of the PPO update, cn_dsrnn_edge_sequence_step): rows are addressed as
+    // spatial row m -> in/out_off_s + m, temporal row m -> in/out_off_t + m (the [T*S | T*N] sequence layout) and the kernel
+    // also writes what the backward needs: the gate values and the split-bf16 operands of the weight-gradient products
+    int train;
+    long long in_off_s, in_off_t, out_off_s, out_off_t;
+    float *ws;                         // [rows, 4, 256] r | z | n | W_hn hm + b_hn
+    __nv_bfloat16 *hm_hi, *hm_lo;      // [rows, 256] masked previous state
+    __nv_bfloat16 *e_hi, *e_lo;        // [rows, 64] encoded input
 };
 
 struct TileInfo { bool spatial; int p, row0, M; };
 
+template <bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__ CUtensorMap wmap)
 {
@@ -211,6 +220,9 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
         env = t.spatial ? m / H : m;
         return t.spatial ? env * stride + 1 + (m - env * H) : env * stride;
     };
+    // sequence layout (training): input row (previous step / initial state) and output row (this step) of logical row m
+    auto seq_in_row = [&](const TileInfo &t, int m) { return (size_t)((t.spatial ? a.in_off_s : a.in_off_t) + m); };
+    auto seq_out_row = [&](const TileInfo &t, int m) { return (size_t)((t.spatial ? a.out_off_s : a.out_off_t) + m); };
 
     if (warp < kEpiWarps) {
         // =============================================================== epilogue warps
@@ -227,7 +239,8 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
             const int m = t.row0 + tid;
             const bool ok = m < t.M;
             size_t mem_row = 0;
-            if (ok) { int env; mem_row = (size_t)mem_row_of(t, m, env); }
+            if (ok) { int env; mem_row = kTrain ? seq_out_row(t, m) : (size_t)mem_row_of(t, m, env); }
+            float *wsrow = kTrain ? a.ws + mem_row * 1024 : nullptr;
             if (t.p != bias_p) {                  // at most twice per CTA: spatial pairs come first, then temporal ones
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 reinterpret_cast<float4 *>(s_bias)[threadIdx.x] = __ldg(reinterpret_cast<const float4 *>(a.bias4 + t.p * 4 * 256) + threadIdx.x);
@@ -285,7 +298,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     tmem_ld_wait();
                     const int c0 = ct * 64 + c16 * 16;
                     if (ok && !DBG(4)) {
-                        float o8[8];
+                        float o8[8], r8[8], z8[8], n8[8], h8[8];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int c = c0 + q * 4;
@@ -296,11 +309,23 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int j = q * 4 + i;
-                                o8[(q & 1) * 4 + i] = gru_blend(rg[j] + br[i], zg[j] + bz[i], ni[j] + bn[i], nh[j] + bh[i], hprev[cc * 16 + j]);
+                                const int o = (q & 1) * 4 + i;
+                                if (kTrain) {
+                                    h8[o] = nh[j] + bh[i];
+                                    o8[o] = gru_blend_ws(rg[j] + br[i], zg[j] + bz[i], ni[j] + bn[i], h8[o], hprev[cc * 16 + j], r8[o], z8[o], n8[o]);
+                                } else {
+                                    o8[o] = gru_blend(rg[j] + br[i], zg[j] + bz[i], ni[j] + bn[i], nh[j] + bh[i], hprev[cc * 16 + j]);
+                                }
                             }
                             // a row is 1 KB away from the next lane's row: every store instruction touches 32 lines, so the
                             // 32-byte form halves the LSU work of the epilogue
-                            if (q & 1) st_global_v8(orow + c0 + (q - 1) * 4, o8);
+                            if (q & 1) {
+                                st_global_v8(orow + c0 + (q - 1) * 4, o8);
+                                if (kTrain) {
+                                    float *w8 = wsrow + c0 + (q - 1) * 4;
+                                    st_global_v8(w8, r8); st_global_v8(w8 + 256, z8); st_global_v8(w8 + 512, n8); st_global_v8(w8 + 768, h8);
+                                }
+                            }
                         }
                     }
                 }
@@ -330,9 +355,11 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
             const bool ok_l = m_l < t.M;
             int ridx_l = 0;
             float mk_l = 0.f, x0_l = 0.f, x1_l = 0.f;
+            long long orow_l = 0;                 // training: this row's index in the step's output arrays
             if (ok_l) {
                 int env;
                 ridx_l = mem_row_of(t, m_l, env);
+                if (kTrain) { ridx_l = (int)seq_in_row(t, m_l); orow_l = (long long)seq_out_row(t, m_l); }
                 mk_l = a.masks[env];
                 const float *x = t.spatial ? a.spatial_edges + 2 * (size_t)m_l : a.temporal_edges + 2 * (size_t)m_l;
                 x0_l = x[0]; x1_l = x[1];
@@ -369,6 +396,11 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                         const int off = sw128_offset(r, 2 * lane);
                         *reinterpret_cast<uint32_t *>(smem + kOffAHi + off) = hi;
                         if (a.three_pass) *reinterpret_cast<uint32_t *>(smem + kOffALo + off) = lo;
+                        if (kTrain && okb) {      // operand of dW_ih = dgi^T e (128 contiguous bytes per row and warp)
+                            const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
+                            reinterpret_cast<uint32_t *>(a.e_hi + orow * 64)[lane] = hi;
+                            reinterpret_cast<uint32_t *>(a.e_lo + orow * 64)[lane] = lo;
+                        }
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -394,6 +426,13 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     else { split_bf16x2(h4.x, h4.y, hi.x, lo.x); split_bf16x2(h4.z, h4.w, hi.y, lo.y); }
                     *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = hi;
                     if (a.three_pass) *reinterpret_cast<uint2 *>(smem + kOffALo + off) = lo;
+                    if (kTrain) {                 // operand of dW_hh = dgh^T hm
+                        const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
+                        if (__shfl_sync(0xffffffffu, (int)ok_l, b)) {
+                            *reinterpret_cast<uint2 *>(a.hm_hi + orow * 256 + e0) = hi;
+                            *reinterpret_cast<uint2 *>(a.hm_lo + orow * 256 + e0) = lo;
+                        }
+                    }
                 }
                 fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
                 __syncwarp();
@@ -407,7 +446,8 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                 const int mn = tn.row0 + sw * 16 + (lane & 15);
                 if (mn < tn.M) {
                     int env;
-                    const float *row = a.h_in + (size_t)mem_row_of(tn, mn, env) * 256 + (lane >> 4) * 128;
+                    const size_t nrow = kTrain ? seq_in_row(tn, mn) : (size_t)mem_row_of(tn, mn, env);
+                    const float *row = a.h_in + nrow * 256 + (lane >> 4) * 128;
 #pragma unroll
                     for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + l * 32));
                 }
@@ -547,6 +587,7 @@ extern "C" int cn_debug_edge_profile(unsigned long long *out32, int reset)
 }
 #endif
 void dsrnn_tc_destroy(void *state);
+const char *dsrnn_tc_repack(void *state, const CnDsrnnWeights *w, cudaStream_t stream);
 
 const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void **state)
 {
@@ -582,18 +623,28 @@ const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void *
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaFuncSetAttribute(edge_gru_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(edge_gru_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess) {
+        dsrnn_tc_destroy(st);
+        return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+    }
+    if (const char *msg = dsrnn_tc_repack(st, w, stream)) { dsrnn_tc_destroy(st); return msg; }
+    *state = st;
+    return nullptr;
+}
+
+// re-runs the pack kernel into the EXISTING images (same addresses: CUDA graphs that captured the forward stay valid,
+// no allocation, no synchronisation); called after every optimiser step
+const char *dsrnn_tc_repack(void *state, const CnDsrnnWeights *w, cudaStream_t stream)
+{
+    TcState *st = static_cast<TcState *>(state);
+    if (!st) return "tensor-core edge stage was not initialised";
     PackArgs pa;
     pa.w_ih[0] = w->s_w_ih; pa.w_hh[0] = w->s_w_hh; pa.b_ih[0] = w->s_b_ih; pa.b_hh[0] = w->s_b_hh; pa.enc_w[0] = w->s_enc_w; pa.enc_b[0] = w->s_enc_b;
     pa.w_ih[1] = w->t_w_ih; pa.w_hh[1] = w->t_w_hh; pa.b_ih[1] = w->t_b_ih; pa.b_hh[1] = w->t_b_hh; pa.enc_w[1] = w->t_enc_w; pa.enc_b[1] = w->t_enc_b;
     pa.wimg = st->wimg; pa.bias4 = st->bias4; pa.enc = st->enc;
     pack_edge_weights_kernel<<<256, 256, 0, stream>>>(pa);
-    if (cudaGetLastError() != cudaSuccess) { dsrnn_tc_destroy(st); return "pack_edge_weights_kernel launch failed"; }
-    if (cudaFuncSetAttribute(edge_gru_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess) {
-        dsrnn_tc_destroy(st);
-        return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-    }
-    *state = st;
-    return nullptr;
+    return cudaGetLastError() == cudaSuccess ? nullptr : "pack_edge_weights_kernel launch failed";
 }
 
 void dsrnn_tc_destroy(void *state)
@@ -622,13 +673,44 @@ const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *, int n_env
     a.three_pass = precision == CN_PREC_BF16X3 ? 1 : 0;
     a.fp16 = precision == CN_PREC_FP16 ? 1 : 0;
     a.debug = 0;
+    a.train = 0;
+    a.in_off_s = a.in_off_t = a.out_off_s = a.out_off_t = 0;
+    a.ws = nullptr; a.hm_hi = a.hm_lo = a.e_hi = a.e_lo = nullptr;
 #ifdef EDGE_PROFILE
     if (const char *dbg = getenv("CN_EDGE_DEBUG")) a.debug = atoi(dbg);
 #endif
     const int max_pairs = st->num_sms / 2;                        // one CTA pair (cluster of 2) per TPC, persistent
     const int grid = 2 * (a.pairs_total < max_pairs ? a.pairs_total : max_pairs);
-    edge_gru_tc_kernel<<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap);
+    edge_gru_tc_kernel<false><<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap);
     ++*launches;
+    const cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
+// One step t of the two masked edge-GRU sequences of the PPO update (both weight sets in one launch), bf16x3:
+// h_out = GRUCell(ReLU(W_enc x_t + b), m_t * h_in) plus the records of the backward (see EdgeTcArgs).
+const char *dsrnn_tc_edge_sequence_step(void *state, int n_envs, int H, const CnEdgeSeqStep *io, cudaStream_t stream)
+{
+    TcState *st = static_cast<TcState *>(state);
+    if (!st) return "tensor-core edge stage was not initialised";
+    EdgeTcArgs a;
+    a.temporal_edges = io->temporal_edges; a.spatial_edges = io->spatial_edges; a.h_in = io->h_in; a.masks = io->masks;
+    a.h_out = io->h_out; a.wimg = st->wimg; a.bias4 = st->bias4; a.enc = st->enc;
+    a.N = n_envs; a.H = H;
+    a.tiles_spatial = (int)(((size_t)n_envs * H + kRows - 1) / kRows);
+    a.tiles_temporal = (n_envs + kRows - 1) / kRows;
+    a.pairs_spatial = (a.tiles_spatial + 1) / 2;
+    a.pairs_total = a.pairs_spatial + (a.tiles_temporal + 1) / 2;
+    a.three_pass = 1; a.fp16 = 0; a.debug = 0;
+    a.train = 1;
+    a.in_off_s = io->in_row_spatial; a.in_off_t = io->in_row_temporal;
+    a.out_off_s = io->out_row_spatial; a.out_off_t = io->out_row_temporal;
+    a.ws = io->ws;
+    a.hm_hi = static_cast<__nv_bfloat16 *>(io->hm_hi); a.hm_lo = static_cast<__nv_bfloat16 *>(io->hm_lo);
+    a.e_hi = static_cast<__nv_bfloat16 *>(io->e_hi); a.e_lo = static_cast<__nv_bfloat16 *>(io->e_lo);
+    const int max_pairs = st->num_sms / 2;
+    const int grid = 2 * (a.pairs_total < max_pairs ? a.pairs_total : max_pairs);
+    edge_gru_tc_kernel<true><<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap);
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }

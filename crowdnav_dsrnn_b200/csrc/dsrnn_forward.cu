@@ -21,6 +21,7 @@
 
 // dsrnn_node_tc.cu: stages 3 + 4 as one tcgen05 kernel
 const char *dsrnn_node_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void **state);
+const char *dsrnn_node_tc_repack(void *state, const CnDsrnnWeights *w, cudaStream_t stream);
 void dsrnn_node_tc_destroy(void *state);
 const char *dsrnn_node_tc_forward(void *state, int n_envs, const CnDsrnnIO *io, const float *cat, float *feat, int precision,
                                   cudaStream_t stream, int *launches);
@@ -60,6 +61,7 @@ float dsrnn_time_ms(CnDsrnn *m, int *count)
 
 // implemented in dsrnn_edge_tc.cu
 const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void **state);
+const char *dsrnn_tc_repack(void *state, const CnDsrnnWeights *w, cudaStream_t stream);
 void dsrnn_tc_destroy(void *state);
 const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *w, int n_envs, int H, const CnDsrnnIO *io,
                                   int precision, cudaStream_t stream, int *launches);
@@ -412,12 +414,14 @@ static void destroy_tc_linears(CnDsrnn *m)
     m->att_wc = m->att_bc = nullptr;
 }
 
-static const char *create_tc_linears(CnDsrnn *m, cudaStream_t s)
+// `create`: allocate the packed images and pack; otherwise re-pack the current weights into the existing images
+static const char *pack_tc_linears(CnDsrnn *m, cudaStream_t s, bool create)
 {
     const CnDsrnnWeights &w = m->w;
     const char *msg;
-#define CN_TCL(L, W0, B0, N0, W1, B1, N1, K, NT) if ((msg = tc_linear_create(&m->L, W0, B0, N0, W1, B1, N1, K, NT, s))) return msg
-    if (cudaMalloc(&m->att_wc, 256 * 256 * sizeof(float)) != cudaSuccess || cudaMalloc(&m->att_bc, 256 * sizeof(float)) != cudaSuccess)
+#define CN_TCL(L, W0, B0, N0, W1, B1, N1, K, NT) \
+    if ((msg = create ? tc_linear_create(&m->L, W0, B0, N0, W1, B1, N1, K, NT, s) : tc_linear_repack(&m->L, W0, B0, N0, W1, B1, N1, s))) return msg
+    if (create && (cudaMalloc(&m->att_wc, 256 * 256 * sizeof(float)) != cudaSuccess || cudaMalloc(&m->att_bc, 256 * sizeof(float)) != cudaSuccess))
         return "cudaMalloc of the folded attention projection failed";
     fold_attention_kernel<<<256, 256, 0, s>>>(w.att_t_w, w.att_t_b, w.att_s_w, m->att_wc, m->att_bc);
     CN_TCL(att_qt, m->att_wc, m->att_bc, 256, nullptr, nullptr, 0, 256, 256);
@@ -429,7 +433,7 @@ static const char *create_tc_linears(CnDsrnn *m, cudaStream_t s)
     CN_TCL(actor2, w.actor2_w, w.actor2_b, 256, nullptr, nullptr, 0, 256, 256);
     CN_TCL(critic2, w.critic2_w, w.critic2_b, 256, nullptr, nullptr, 0, 256, 256);
 #undef CN_TCL
-    return nullptr;
+    return cudaGetLastError() == cudaSuccess ? nullptr : "packing the linear layers failed";
 }
 
 const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t stream, CnDsrnn **out)
@@ -442,11 +446,13 @@ const char *dsrnn_create(const CnDsrnnWeights *w, int device, cudaStream_t strea
     m->tc_state = nullptr;
     m->timing = false;
     cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
-    const char *env = getenv("CN_NODE_UNFUSED");
+#ifdef CN_DEBUG_SWITCHES
+    const char *env = getenv("CN_NODE_UNFUSED");      // development builds only: one launch per node / head layer
     m->unfused_node = env && env[0] == '1';
+#endif
     const char *msg = dsrnn_tc_create(w, stream, &m->tc_state);
     if (!msg) msg = dsrnn_node_tc_create(w, stream, &m->node_state);
-    if (!msg) msg = create_tc_linears(m, stream);
+    if (!msg) msg = pack_tc_linears(m, stream, true);
     if (msg) { dsrnn_destroy(m); return msg; }
     *out = m;
     return nullptr;
@@ -462,20 +468,26 @@ void dsrnn_destroy(CnDsrnn *m)
     delete m;
 }
 
+// New weight VALUES (after an optimiser step or load_state_dict), possibly at new addresses: every packed image is
+// re-written in place by its pack kernel on `stream`.  Nothing is freed or allocated and nothing synchronises, so the
+// images keep their addresses -- CUDA graphs that captured a forward (rollout.GraphedRollout) stay valid and simply see
+// the new weights -- and a failure leaves the previous state usable.
 const char *dsrnn_update_weights(CnDsrnn *m, const CnDsrnnWeights *w, cudaStream_t stream)
 {
+    if (!m->tc_state || !m->node_state) return "dsrnn_update_weights: model was not fully created";
     m->w = *w;
-    if (m->tc_state) dsrnn_tc_destroy(m->tc_state);
-    m->tc_state = nullptr;
-    if (m->node_state) dsrnn_node_tc_destroy(m->node_state);
-    m->node_state = nullptr;
-    destroy_tc_linears(m);
-    const char *msg = dsrnn_tc_create(w, stream, &m->tc_state);
-    if (!msg) msg = dsrnn_node_tc_create(w, stream, &m->node_state);
-    return msg ? msg : create_tc_linears(m, stream);
+    const char *msg = dsrnn_tc_repack(m->tc_state, w, stream);
+    if (!msg) msg = dsrnn_node_tc_repack(m->node_state, w, stream);
+    return msg ? msg : pack_tc_linears(m, stream, false);
 }
 
 int dsrnn_last_launches(const CnDsrnn *m) { return m->last_launches; }
+int dsrnn_device(const CnDsrnn *m) { return m->device; }
+const char *dsrnn_tc_edge_sequence_step(void *state, int n_envs, int H, const CnEdgeSeqStep *io, cudaStream_t stream);
+const char *dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, const CnEdgeSeqStep *io, cudaStream_t stream)
+{
+    return dsrnn_tc_edge_sequence_step(m->tc_state, n_envs, human_num, io, stream);
+}
 void dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env) { m->refill_env = env; }
 
 // one linear layer, on CUDA cores (fp32) or tensor cores (bf16x3 / bf16)
@@ -507,7 +519,6 @@ static TcLinearCall call(const float *X, int ldx, int M, float *Y, int ldy, int 
 
 const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int precision, void *workspace, cudaStream_t s)
 {
-    if (cudaSetDevice(m->device) != cudaSuccess) return "cudaSetDevice failed";
     const CnDsrnnWeights &w = m->w;
     Workspace ws;
     carve_ws(&ws, workspace, N, H);

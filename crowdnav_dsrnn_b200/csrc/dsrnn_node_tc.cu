@@ -64,12 +64,14 @@ struct PackSeg { const float *w; int ld, src_row, k0, dst_row, count; };
 struct PackChunk { PackSeg seg[2]; int nseg; };
 struct PackTable { PackChunk c[kNumChunks]; };
 
-__global__ void pack_node_weights_kernel(const PackTable *__restrict__ table, __nv_bfloat16 *__restrict__ wimg)
+static_assert(sizeof(PackTable) <= 3584, "the pack table travels as a kernel parameter");
+
+__global__ void pack_node_weights_kernel(const __grid_constant__ PackTable table, __nv_bfloat16 *__restrict__ wimg)
 {
     const int total = kNumChunks * 256 * 64;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int k = idx & 63, row = (idx >> 6) & 255, ch = idx >> 14;
-        const PackChunk &pc = table->c[ch];
+        const PackChunk &pc = table.c[ch];
         float w = 0.0f;
         for (int s = 0; s < pc.nseg; ++s) {
             const PackSeg &g = pc.seg[s];
@@ -493,6 +495,8 @@ void dsrnn_node_tc_destroy(void *state)
     delete st;
 }
 
+const char *dsrnn_node_tc_repack(void *state, const CnDsrnnWeights *w, cudaStream_t stream);
+
 const char *dsrnn_node_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void **state)
 {
     *state = nullptr;
@@ -500,10 +504,7 @@ const char *dsrnn_node_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, v
     if (!st) return "out of host memory";
     st->wimg = nullptr; st->consts = nullptr;
     const size_t img_bytes = (size_t)kNumChunks * 3 * kBSlotBytes;
-    PackTable *d_table = nullptr;
-    if (cudaMalloc(&st->wimg, img_bytes) != cudaSuccess || cudaMalloc(&st->consts, kCTotal * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&d_table, sizeof(PackTable)) != cudaSuccess) {
-        cudaFree(d_table);
+    if (cudaMalloc(&st->wimg, img_bytes) != cudaSuccess || cudaMalloc(&st->consts, kCTotal * sizeof(float)) != cudaSuccess) {
         dsrnn_node_tc_destroy(st);
         return "cudaMalloc of the packed node / head weights failed";
     }
@@ -513,21 +514,30 @@ const char *dsrnn_node_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, v
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    // the schedule of the 34 chunks does not depend on the weights: uploaded once (`chunks` lives on this stack frame)
     bool ok = cudaMemcpyToSymbolAsync(c_chunks, chunks, sizeof(chunks), 0, cudaMemcpyHostToDevice, stream) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(d_table, &table, sizeof(table), cudaMemcpyHostToDevice, stream) == cudaSuccess;
-    ok = ok && cudaStreamSynchronize(stream) == cudaSuccess;      // `table` and `chunks` live on this stack frame
-    if (ok) {
-        pack_node_weights_kernel<<<512, 256, 0, stream>>>(d_table, st->wimg);
-        pack_node_consts_kernel<<<8, 256, 0, stream>>>(*w, st->consts);
-        ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess;
-    }
-    cudaFree(d_table);
+    ok = ok && cudaStreamSynchronize(stream) == cudaSuccess;
     if (!ok || cudaFuncSetAttribute(node_heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess) {
         dsrnn_node_tc_destroy(st);
-        return "packing the node / head weights failed";
+        return "setting up the node / heads kernel failed";
     }
+    if (const char *msg = dsrnn_node_tc_repack(st, w, stream)) { dsrnn_node_tc_destroy(st); return msg; }
     *state = st;
     return nullptr;
+}
+
+// packs the current weights into the EXISTING images (stable addresses, no allocation, no synchronisation): the pack
+// table (pointers into the caller's parameters) travels as a kernel parameter
+const char *dsrnn_node_tc_repack(void *state, const CnDsrnnWeights *w, cudaStream_t stream)
+{
+    NodeTcState *st = static_cast<NodeTcState *>(state);
+    if (!st) return "tensor-core node stage was not initialised";
+    PackTable table;
+    NodeChunk chunks[kNumChunks];
+    build_tables(*w, &table, chunks);
+    pack_node_weights_kernel<<<512, 256, 0, stream>>>(table, st->wimg);
+    pack_node_consts_kernel<<<8, 256, 0, stream>>>(*w, st->consts);
+    return cudaGetLastError() == cudaSuccess ? nullptr : "packing the node / head weights failed";
 }
 
 const char *dsrnn_node_tc_forward(void *state, int n_envs, const CnDsrnnIO *io, const float *cat, float *feat, int precision,

@@ -266,14 +266,22 @@ const char *tc_linear_create(TcLinear *L, const float *W0, const float *b0, int 
     const size_t bytes = (size_t)L->n_blocks * (K / 64) * 3 * n_tile * 128;
     if (cudaMalloc(&L->wimg, bytes) != cudaSuccess || cudaMalloc(&L->bias, (size_t)L->n_blocks * n_tile * sizeof(float)) != cudaSuccess)
         return "tc_linear_create: cudaMalloc failed";
-    pack_linear_kernel<<<128, 256, 0, stream>>>(W0, n0, W1, n1, b0, b1, K, n_tile, L->n_blocks,
-                                                reinterpret_cast<__nv_bfloat16 *>(L->wimg), L->bias);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess)
             return "tc_linear_create: cudaFuncSetAttribute failed";
         attr_set = true;
     }
+    return tc_linear_repack(L, W0, b0, n0, W1, b1, n1, stream);
+}
+
+// packs new values of the same weights into the existing images (stable addresses, no allocation, no synchronisation)
+const char *tc_linear_repack(TcLinear *L, const float *W0, const float *b0, int n0, const float *W1, const float *b1, int n1,
+                             cudaStream_t stream)
+{
+    if (!L->wimg || n0 + n1 != L->N) return "tc_linear_repack: layer was not created with this shape";
+    pack_linear_kernel<<<128, 256, 0, stream>>>(W0, n0, W1, n1, b0, b1, L->K, L->n_tile, L->n_blocks,
+                                                reinterpret_cast<__nv_bfloat16 *>(L->wimg), L->bias);
     return cudaGetLastError() == cudaSuccess ? nullptr : "pack_linear_kernel launch failed";
 }
 

@@ -22,5 +22,7 @@ struct TcLinearCall {
 // W = [W0 (n0 rows); W1 (n1 rows, may be NULL/0)], row-major [*, K]; each returns NULL or an error string
 const char *tc_linear_create(TcLinear *L, const float *W0, const float *b0, int n0, const float *W1, const float *b1, int n1,
                              int K, int n_tile, cudaStream_t stream);
+const char *tc_linear_repack(TcLinear *L, const float *W0, const float *b0, int n0, const float *W1, const float *b1, int n1,
+                             cudaStream_t stream);
 void tc_linear_destroy(TcLinear *L);
 const char *tc_linear_run(const TcLinear *L, const TcLinearCall &c, int num_sms, cudaStream_t stream);

@@ -113,6 +113,51 @@ gru_gates_backward_kernel(const float *__restrict__ grad_h, const float *__restr
     }
 }
 
+// Gate gradients of one step, written as the split-bf16 operand G = [pn | pr | pz | pn*r] ([R, 4 hid]) of the tensor-core
+// products that follow (cn_gemm_bf16x3): columns [0, 3 hid) are d(gi) in gate order n|r|z (-> dx, dW_ih), columns
+// [hid, 4 hid) are d(gh) in gate order r|z|n (-> the recurrent product G[:, hid:] W_hh and dW_hh).  d = g * z in place.
+// 9 floats read + 1 float and 8 bf16 written per hidden unit (56 B).
+__global__ void __launch_bounds__(256)
+gru_gates_backward_pairs_kernel(const float *__restrict__ grad_h, float *__restrict__ d, int d_live, const float *__restrict__ m_next,
+                                const float *__restrict__ ws, const float *__restrict__ h_prev, const float *__restrict__ m_cur,
+                                __nv_bfloat16 *__restrict__ g_hi, __nv_bfloat16 *__restrict__ g_lo, int R, int hid)
+{
+    const int q = hid >> 2;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)R * q) return;
+    const int row = (int)(idx / q), c = (int)(idx - (size_t)row * q) << 2;
+    F4 g = ld4(grad_h + (size_t)row * hid + c);
+    float *drow = d + (size_t)row * hid + c;
+    if (d_live) {
+        const float m = m_next[row];
+        const F4 dn = ld4(drow);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g.v[k] = g.v[k] + dn.v[k] * m;
+    }
+    const float *w = ws + (size_t)row * 4 * hid;
+    const F4 r = ld4(w + c), z = ld4(w + hid + c), n = ld4(w + 2 * hid + c), hn = ld4(w + 3 * hid + c);
+    F4 hp = F4{{0.f, 0.f, 0.f, 0.f}};
+    if (h_prev) {
+        const float mc = m_cur[row];
+        hp = ld4(h_prev + (size_t)row * hid + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hp.v[k] *= mc;
+    }
+    F4 pr, pz, pn, pnr, dh;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pn.v[k] = g.v[k] * (1.0f - z.v[k]) * (1.0f - n.v[k] * n.v[k]);
+        pr.v[k] = pn.v[k] * hn.v[k] * r.v[k] * (1.0f - r.v[k]);
+        pz.v[k] = g.v[k] * (hp.v[k] - n.v[k]) * z.v[k] * (1.0f - z.v[k]);
+        pnr.v[k] = pn.v[k] * r.v[k];
+        dh.v[k] = g.v[k] * z.v[k];
+    }
+    st4(drow, dh);
+    const size_t o = (size_t)row * 4 * hid + c;
+    st4_split(g_hi + o, g_lo + o, pn); st4_split(g_hi + o + hid, g_lo + o + hid, pr);
+    st4_split(g_hi + o + 2 * hid, g_lo + o + 2 * hid, pz); st4_split(g_hi + o + 3 * hid, g_lo + o + 3 * hid, pnr);
+}
+
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float *__restrict__ a, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, size_t n4)
 {
@@ -165,5 +210,17 @@ extern "C" int cn_launch_split_bf16(const float *a, void *hi, void *lo, size_t n
     if (n == 0 || (n & 3) || !aligned16(a) || !aligned8(hi) || !aligned8(lo)) return -1;
     const size_t n4 = n >> 2;
     split_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(a, static_cast<__nv_bfloat16 *>(hi), static_cast<__nv_bfloat16 *>(lo), n4);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cn_launch_gru_gates_backward_pairs(const float *grad_h, float *d, int d_live, const float *m_next, const float *ws,
+                                                  const float *h_prev, const float *m_cur, void *g_hi, void *g_lo, int R, int hid,
+                                                  cudaStream_t stream)
+{
+    if (R < 1 || hid < 4 || (hid & 3) || !aligned16(grad_h) || !aligned16(d) || !aligned16(ws) || (h_prev && (!aligned16(h_prev) || !m_cur)) ||
+        (d_live && !m_next) || !aligned8(g_hi) || !aligned8(g_lo)) return -1;
+    const size_t n = (size_t)R * (hid >> 2);
+    gru_gates_backward_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_h, d, d_live, m_next, ws, h_prev, m_cur,
+        static_cast<__nv_bfloat16 *>(g_hi), static_cast<__nv_bfloat16 *>(g_lo), R, hid);
     return (int)cudaGetLastError();
 }

@@ -172,6 +172,21 @@ __device__ __forceinline__ float gru_blend(float xr, float xz, float xn, float x
     return n + z * (h - n);
 }
 
+// the same cell, also returning the gate values the backward of the PPO update needs (r, z, n)
+__device__ __forceinline__ float gru_blend_ws(float xr, float xz, float xn, float xh, float h, float &r_out, float &z_out, float &n_out)
+{
+    const float kLog2e = 1.4426950408889634f;
+    const float r = fast_rcp(1.0f + fast_exp2(-kLog2e * xr));
+    const float u = xn + r * xh;
+    const float ez = fast_exp2(fminf(-kLog2e * xz, 60.0f));
+    const float en = fast_exp2(fminf(2.0f * kLog2e * u, 60.0f));
+    const float q = fast_rcp((1.0f + ez) * (1.0f + en));
+    const float z = q * (1.0f + en);
+    const float n = 1.0f - 2.0f * q * (1.0f + ez);
+    r_out = r; z_out = z; n_out = n;
+    return n + z * (h - n);
+}
+
 // split an fp32 pair into bf16 hi and bf16 lo (residual) pairs: x ~= hi + lo with ~2^-17 relative error
 __device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t &hi, uint32_t &lo)
 {

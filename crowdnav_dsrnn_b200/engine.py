@@ -22,19 +22,37 @@ def _ptr(t):
 class StepBuffers:
     """One set of per-step outputs (torch-owned device tensors in the reference's shapes)."""
 
+    # per-step records a caller may keep beyond the next step (infos): carved out of ONE block so that a single
+    # device-side clone snapshots them all (envs.LazyInfos)
+    INFO_FIELDS = (("info", torch.float32, abi.INFO_DIM), ("reward", torch.float32, 1), ("episode_return", torch.float32, 1),
+                   ("event", torch.int32, 1), ("scenario", torch.int32, 1), ("episode_length", torch.int32, 1),
+                   ("done", torch.uint8, 1))
+
+    @classmethod
+    def carve_info(cls, block, n):
+        """Typed views (name -> tensor) into an info block; every view starts on a 256-byte boundary."""
+        views, off = {}, 0
+        for name, dtype, width in cls.INFO_FIELDS:
+            nbytes = n * width * torch.empty(0, dtype=dtype).element_size()
+            v = block[off:off + nbytes].view(dtype)
+            views[name] = v.view(n, width) if width > 1 else v
+            off += (nbytes + 255) & ~255
+        return views
+
+    @classmethod
+    def info_block_bytes(cls, n):
+        return sum(((n * width * torch.empty(0, dtype=dtype).element_size()) + 255) & ~255 for _, dtype, width in cls.INFO_FIELDS)
+
     def __init__(self, n, h, device):
         f32 = dict(dtype=torch.float32, device=device)
+        self.n = n
         self.robot_node = torch.zeros(n, 1, 7, **f32)
         self.temporal_edges = torch.zeros(n, 1, 2, **f32)
         self.spatial_edges = torch.zeros(n, h, 2, **f32)
         self.visible_mask = torch.zeros(n, dtype=torch.int32, device=device)
-        self.reward = torch.zeros(n, **f32)
-        self.done = torch.zeros(n, dtype=torch.uint8, device=device)
-        self.event = torch.zeros(n, dtype=torch.int32, device=device)
-        self.scenario = torch.zeros(n, dtype=torch.int32, device=device)
-        self.info = torch.zeros(n, abi.INFO_DIM, **f32)
-        self.episode_return = torch.zeros(n, **f32)
-        self.episode_length = torch.zeros(n, dtype=torch.int32, device=device)
+        self.info_block = torch.zeros(self.info_block_bytes(n), dtype=torch.uint8, device=device)
+        for name, view in self.carve_info(self.info_block, n).items():
+            setattr(self, name, view)
         self.goal_changed = torch.zeros(n, dtype=torch.int32, device=device)
         self.not_done = torch.ones(n, 1, **f32)            # 1 - done: the masks of the next Policy.act
         self.obs_struct = abi.CnObsOut(_ptr(self.robot_node), _ptr(self.temporal_edges), _ptr(self.spatial_edges),

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import abi
-from .engine import CrowdEngine
+from .engine import CrowdEngine, StepBuffers
 from .info import make_event
 from .spaces import crowd_spaces
 
@@ -31,8 +31,11 @@ class LazyInfos(object):
     """Sequence of per-env info dicts materialised on access (hard part 7)."""
 
     def __init__(self, buf, side_preference, t0):
-        self.tensors = {"event": buf.event, "scenario": buf.scenario, "info": buf.info, "done": buf.done,
-                        "episode_return": buf.episode_return, "episode_length": buf.episode_length}
+        # The engine double-buffers its outputs, so `buf` is overwritten by the step after next.  The reference returns
+        # materialised dicts that stay valid for ever (train.py keeps them for logging), so the per-step records are
+        # snapshotted here -- one device-side clone of the block they are carved from, no synchronisation.
+        snap = StepBuffers.carve_info(buf.info_block.clone(), buf.n)
+        self.tensors = {k: snap[k] for k in ("event", "scenario", "info", "done", "episode_return", "episode_length")}
         self._side = side_preference
         self._host = None
         self._t0 = t0

@@ -22,7 +22,7 @@ import weakref
 import torch
 import torch.nn as nn
 
-from . import _lib, abi
+from . import _lib, abi, native
 
 
 def _ptr(t):
@@ -37,7 +37,8 @@ def _orthogonal(module, gain=1.0):
 
 # GEMM arithmetic of the masked GRU sequences' recurrent products (PPO update): "fp32" = torch's fp32 matmul (SIMT, or TF32
 # when torch.backends.cuda.matmul.allow_tf32 is set), "bf16x3" = split-bf16 3-pass on the tensor cores with fp32 accumulation
-# (A_hi B_hi + A_lo B_hi + A_hi B_lo, operand error ~2^-16: the rollout kernels' precision), CUDA only.
+# (A_hi B_hi + A_lo B_hi + A_hi B_lo, operand error ~2^-16: the rollout kernels' precision) through three cuBLAS calls,
+# "native" = the same arithmetic in ONE launch of the library's tcgen05 kernel (cn_gemm_bf16x3, csrc/gemm_bf16x3.cu); CUDA only.
 SEQUENCE_GEMM = "fp32"
 
 
@@ -85,8 +86,14 @@ class _MaskedGruSequence(torch.autograd.Function):
     def forward(ctx, x, h0, m, w_ih, w_hh, b_ih, b_hh):
         T, R, hid = x.shape[0], x.shape[1], h0.shape[1]
         cuda = x.is_cuda and x.dtype is torch.float32
-        x3 = cuda and SEQUENCE_GEMM == "bf16x3" and (R * hid) % 4 == 0
-        if x3:
+        nat = cuda and SEQUENCE_GEMM == "native" and hid % 8 == 0 and x.shape[2] % 8 == 0
+        x3 = nat or (cuda and SEQUENCE_GEMM == "bf16x3" and (R * hid) % 4 == 0)
+        x_pair = ()
+        if nat:
+            x_pair = native.split(x.reshape(T * R, -1))
+            gi = x.new_empty(T, R, 3 * hid)
+            native.gemm([dict(a=x_pair, b=native.split(w_ih), c=gi.view(T * R, 3 * hid))])
+        elif x3:
             gi = _mm_bf16x3(x.reshape(T * R, -1), *_split_bf16(w_ih.t())).view(T, R, 3 * hid)
         else:
             gi = torch.matmul(x, w_ih.t())                   # [T, R, 3h]; the gate math adds both biases
@@ -101,14 +108,21 @@ class _MaskedGruSequence(torch.autograd.Function):
             lib = _lib.load()
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
             b_ih, b_hh = b_ih.contiguous(), b_hh.contiguous()
-            if x3:                                           # bf16 hi/lo pair of every step's masked state, written by the gate kernel
+            if nat:
+                w_pair, gh_buf = native.split(w_hh), x.new_empty(R, 3 * hid)      # W_hh [3h, hid]: K-major B of gh = hm W_hh^T
+            elif x3:
                 wt_hi, wt_lo = _split_bf16(w_hh_t)
+            if x3:                                           # bf16 hi/lo pair of every step's masked state, written by the gate kernel
                 hm_hi = torch.empty(T, R, hid, dtype=torch.bfloat16, device=x.device)
                 hm_lo = torch.empty_like(hm_hi)
                 _lib.check(lib.cn_split_bf16(_ptr(hm[0]), _ptr(hm_hi[0]), _ptr(hm_lo[0]), R * hid, stream), "cn_split_bf16")
                 pairs = (hm_hi, hm_lo)
             for t in range(T):
-                gh = _mm3(hm_hi[t], hm_lo[t], wt_hi, wt_lo) if x3 else torch.mm(hm[t], w_hh_t)
+                if nat:
+                    gh = gh_buf
+                    native.gemm([dict(a=(hm_hi[t], hm_lo[t]), b=w_pair, c=gh)])
+                else:
+                    gh = _mm3(hm_hi[t], hm_lo[t], wt_hi, wt_lo) if x3 else torch.mm(hm[t], w_hh_t)
                 last = t == T - 1
                 _lib.check(lib.cn_gru_gates_forward(_ptr(gi[t]), _ptr(gh), _ptr(hm[t]), _ptr(b_ih), _ptr(b_hh),
                                                     None if last else _ptr(m[t + 1]), _ptr(hs[t]),
@@ -127,9 +141,10 @@ class _MaskedGruSequence(torch.autograd.Function):
                 ws[t] = torch.cat([r, z, n, hn], 1)
                 if t + 1 < T:
                     torch.mul(hs[t], m[t + 1], out=hm[t + 1])
-        ctx.save_for_backward(x, m, w_ih, w_hh, hm, ws, *pairs)
+        ctx.save_for_backward(x, m, w_ih, w_hh, hm, ws, *pairs, *x_pair)
         ctx.cuda = cuda
         ctx.x3 = x3
+        ctx.nat = nat
         return hs
 
     @staticmethod
@@ -144,8 +159,11 @@ class _MaskedGruSequence(torch.autograd.Function):
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
             grad_hs = grad_hs.contiguous()
             dhm = x.new_empty(R, hid)
+            if ctx.nat:
+                w_pair = native.split(w_hh)                  # [3h, hid] = [K, N]: MN-major B of d_next = dhm + dgh W_hh
+                dhm_alt = x.new_empty(R, hid)
             if ctx.x3:
-                w_hi, w_lo = _split_bf16(w_hh)
+                w_hi, w_lo = (None, None) if ctx.nat else _split_bf16(w_hh)
                 bf = lambda: torch.empty(T, R, 3 * hid, dtype=torch.bfloat16, device=x.device)
                 dgi_hi, dgi_lo, dgh_hi, dgh_lo = bf(), bf(), bf(), bf()
             for t in range(T - 1, -1, -1):
@@ -153,7 +171,11 @@ class _MaskedGruSequence(torch.autograd.Function):
                 _lib.check(lib.cn_gru_gates_backward(_ptr(grad_hs[t]), _ptr(d_next), None if d_next is None else _ptr(m[t + 1]),
                                                      _ptr(ws[t]), _ptr(hm[t]), _ptr(dgi[t]), _ptr(dgh[t]), _ptr(dhm), *extra,
                                                      R, hid, stream), "cn_gru_gates_backward")
-                d_next = _mm3(dgh_hi[t], dgh_lo[t], w_hi, w_lo, add=dhm) if ctx.x3 else torch.addmm(dhm, dgh[t], w_hh)
+                if ctx.nat:
+                    native.gemm([dict(a=(dgh_hi[t], dgh_lo[t]), b=w_pair, b_mn=True, c=dhm, accumulate=True)])
+                    d_next, dhm, dhm_alt = dhm, dhm_alt, dhm      # ping-pong: the next gate kernel reads d_next and writes dhm
+                else:
+                    d_next = _mm3(dgh_hi[t], dgh_lo[t], w_hi, w_lo, add=dhm) if ctx.x3 else torch.addmm(dhm, dgh[t], w_hh)
         else:
             for t in range(T - 1, -1, -1):
                 g = grad_hs[t] if d_next is None else grad_hs[t] + d_next * m[t + 1]
@@ -165,7 +187,19 @@ class _MaskedGruSequence(torch.autograd.Function):
                 dgh[t] = torch.cat([dpre_r, dpre_z, dpre_n * r], 1)
                 d_next = torch.addmm(g * z, dgh[t], w_hh)
         dgi2, dgh2 = dgi.view(T * R, 3 * hid), dgh.view(T * R, 3 * hid)
-        if ctx.x3:
+        if ctx.nat:
+            gi_pair = (dgi_hi.view(T * R, 3 * hid), dgi_lo.view(T * R, 3 * hid))
+            gh_pair = (dgh_hi.view(T * R, 3 * hid), dgh_lo.view(T * R, 3 * hid))
+            hm_pair = (pairs[0].view(T * R, hid), pairs[1].view(T * R, hid))
+            x_pair = tuple(pairs[2:4])
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = x.new_empty(T, R, x.shape[2])
+                native.gemm([dict(a=gi_pair, b=native.split(w_ih), b_mn=True, c=dx.view(T * R, -1))])
+            dw_ih, dw_hh = torch.zeros_like(w_ih), torch.zeros_like(w_hh)
+            native.gemm([dict(a=gi_pair, a_mn=True, b=x_pair, b_mn=True, c=dw_ih, split_k=0),
+                         dict(a=gh_pair, a_mn=True, b=hm_pair, b_mn=True, c=dw_hh, split_k=0)])
+        elif ctx.x3:
             a_hi, a_lo = dgi_hi.view(T * R, 3 * hid), dgi_lo.view(T * R, 3 * hid)
             dx = _mm3(a_hi, a_lo, *_split_bf16(w_ih)).view(T, R, -1) if ctx.needs_input_grad[0] else None
             dw_ih = _mm3(a_hi.t(), a_lo.t(), *_split_bf16(x.reshape(T * R, -1)))
@@ -349,6 +383,12 @@ class Policy(nn.Module):
         self._weights_key = key
         return lib
 
+    def invalidate_weights(self):
+        """Force the next forward to re-pack the weights (call after editing parameters through `.data` or any other
+        path that does not bump their version counter)."""
+        self._weights_key = None
+        self.__dict__.pop("_gauss_cache", None)
+
     def __del__(self):
         try:  # best effort: at interpreter shutdown torch / ctypes may already be torn down
             handle = self.__dict__.get("_handle")
@@ -480,8 +520,11 @@ class Policy(nn.Module):
         """The whole [T, N] chunk at once.  The edge GRUs do not depend on the node RNN (srnn_model.py:464-480), so their
         T steps run first as one `_MaskedGruSequence` each; the attention, the encoders and the heads have no recurrence
         and are evaluated for all T*N samples in one batch; the node GRU is a second (small) masked sequence."""
-        if getattr(self, "sequence_impl", "batched") == "per_step":
+        impl = getattr(self, "sequence_impl", "batched")
+        if impl == "per_step":
             return self._torch_sequence_forward_per_step(inputs, rnn_hxs, masks)
+        if impl == "native":
+            return self._native_sequence_forward(inputs, rnn_hxs, masks)
         b = self.base
         se = inputs["spatial_edges"]
         H = se.shape[1]
@@ -513,6 +556,52 @@ class Policy(nn.Module):
         rnn_hxs["human_node_rnn"] = h_n[-1].unsqueeze(1)
         rnn_hxs["human_human_edge_rnn"] = torch.cat([o_t[-1].unsqueeze(1), o_s[-1].view(N, H, 256)], 1)
         return b.critic_linear(b.critic(y)), b.actor(y), rnn_hxs
+
+    def _native_sequence_forward(self, inputs, rnn_hxs, masks):
+        """The batched form with every contraction on the library's own tensor-core kernels (native.py): the two edge GRUs as
+        one `EdgeGruSequence` (the rollout's tcgen05 edge kernel in training mode + its backward), every linear layer and
+        the node GRU's products on cn_gemm_bf16x3.  The attention's key projection is folded into the query exactly as in
+        the rollout kernel: q.(W_s o_i + b_s) = (W_s^T q).o_i + q.b_s, and the softmax ignores the per-sample constant."""
+        global SEQUENCE_GEMM
+        b = self.base
+        se = inputs["spatial_edges"]
+        if se.device.type != "cuda":
+            raise _lib.CrowdNavLibraryError("sequence_impl='native' runs on a B200 only (no CPU fallback); use 'batched' on the CPU")
+        H = se.shape[1]
+        N = rnn_hxs["human_node_rnn"].shape[0]
+        T = se.shape[0] // N
+        S = N * H
+        rn = inputs["robot_node"].reshape(T * N, 7)
+        mk = masks.reshape(T, N)
+        h_node = rnn_hxs["human_node_rnn"].reshape(N, 128)
+        h_edge = rnn_hxs["human_human_edge_rnn"].reshape(N, H + 1, 256)
+        h0 = torch.cat([h_edge[:, 1:].reshape(S, 256), h_edge[:, 0]], 0)
+        es, et = b.humanhumanEdgeRNN_spatial, b.humanhumanEdgeRNN_temporal
+        edge_params = [p for m in (es, et) for p in (m.encoder_linear.weight, m.encoder_linear.bias, m.gru.weight_ih_l0,
+                                                     m.gru.weight_hh_l0, m.gru.bias_ih_l0, m.gru.bias_hh_l0)]
+        hs = native.EdgeGruSequence.apply(self, se.reshape(T, S, 2), inputs["temporal_edges"].reshape(T, N, 2), h0, mk, *edge_params)
+        o_s, o_t = hs[:T * S].view(T, S, 256), hs[T * S:].view(T, N, 256)
+        o_t2, o_s3 = o_t.reshape(T * N, 256), o_s.view(T * N, H, 256)
+        q = native.linear(o_t2, b.attn.temporal_edge_layer[0])                                   # [TN, 64]
+        qt = native.matmul_nt(q, b.attn.spatial_edge_layer[0].weight.t())                        # [TN, 256] = q W_s
+        const = (q * b.attn.spatial_edge_layer[0].bias).sum(-1, keepdim=True)                    # q.b_s (no effect on the softmax)
+        alpha = torch.softmax((torch.bmm(o_s3, qt.unsqueeze(-1)).squeeze(-1) + const) * (H / math.sqrt(64.0)), dim=-1)
+        c = torch.bmm(alpha.unsqueeze(1), o_s3).squeeze(1)
+        enc = torch.relu(b.humanNodeRNN.encoder_linear(b.robot_linear(rn)))                      # K = 7 / 3: CUDA cores
+        emb = native.linear(torch.cat([o_t2, c], -1), b.humanNodeRNN.edge_attention_embed, "relu")
+        prev, SEQUENCE_GEMM = SEQUENCE_GEMM, "native"
+        try:
+            g = b.humanNodeRNN.gru
+            h_n = _MaskedGruSequence.apply(torch.cat([enc, emb], -1).view(T, N, -1), h_node, mk.reshape(T, N, 1),
+                                           g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)     # [T, N, 128]
+        finally:
+            SEQUENCE_GEMM = prev
+        y = native.linear(h_n.view(T * N, 128), b.humanNodeRNN.output_linear)
+        actor = native.linear(native.linear(y, b.actor[0], "tanh"), b.actor[2], "tanh")
+        critic = native.linear(native.linear(y, b.critic[0], "tanh"), b.critic[2], "tanh")
+        rnn_hxs["human_node_rnn"] = h_n[-1].unsqueeze(1)
+        rnn_hxs["human_human_edge_rnn"] = torch.cat([o_t[-1].unsqueeze(1), o_s[-1].view(N, H, 256)], 1)
+        return b.critic_linear(critic), actor, rnn_hxs
 
     def _torch_sequence_forward_per_step(self, inputs, rnn_hxs, masks):
         """One autograd graph per rollout step (the first form of this path; kept as the cross-check of the batched one)."""

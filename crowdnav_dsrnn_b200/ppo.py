@@ -45,7 +45,8 @@ def normalized_advantages(rollouts, group=None):
 
 class PPO:
     def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef, lr=None, eps=None,
-                 max_grad_norm=None, use_clipped_value_loss=True, group=None, max_envs_per_pass=None, tf32=False, bf16x3=False):
+                 max_grad_norm=None, use_clipped_value_loss=True, group=None, max_envs_per_pass=None, tf32=False, bf16x3=False,
+                 native=False):
         self.actor_critic = actor_critic
         self.clip_param = clip_param
         self.ppo_epoch = ppo_epoch
@@ -58,6 +59,7 @@ class PPO:
         self.max_envs_per_pass = max_envs_per_pass
         self.tf32 = bool(tf32)         # TF32 tensor cores for the fp32 GEMMs of the update's forward + backward
         self.bf16x3 = bool(bf16x3)     # split-bf16 3-pass tensor-core GEMMs (fp32-level accuracy) for the recurrent products
+        self.native = bool(native)     # every contraction of the update on the library's own tcgen05 kernels (native.py), CUDA only
         self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, eps=eps)
         self.perm_fn = None            # tests / reproducibility: callable(num_processes) -> env permutation
         self.allreduce_calls = 0
@@ -98,14 +100,18 @@ class PPO:
         from . import model as _model
 
         prev, prev_gemm = torch.backends.cuda.matmul.allow_tf32, _model.SEQUENCE_GEMM
+        prev_impl = getattr(self.actor_critic, "sequence_impl", "batched")
         torch.backends.cuda.matmul.allow_tf32 = prev or self.tf32
         if self.bf16x3:
             _model.SEQUENCE_GEMM = "bf16x3"
+        if self.native and rollouts.device.type == "cuda":
+            self.actor_critic.sequence_impl = "native"
         try:
             return self._update(rollouts)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
             _model.SEQUENCE_GEMM = prev_gemm
+            self.actor_critic.sequence_impl = prev_impl
 
     def _update(self, rollouts):
         advantages = normalized_advantages(rollouts, self.group)

@@ -130,7 +130,7 @@ class SRNNRolloutStorage:
         if perm is None:
             perm = torch.randperm(N)
         perm = torch.as_tensor(perm, dtype=torch.int64).to(self.device)
-        for start in range(0, N, n):
+        for start in range(0, n * num_mini_batch, n):      # N % num_mini_batch envs are left out, as in PPO.update
             ind = perm[start:start + n]
             if env_slice is not None:
                 ind = ind[env_slice[0]:env_slice[1]]

@@ -41,8 +41,10 @@ def train(config, device=None, num_updates=None, output_dir=None, actor_critic=N
         actor_critic = Policy(envs.observation_space.spaces, envs.action_space, base=config.robot.policy, base_kwargs=config)
     actor_critic.to(device)
     if world > 1:                         # same initial weights everywhere
-        for p in actor_critic.parameters():
-            dist.broadcast(p.data, src=0)
+        with torch.no_grad():             # in place on the parameter itself: bumps its version, so packed copies are refreshed
+            for p in actor_critic.parameters():
+                dist.broadcast(p, src=0)
+        actor_critic.invalidate_weights()
     rollouts = SRNNRolloutStorage(T, N, envs.observation_space.spaces, envs.action_space, config.SRNN.human_node_rnn_size,
                                   config.SRNN.human_human_edge_rnn_size, "GRU", device=device,
                                   keep_hidden_history=keep_hidden_history)

@@ -274,6 +274,62 @@ int cn_gru_gates_backward(const float *grad_h, const float *d_next, const float 
  * (same arithmetic as the rollout's CN_PREC_BF16X3).  n % 4 == 0. */
 int cn_split_bf16(const float *a, void *hi, void *lo, size_t n, void *stream);
 
+/*
+ * Native PPO-update path (replaces the cuBLAS calls under `evaluate_actions` + autograd,
+ * model.py:96-104, srnn_model.py:53-104, ppo.py:76-106).
+ *
+ * Sequence layout of every [T, rows, ...] array of the two edge GRUs: the T*S spatial rows (S = n_envs * human_num, step-major,
+ * env-major, human-minor) come first, the T*n_envs temporal rows after them; "row" below is an index into that layout.
+ */
+
+/* One step t of both edge-GRU sequences: h_out = GRUCell(ReLU(W_enc x_t + b), m_t * h_in) on the tensor cores (the rollout's
+ * edge kernel, CN_PREC_BF16X3), also writing what the backward reads. */
+typedef struct CnEdgeSeqStep {
+    const float *temporal_edges;   /* [n_envs, 2]    x_t of the temporal edges */
+    const float *spatial_edges;    /* [S, 2]         x_t of the spatial edges */
+    const float *masks;            /* [n_envs]       m_t */
+    const float *h_in;             /* [*, 256] state before the step: rows in_row_spatial + s, in_row_temporal + e */
+    long long in_row_spatial, in_row_temporal;
+    long long out_row_spatial, out_row_temporal;   /* rows of this step in the arrays below */
+    float *h_out;                  /* [*, 256]  h_t */
+    float *ws;                     /* [*, 1024] r | z | n | W_hn hm + b_hn */
+    void *hm_hi, *hm_lo;           /* bf16 [*, 256] split masked previous state m_t h_{t-1} (operand of dW_hh) */
+    void *e_hi, *e_lo;             /* bf16 [*, 64]  split encoded input (operand of dW_ih) */
+} CnEdgeSeqStep;
+int cn_dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, const CnEdgeSeqStep *io, void *stream);
+
+/* Gate gradients of one step of a masked GRU sequence over `rows` rows, hid % 4 == 0 (elementwise, HBM-bound):
+ *   g = grad_h + (d_inout_is_live ? m_next[row] * d : 0);  writes G = [dpre_n | dpre_r | dpre_z | dpre_n * r] as bf16 hi/lo
+ *   pairs ([rows, 4 hid]: columns [0, 3 hid) are the gradient of gi in gate order n|r|z, columns [hid, 4 hid) the gradient of gh
+ *   in gate order r|z|n) and d = g * z (fp32, in place), to which the caller adds G[:, hid:] W_hh with cn_gemm_bf16x3.
+ *   hm = m_cur[row] * h_prev[row] is the masked state the step started from (h_prev == NULL: zero state). */
+int cn_gru_gates_backward_pairs(const float *grad_h, float *d, int d_live, const float *m_next, const float *ws, const float *h_prev,
+                                const float *m_cur, void *g_hi, void *g_lo, int rows, int hid, void *stream);
+
+/* Generic split-bf16 3-pass tensor-core GEMM (tcgen05, TMA-fed, fp32 accumulation in TMEM):
+ *   C[m, n] (=, +=, or atomically += for split-K)  (A_hi + A_lo)(B_hi + B_lo) minus the lo*lo term  (+ bias[n], activation).
+ * An operand is K-major (row-major [m|n, k] array) or MN-major (row-major [k, m|n] array); lo == NULL drops that operand's
+ * correction pass.  Up to CN_GEMM_MAX_PROBLEMS independent problems per launch (grouped GEMM). */
+#define CN_GEMM_MAX_PROBLEMS 4
+typedef struct CnGemmOperand {
+    const void *hi, *lo;   /* bfloat16, 16-byte aligned; ld % 8 == 0 */
+    long long ld;          /* elements between consecutive rows of the array */
+    int mn_major;          /* 0: array is [m|n, k] ; 1: array is [k, m|n] */
+    int reserved;
+} CnGemmOperand;
+typedef struct CnGemm {
+    CnGemmOperand a, b;
+    float *c;              /* [m, ldc] */
+    long long ldc;
+    const float *bias;     /* [n] or NULL */
+    int m, n, k;
+    int act;               /* 0 none, 1 ReLU, 2 tanh */
+    int accumulate;        /* split_k == 1 only: C += product instead of C = product */
+    int split_k;           /* 1: no split.  >1 or 0 (= chosen by the library): k is cut into slices whose partial products are added
+                              to C with atomics -- C must hold the initial value (zeros); no bias / activation */
+} CnGemm;
+int cn_gemm_bf16x3(const CnGemm *problems, int n_problems, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,13 +130,13 @@ def _sequence_case(dtype, device, n=6, H=5, T=7, seed=0):
     return policy, obs, masks, action, h0
 
 
-def sequence_impls_agree(dtype, device, tol):
+def sequence_impls_agree(dtype, device, tol, impls=("per_step", "batched"), case=None):
     """evaluate_actions over a [T, n] chunk: the batched form (one masked GRU sequence per recurrent unit, everything else
     evaluated for all T*n samples at once) against the per-step autograd graph -- outputs, final hidden state, every
     parameter gradient and the gradient with respect to the initial hidden state."""
-    policy, obs, masks, action, h0 = _sequence_case(dtype, device)
+    policy, obs, masks, action, h0 = _sequence_case(dtype, device, **(case or {}))
     res = {}
-    for impl in ("per_step", "batched"):
+    for impl in impls:
         policy.sequence_impl = impl
         policy.zero_grad(set_to_none=True)
         hx = {k: v.clone().requires_grad_(True) for k, v in h0.items()}
@@ -147,7 +147,7 @@ def sequence_impls_agree(dtype, device, tol):
         grads = {k: q.grad.clone() for k, q in policy.named_parameters() if q.grad is not None}
         res[impl] = (value.detach(), logp.detach(), out["human_human_edge_rnn"].detach(), out["human_node_rnn"].detach(),
                      grads, [hx[k].grad.clone() for k in sorted(hx)])
-    a, b = res["per_step"], res["batched"]
+    a, b = res[impls[0]], res[impls[1]]
     for x, y in list(zip(a[:4], b[:4])) + list(zip(a[5], b[5])):
         assert (x - y).abs().max().item() <= tol * max(1.0, x.abs().max().item())
     assert sorted(a[4]) == sorted(b[4]) and len(a[4]) >= 40

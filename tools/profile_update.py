@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--bf16x3", action="store_true", help="model.SEQUENCE_GEMM = 'bf16x3'")
     ap.add_argument("--per-step", action="store_true", help="the per-step autograd graph (Policy.sequence_impl='per_step')")
+    ap.add_argument("--native", action="store_true", help="Policy.sequence_impl='native': every contraction on the library's tcgen05 kernels")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.backends.cuda.matmul.allow_tf32 = args.tf32
@@ -36,6 +37,8 @@ def main():
     policy = Policy(obs_space.spaces, act_space, base="srnn", base_kwargs=cfg).to(dev)
     if args.per_step:
         policy.sequence_impl = "per_step"
+    if args.native:
+        policy.sequence_impl = "native"
     g = torch.Generator(device=dev).manual_seed(0)
     obs = {"robot_node": torch.randn(T * n, 1, 7, device=dev, generator=g),
            "temporal_edges": torch.randn(T * n, 1, 2, device=dev, generator=g),
@@ -59,8 +62,8 @@ def main():
         one_pass()
     e1.record()
     torch.cuda.synchronize()
-    print("pass of %d envs x %d humans x %d steps: %.2f ms (tf32=%s, per_step=%s, bf16x3=%s), peak mem %.2f GB" % (
-        n, H, T, e0.elapsed_time(e1) / 3, args.tf32, args.per_step, args.bf16x3, torch.cuda.max_memory_allocated() / 2**30))
+    print("pass of %d envs x %d humans x %d steps: %.2f ms (tf32=%s, per_step=%s, bf16x3=%s, native=%s), peak mem %.2f GB" % (
+        n, H, T, e0.elapsed_time(e1) / 3, args.tf32, args.per_step, args.bf16x3, args.native, torch.cuda.max_memory_allocated() / 2**30))
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         one_pass()
