@@ -14,17 +14,22 @@
 // Both forms are fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) straight into the canonical UMMA shared-memory
 // layouts; the MMA instruction descriptor carries the a_major / b_major bits.
 //
-// One persistent CTA per SM walks work items (problem, k-slice, 128-row tile, n-tile).  192 threads:
+// One persistent CTA per SM walks work items (problem, k-slice, 128-row tile, n-tile).  320 threads:
 //   warp 0      TMA producer: one elected lane streams 64-deep k-blocks of A (hi, lo) and B (hi, lo) through a ring of stages;
 //   warp 1      owns TMEM (512 columns = two accumulator buffers of up to 256 columns) and issues tcgen05.mma
 //               (M = 128, N = n-tile, K = 16; 12 per k-block for the three passes);
-//   warps 2-5   epilogue: tcgen05.ld -> (bias, activation) -> transposed through shared memory -> coalesced float4 stores,
-//               read-modify-write (accumulate) or red.global.add (split-K partial sums), overlapped with the MMAs of the
-//               next item through the second TMEM buffer.
+//   warps 2-9   epilogue: tcgen05.ld -> (bias, activation) -> 256-bit stores of each lane's row segment, read-modify-write
+//               (accumulate) or red.global.add (split-K partial sums), overlapped with the MMAs of the next item through
+//               the second TMEM buffer.
+// CTAs are launched as clusters of c = 1, 2 or 4 that walk c consecutive 128-row tiles of the same (k-slice, n-tile) in lock
+// step: the B tile (weights: the same for every row tile, and the larger operand of the recurrent products) is fetched from
+// L2 once per cluster -- every CTA loads 1/c of it and TMA-multicasts it into all c shared memories
+// (cp.async.bulk.tensor ... .multicast::cluster); tcgen05.commit multicasts the "stage free" arrivals back.
 // Up to kMaxProblems independent problems share one launch (grouped GEMM: the spatial / temporal edge GRUs have different
 // weights; the weight gradients of both are one launch).
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "tc_common.cuh"
 #include "../../include/crowdnav_b200.h"
@@ -34,11 +39,11 @@ using namespace tc;
 namespace {
 
 constexpr int kMaxProblems = CN_GEMM_MAX_PROBLEMS;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;              // TMA producer, MMA issuer, 8 epilogue warps
 constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 128;              // one 128 x 64 bf16 image (hi or lo) of A: 16 KB in either major
 constexpr int kMaxStages = 6;
-constexpr int kScratchBytes = 4 * 32 * 33 * 4;     // epilogue transposition: 4 warps x 32 rows x 33 floats
+constexpr int kScratchBytes = 0;
 constexpr int kSmemLimit = 232448 - 1024;          // dynamic shared memory of one sm_100 CTA minus the alignment slack
 
 struct alignas(64) GemmProblem {
@@ -53,7 +58,9 @@ struct alignas(64) GemmProblem {
     int a_mn, b_mn;            // operand majors (1 = MN-major)
     int a_lo_on, b_lo_on;      // passes A_lo*B_hi / A_hi*B_lo enabled
     int act, mode;             // mode 0 store, 1 read-modify-write add, 2 atomic add
-    int item0, items;          // this problem's range of global work items
+    int m_groups;              // groups of c consecutive m-tiles (one per cluster and item)
+    int b_slice_bytes;         // bytes of one CTA's slice of the B tile (K-major: bn/c rows; MN-major: 64/c k-rows of every atom)
+    int item0, items;          // this problem's range of global work items (one item = one cluster-wide group of m-tiles)
     unsigned stage_tx;         // bytes one stage of this problem brings in
 };
 
@@ -61,6 +68,7 @@ struct GemmArgs {
     GemmProblem p[kMaxProblems];
     int n_problems, total_items;
     int stages, stage_bytes, b_off_lo;   // ring geometry: A_hi @0, A_lo @16K, B_hi @32K, B_lo @32K + b_off_lo
+    int cluster;                         // CTAs per cluster (1, 2, 4)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int c0, int c1, uint32_t mbar)
@@ -69,9 +77,35 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int 
                  ::"r"(dst), "l"(tmap), "r"(mbar), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void *tmap, int c0, int c1, uint32_t mbar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(tmap), "r"(mbar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+// completion of all prior MMAs of this thread arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_nctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void ld_global_v8(const float *p, float *v)
+{
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
+}
+
 struct Item { int p, ks, mt, nt; };
 
-__device__ __forceinline__ Item decode_item(const GemmArgs &a, int item)
+// item -> (problem, k-slice, m-tile of THIS CTA, n-tile); the c CTAs of a cluster get c consecutive m-tiles of the same
+// (k-slice, n-tile), possibly past the last one (then the tile is all padding: zero operands, no stores)
+__device__ __forceinline__ Item decode_item(const GemmArgs &a, int item, int rank)
 {
     Item it;
     int p = 0;
@@ -79,8 +113,8 @@ __device__ __forceinline__ Item decode_item(const GemmArgs &a, int item)
     const GemmProblem &g = a.p[p];
     int r = item - g.item0;
     it.p = p;
-    it.nt = r % g.n_tiles; r /= g.n_tiles;      // n-tiles of the same rows run on neighbouring CTAs (A comes out of L2),
-    it.mt = r % g.m_tiles; r /= g.m_tiles;      // then the m-tiles of one k-slice (split-K: B comes out of L2)
+    it.nt = r % g.n_tiles; r /= g.n_tiles;      // n-tiles of the same rows run on neighbouring clusters (A comes out of L2),
+    it.mt = (r % g.m_groups) * a.cluster + rank; r /= g.m_groups;   // then the m-tiles of one k-slice (split-K: B comes out of L2)
     it.ks = r;
     return it;
 }
@@ -91,7 +125,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const uint32_t s_base = smem_u32(smem);
     const int ring_bytes = a.stages * a.stage_bytes;
-    float *scratch_all = reinterpret_cast<float *>(smem + ring_bytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ring_bytes + kScratchBytes);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 4);
     const uint32_t bar0 = smem_u32(bars);
@@ -101,11 +134,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
     auto bar_tfull = [&](int b) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + b); };
     auto bar_tempty = [&](int b) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 2 + b); };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int csize = a.cluster;
+    const int rank = csize > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = blockIdx.x / csize, num_clusters = gridDim.x / csize;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        // a stage is free when the MMAs of ALL CTAs of the cluster have read it (peers multicast into it)
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), csize); }
         mbar_init(bar_tfull(0), 1); mbar_init(bar_tfull(1), 1);
-        mbar_init(bar_tempty(0), 4); mbar_init(bar_tempty(1), 4);
+        mbar_init(bar_tempty(0), 8); mbar_init(bar_tempty(1), 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -114,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();          // barrier initialisation is visible to the peers before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
@@ -121,14 +160,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
         // =============================================================== TMA producer
         if (lane == 0) {
             uint32_t stage = 0, parity = 1;           // a fresh barrier passes a wait on parity 1
-            for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-                const Item it = decode_item(a, item);
+            for (int item = cluster_id; item < a.total_items; item += num_clusters) {
+                const Item it = decode_item(a, item, rank);
                 const GemmProblem &g = a.p[it.p];
                 const int kb0 = it.ks * g.kb_per_split;
                 int kb1 = kb0 + g.kb_per_split;
                 const int kb_total = (g.k + 63) >> 6;
                 if (kb1 > kb_total) kb1 = kb_total;
                 const int m0 = it.mt * kTileM, n0 = it.nt * g.bn;
+                const int brow = g.b_mn ? rank * (64 / csize) : rank * (g.bn / csize);    // this CTA's slice of the B tile
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(bar_empty(stage), parity);
                     const uint32_t full = bar_full(stage);
@@ -143,14 +183,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
                         tma_load_2d(sa, &g.a_hi, k0, m0, full);
                         if (g.a_lo_on) tma_load_2d(sa + kABytes, &g.a_lo, k0, m0, full);
                     }
-                    if (g.b_mn) {
-                        for (int j = 0; j * 64 < g.bn; ++j) {
-                            tma_load_2d(sb + j * 8192, &g.b_hi, n0 + j * 64, k0, full);
-                            if (g.b_lo_on) tma_load_2d(sb + a.b_off_lo + j * 8192, &g.b_lo, n0 + j * 64, k0, full);
+                    if (csize == 1) {
+                        if (g.b_mn) {
+                            for (int j = 0; j * 64 < g.bn; ++j) {
+                                tma_load_2d(sb + j * 8192, &g.b_hi, n0 + j * 64, k0, full);
+                                if (g.b_lo_on) tma_load_2d(sb + a.b_off_lo + j * 8192, &g.b_lo, n0 + j * 64, k0, full);
+                            }
+                        } else {
+                            tma_load_2d(sb, &g.b_hi, k0, n0, full);
+                            if (g.b_lo_on) tma_load_2d(sb + a.b_off_lo, &g.b_lo, k0, n0, full);
                         }
-                    } else {
-                        tma_load_2d(sb, &g.b_hi, k0, n0, full);
-                        if (g.b_lo_on) tma_load_2d(sb + a.b_off_lo, &g.b_lo, k0, n0, full);
+                    } else if (g.b_mn) {           // 64/c k-rows of every 64-wide atom, multicast to the whole cluster
+                        const uint32_t soff = (uint32_t)brow * 128u;
+                        for (int j = 0; j * 64 < g.bn; ++j) {
+                            tma_load_2d_mc(sb + j * 8192 + soff, &g.b_hi, n0 + j * 64, k0 + brow, full, cmask);
+                            if (g.b_lo_on) tma_load_2d_mc(sb + a.b_off_lo + j * 8192 + soff, &g.b_lo, n0 + j * 64, k0 + brow, full, cmask);
+                        }
+                    } else {                       // bn/c rows of the [bn, 64] tile
+                        const uint32_t soff = (uint32_t)brow * 128u;
+                        tma_load_2d_mc(sb + soff, &g.b_hi, k0, n0 + brow, full, cmask);
+                        if (g.b_lo_on) tma_load_2d_mc(sb + a.b_off_lo + soff, &g.b_lo, k0, n0 + brow, full, cmask);
                     }
                     if (++stage == (uint32_t)a.stages) { stage = 0; parity ^= 1u; }
                 }
@@ -162,8 +214,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
             constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO = 1024 B, version 1, SWIZZLE_128B
             auto make_desc = [](uint32_t lo) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi)); return d; };
             uint32_t stage = 0, parity = 0, iter = 0;
-            for (int item = blockIdx.x; item < a.total_items; item += gridDim.x, ++iter) {
-                const Item it = decode_item(a, item);
+            for (int item = cluster_id; item < a.total_items; item += num_clusters, ++iter) {
+                const Item it = decode_item(a, item, rank);
                 const GemmProblem &g = a.p[it.p];
                 const int kb0 = it.ks * g.kb_per_split;
                 int kb1 = kb0 + g.kb_per_split;
@@ -182,7 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(bar_full(stage), parity);
                     tc_fence_after();
-                    const uint32_t sa = s_base + stage * a.stage_bytes, sb = sa + 2 * kABytes;
+                    // (in a cluster the shared-window address carries the CTA rank in its upper bits: only the low 18 bits
+                    // are the matrix start address, anything above would spill into the descriptor's LBO field)
+                    const uint32_t sa = (s_base & 0x3FFFFu) + stage * a.stage_bytes, sb = sa + 2 * kABytes;
                     const uint32_t a_hi = (sa >> 4) | a_lbo, a_lo = ((sa + kABytes) >> 4) | a_lbo;
                     const uint32_t b_hi = (sb >> 4) | b_lbo, b_lo = ((sb + a.b_off_lo) >> 4) | b_lbo;
 #pragma unroll
@@ -198,72 +252,84 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
 #pragma unroll
                         for (int k16 = 0; k16 < 4; ++k16) umma_bf16(d, make_desc(a_hi + k16 * a_step), make_desc(b_lo + k16 * b_step), idesc, 1u);
                     }
-                    umma_commit(bar_empty(stage));
+                    if (csize == 1) umma_commit(bar_empty(stage));
+                    else umma_commit_mc(bar_empty(stage), cmask);       // frees the stage in every CTA of the cluster
                     if (++stage == (uint32_t)a.stages) { stage = 0; parity ^= 1u; }
                 }
                 umma_commit(bar_tfull(buf));
             }
         }
     } else {
-        // =============================================================== epilogue (warps 2-5; TMEM lane quarter = warp % 4)
-        const int q = warp & 3;
-        float *scratch = scratch_all + (warp - 2) * (32 * 33);
-        const int rq = lane >> 3, cq = (lane & 7) * 4;       // store mapping: 4 rows x 128 B per instruction
+        // =============================================================== epilogue (warps 2-9)
+        // tcgen05.ld gives every lane one row of the tile (TMEM lane quarter = warp % 4); the two warps of a quarter take the
+        // even / odd 32-column chunks.  A thread therefore owns 128 contiguous bytes of a row of C per chunk: four 256-bit
+        // stores (full 32-byte sectors), for the accumulating form four 256-bit loads issued together before them.
+        const int q = warp & 3, half = (warp - 2) >> 2;
         uint32_t iter = 0;
-        for (int item = blockIdx.x; item < a.total_items; item += gridDim.x, ++iter) {
-            const Item it = decode_item(a, item);
+        for (int item = cluster_id; item < a.total_items; item += num_clusters, ++iter) {
+            const Item it = decode_item(a, item, rank);
             const GemmProblem &g = a.p[it.p];
             const uint32_t buf = iter & 1u;
-            const int kb0 = it.ks * g.kb_per_split;
-            const bool empty_slice = kb0 >= ((g.k + 63) >> 6);        // never produced by the host's split; guards a zero-trip MMA loop
-            mbar_wait(bar_tfull(buf), (iter >> 1) & 1u);
+            mbar_wait(bar_tfull(buf), (iter >> 1) & 1u);     // (also for padding tiles: keeps the phase bookkeeping in step)
             tc_fence_after();
             const uint32_t t0 = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
-            const int row0 = it.mt * kTileM + q * 32;
-            const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.c) & 15) == 0);
-            for (int cb = 0; cb * 32 < g.bn; ++cb) {
-                float acc[32];
-                tmem_ld16(t0 + cb * 32, acc);
-                if (cb * 32 + 16 < g.bn) tmem_ld16(t0 + cb * 32 + 16, acc + 16);
-                tmem_ld_wait();
-                const int nbase = it.nt * g.bn + cb * 32;
+            const int m = it.mt * kTileM + q * 32 + lane;
+            const int col0 = it.nt * g.bn;
+            const int ncols = g.n - col0 < g.bn ? g.n - col0 : g.bn;       // valid columns of this n-tile
+            const int mode = g.mode, act = g.act;
+            if (it.mt * kTileM + q * 32 < g.m) {              // else padding rows (ragged last tile / last group): nothing to store
+                const bool row_ok = m < g.m;
+                float *crow = g.c + (size_t)(row_ok ? m : 0) * g.ldc + col0;
+                const bool fast = ((g.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.c) & 31) == 0) && ((col0 & 7) == 0);
+                for (int cb = half; cb * 32 < ncols; cb += 2) {
+                    const int c0 = cb * 32;
+                    const int nvalid = ncols - c0 < 32 ? ncols - c0 : 32;
+                    float acc[32];
+                    tmem_ld16(t0 + c0, acc);
+                    if (c0 + 16 < g.bn) tmem_ld16(t0 + c0 + 16, acc + 16);
+                    else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float v = empty_slice ? 0.f : acc[j];
-                    if (g.mode != 2) {
-                        if (g.bias && nbase + j < g.n) v += __ldg(g.bias + nbase + j);
-                        if (g.act == 1) v = fmaxf(v, 0.f);
-                        else if (g.act == 2) v = tanhf(v);
+                        for (int j = 16; j < 32; ++j) acc[j] = 0.f;
                     }
-                    scratch[lane * 33 + j] = v;
-                }
-                __syncwarp();
-                const int ncol = nbase + cq;
-                const bool col_in_tile = cb * 32 + cq < g.bn;
+                    tmem_ld_wait();
+                    if (mode == 2) {                          // split-K partial sums
+                        if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int rl = rq + 4 * j;
-                    const int m = row0 + rl;
-                    const float *sp = scratch + rl * 33 + cq;
-                    float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
-                    if (m < g.m && col_in_tile && ncol < g.n) {
-                        float *y = g.c + (size_t)m * g.ldc + ncol;
-                        if (g.mode == 2) {
-                            atomicAdd(y, v.x);
-                            if (ncol + 1 < g.n) atomicAdd(y + 1, v.y);
-                            if (ncol + 2 < g.n) atomicAdd(y + 2, v.z);
-                            if (ncol + 3 < g.n) atomicAdd(y + 3, v.w);
-                        } else if (vec_ok && ncol + 4 <= g.n) {
-                            if (g.mode == 1) { const float4 o = *reinterpret_cast<const float4 *>(y); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                            *reinterpret_cast<float4 *>(y) = v;
-                        } else {
-                            const float vv[4] = {v.x, v.y, v.z, v.w};
-                            for (int e = 0; e < 4; ++e)
-                                if (ncol + e < g.n) y[e] = g.mode == 1 ? y[e] + vv[e] : vv[e];
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) atomicAdd(crow + c0 + j, acc[j]);
                         }
+                        continue;
+                    }
+                    if (g.bias) {
+                        const float bv = lane < nvalid ? __ldg(g.bias + col0 + c0 + lane) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] += __shfl_sync(0xffffffffu, bv, j);
+                    }
+                    if (act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+                    } else if (act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = tanhf(acc[j]);
+                    }
+                    if (!row_ok) continue;
+                    float *y = crow + c0;
+                    if (fast && nvalid == 32) {
+                        if (mode == 1) {
+                            float old[32];
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) ld_global_v8(y + 8 * v, old + 8 * v);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] += old[j];
+                        }
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) st_global_v8(y + 8 * v, acc + 8 * v);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) y[j] = mode == 1 ? y[j] + acc[j] : acc[j];
                     }
                 }
-                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -273,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
 
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();          // peers may still multicast into this CTA's shared memory / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -308,16 +375,42 @@ bool make_map(CUtensorMap *map, const void *base, long long rows, long long cols
 
 }  // namespace
 
+// CTAs per cluster for this launch: 2 (4 only when forced) if every problem's B tile can be sliced c ways
+// (K-major B: bn / c rows, a multiple of the 8-row swizzle atom) and little work is padding (m-tile groups are rounded up
+// to c); CN_GEMM_CLUSTER=c overrides (development / A-B timing).
+static int pick_cluster(const GemmArgs &args, int n_problems, int forced)
+{
+    for (int c = forced == 4 ? 4 : 2; c >= 2; c >>= 1) {     // measured: pairs help the weight gradients a little, fours never did
+        if (forced && c != forced) continue;
+        bool ok = true;
+        long long tiles = 0, padded = 0;
+        for (int i = 0; i < n_problems; ++i) {
+            const GemmProblem &g = args.p[i];
+            if (!g.b_mn && (g.bn % (8 * c)) != 0) ok = false;
+            tiles += (long long)g.m_tiles * g.n_tiles;
+            padded += (long long)((g.m_tiles + c - 1) / c) * c * g.n_tiles;
+        }
+        if (ok && (forced || padded * 8 <= tiles * 9)) return c;       // at most 12.5 % padding tiles
+    }
+    return 1;
+}
+
 // returns NULL on success or a static error string (called from c_abi.cu)
 const char *gemm_bf16x3_launch(const CnGemm *problems, int n_problems, cudaStream_t stream, int *items_out)
 {
     static int num_sms = 0;
     static bool attr_set = false;
+    static int forced_cluster = -1;
     if (n_problems < 1 || n_problems > kMaxProblems) return "n_problems out of range";
     if (num_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (forced_cluster < 0) {
+        const char *env = getenv("CN_GEMM_CLUSTER");
+        forced_cluster = env ? atoi(env) : 0;
+        if (forced_cluster != 1 && forced_cluster != 2 && forced_cluster != 4) forced_cluster = 0;
     }
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit + 1024) != cudaSuccess)
@@ -359,22 +452,49 @@ const char *gemm_bf16x3_launch(const CnGemm *problems, int n_problems, cudaStrea
         g.stage_tx = (unsigned)(kABytes * (1 + g.a_lo_on) + b_tile * (1 + g.b_lo_on));
         if (b_tile > max_b_bytes) max_b_bytes = b_tile;
         total_kb_items += (long long)kb_total * g.m_tiles * g.n_tiles;
-        // A: K-major [m, k] box 128 rows; MN-major [k, m] box 64 k-rows.  B likewise with bn rows / 64 k-rows.
+    }
+    const int cluster = forced_cluster == 1 ? 1 : pick_cluster(args, n_problems, forced_cluster);
+    args.cluster = cluster;
+    for (int i = 0; i < n_problems; ++i) {
+        const CnGemm &q = problems[i];
+        GemmProblem &g = args.p[i];
+        // A: K-major [m, k] box 128 rows; MN-major [k, m] box 64 k-rows.  B: this CTA's 1/c slice of the tile -- K-major
+        // [n, k] box bn/c rows; MN-major [k, n] box 64/c k-rows (of every 64-wide atom).
+        const int b_rows = g.b_mn ? 64 / cluster : g.bn / cluster;
         const bool ok = (g.a_mn ? make_map(&g.a_hi, q.a.hi, q.k, q.m, q.a.ld, 64) : make_map(&g.a_hi, q.a.hi, q.m, q.k, q.a.ld, kTileM)) &&
                         (!q.a.lo || (g.a_mn ? make_map(&g.a_lo, q.a.lo, q.k, q.m, q.a.ld, 64) : make_map(&g.a_lo, q.a.lo, q.m, q.k, q.a.ld, kTileM))) &&
-                        (g.b_mn ? make_map(&g.b_hi, q.b.hi, q.k, q.n, q.b.ld, 64) : make_map(&g.b_hi, q.b.hi, q.n, q.k, q.b.ld, bn)) &&
-                        (!q.b.lo || (g.b_mn ? make_map(&g.b_lo, q.b.lo, q.k, q.n, q.b.ld, 64) : make_map(&g.b_lo, q.b.lo, q.n, q.k, q.b.ld, bn)));
+                        (g.b_mn ? make_map(&g.b_hi, q.b.hi, q.k, q.n, q.b.ld, b_rows) : make_map(&g.b_hi, q.b.hi, q.n, q.k, q.b.ld, b_rows)) &&
+                        (!q.b.lo || (g.b_mn ? make_map(&g.b_lo, q.b.lo, q.k, q.n, q.b.ld, b_rows) : make_map(&g.b_lo, q.b.lo, q.n, q.k, q.b.ld, b_rows)));
         if (!ok) return "cuTensorMapEncodeTiled failed (driver entry point missing, or an operand it cannot describe)";
+        g.m_groups = (g.m_tiles + cluster - 1) / cluster;
+        g.b_slice_bytes = b_rows * 128;
     }
-    // split-K "auto" (0): cut the k range so that the launch has about two items per SM, shared out in proportion to the work
+    int max_clusters = num_sms / cluster;
+    if (cluster > 1) {      // clusters that can be co-resident (GPC boundaries): a persistent grid larger than that runs in two waves
+        static int active[5] = {0, 0, 0, 0, 0};
+        if (active[cluster] == 0) {
+            cudaLaunchConfig_t probe = {};
+            probe.gridDim = dim3((unsigned)num_sms / cluster * cluster); probe.blockDim = dim3(kThreads);
+            probe.dynamicSmemBytes = kSmemLimit + 1024;
+            cudaLaunchAttribute pa[1];
+            pa[0].id = cudaLaunchAttributeClusterDimension;
+            pa[0].val.clusterDim.x = (unsigned)cluster; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+            probe.attrs = pa; probe.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_bf16x3_kernel, &probe) != cudaSuccess || n < 1) n = num_sms / cluster;
+            active[cluster] = n;
+        }
+        if (active[cluster] < max_clusters) max_clusters = active[cluster];
+    }
+    // split-K "auto" (0): cut the k range so that the launch has about two items per cluster, shared out in proportion to the work
     int item0 = 0;
     for (int i = 0; i < n_problems; ++i) {
         GemmProblem &g = args.p[i];
         const int kb_total = (g.k + 63) >> 6;
         if (g.split_k == 0) {
-            const long long tiles = (long long)g.m_tiles * g.n_tiles;
-            const double share = (double)kb_total * tiles / (double)total_kb_items;
-            int split = (int)(share * 2.0 * num_sms / (double)tiles + 0.5);
+            const long long tiles = (long long)g.m_groups * g.n_tiles;
+            const double share = (double)kb_total * g.m_tiles * g.n_tiles / (double)total_kb_items;
+            int split = (int)(share * 2.0 * max_clusters / (double)tiles + 0.5);
             if (split < 1) split = 1;
             if (split > kb_total) split = kb_total;
             g.split_k = split;
@@ -382,7 +502,7 @@ const char *gemm_bf16x3_launch(const CnGemm *problems, int n_problems, cudaStrea
         g.kb_per_split = (kb_total + g.split_k - 1) / g.split_k;
         g.split_k = (kb_total + g.kb_per_split - 1) / g.kb_per_split;     // no empty slices
         g.item0 = item0;
-        g.items = g.split_k * g.m_tiles * g.n_tiles;
+        g.items = g.split_k * g.m_groups * g.n_tiles;
         item0 += g.items;
     }
     args.n_problems = n_problems;
@@ -394,9 +514,18 @@ const char *gemm_bf16x3_launch(const CnGemm *problems, int n_problems, cudaStrea
     if (stages < 2) return "tile does not fit two pipeline stages";
     args.stages = stages;
     const int smem = stages * args.stage_bytes + kScratchBytes + 256 + 1024;
-    const int grid = args.total_items < num_sms ? args.total_items : num_sms;
-    gemm_bf16x3_kernel<<<grid, kThreads, smem, stream>>>(args);
+    const int clusters = args.total_items < max_clusters ? args.total_items : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * cluster));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel, args);
     if (items_out) *items_out = args.total_items;
-    const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }

@@ -34,7 +34,7 @@ def test_gemm_kmajor_forward_linear(m, n, k, act):
     native.gemm([dict(a=native.split(x), b=native.split(w), c=y, bias=b, act=act)])
     want = x.double() @ w.double().t() + b.double()
     want = torch.relu(want) if act == 1 else torch.tanh(want) if act == 2 else want
-    _check(y, want)
+    _check(y, want, tol=5e-5)
 
 
 @pytest.mark.parametrize("m,n,k", [(256, 256, 768), (77, 64, 768), (513, 128, 384), (130, 200, 72)])
@@ -83,7 +83,7 @@ def test_gemm_grouped_problems_and_single_pass_operands():
 
 
 def test_gemm_refuses_bad_arguments():
-    x, w = native.split(_rand(64, 64)), native.split(_rand(64, 64))
+    x, w = native.split(_rand(64, 256)), native.split(_rand(64, 256))
     c = torch.empty(64, 64, device=DEV)
     with pytest.raises(Exception):
         native.gemm([dict(a=x, b=w, c=c, bias=_rand(64), split_k=2)])        # split-K cannot carry a bias
@@ -99,6 +99,8 @@ def test_native_linear_autograd_matches_torch(act):
     x = _rand(700, 256, seed=20).requires_grad_(True)
     y = native.linear(x, lin, act)
     gy = _rand(700, 64, seed=21)
+    if act == "relu":            # no gradient through outputs so close to the kink that fp32 and fp64 may disagree on the side
+        gy = gy * (torch.nn.functional.linear(x, lin.weight, lin.bias).abs() > 1e-3)
     y.backward(gy)
     got = (y.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
     x.grad = None

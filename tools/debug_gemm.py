@@ -53,6 +53,28 @@ def main():
             native.gemm([dict(a=native.split(dy), a_mn=True, b=native.split(x), b_mn=True, c=c, split_k=split)])
             torch.cuda.synchronize()
             report("MN-major x MN-major rows %d -> %dx%d split %d" % (rows, m, n, split), c, dy.double().t() @ x.double())
+    if which == "mc":           # multicast debugging: B MN-major, two row tiles, various atom / k-block counts
+        for m, n, k in ((256, 64, 64), (256, 128, 64), (256, 256, 64), (256, 256, 128), (256, 192, 64), (512, 256, 64)):
+            x = rand(m, k, seed=3)
+            w = torch.arange(k, device=DEV, dtype=torch.float32).view(k, 1) * 0 + torch.arange(n, device=DEV, dtype=torch.float32).view(1, n) / 16 + 1
+            w = w + torch.arange(k, device=DEV, dtype=torch.float32).view(k, 1) / 64
+            y = torch.full((m, n), float("nan"), device=DEV)
+            native.gemm([dict(a=native.split(x), b=native.split(w), b_mn=True, c=y)])
+            torch.cuda.synchronize()
+            report("mc K-major x MN-major %dx%dx%d" % (m, n, k), y, x.double() @ w.double())
+            # which B element would explain row 128? solve per column with one-hot A rows
+            eye = torch.zeros(m, k, device=DEV)
+            eye[128:128 + min(k, 128), :] = torch.eye(k, device=DEV)[:min(k, 128)]
+            y2 = torch.full((m, n), float("nan"), device=DEV)
+            native.gemm([dict(a=native.split(eye), b=native.split(w), b_mn=True, c=y2)])
+            torch.cuda.synchronize()
+            got = y2[128:128 + min(k, 128)]            # should equal w[:k]
+            bad = (got - w[:got.shape[0]]).abs() > 1e-3
+            print("   one-hot probe: %d bad of %d; bad k rows %s ; bad n cols %s" % (int(bad.sum()), bad.numel(),
+                  sorted(set(torch.nonzero(bad)[:, 0].tolist()))[:40], sorted(set((torch.nonzero(bad)[:, 1] // 16).tolist()))), flush=True)
+            if bad.any():
+                r, c = [int(v) for v in torch.nonzero(bad)[0]]
+                print("   e.g. B[k=%d, n=%d]: got %g want %g" % (r, c, got[r, c].item(), w[r, c].item()), flush=True)
     if which in ("all", "mnk"):
         for rows, m, n in ((64, 128, 64), (1000, 384, 128)):
             dy, x = rand(rows, m, seed=7), rand(n, rows, seed=8)
