@@ -467,3 +467,38 @@ extern "C" int cn_dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num
     if (msg) return fail(CN_ERR_CUDA, "dsrnn_edge_sequence_step: %s", msg);
     return CN_OK;
 }
+
+extern "C" int cn_launch_attention_train_forward(const float *o, const float *qt, const float *cst, float *c, float *alpha, float scale,
+                                                 int B, int H, cudaStream_t stream);
+extern "C" int cn_launch_attention_train_backward(const float *o, const float *qt, const float *alpha, const float *dc, float *d_o,
+                                                  float *d_qt, float *d_cst, float scale, int B, int H, cudaStream_t stream);
+
+extern "C" int cn_attention_train_forward(const float *o, const float *qt, const float *cst, float *c, float *alpha, float scale,
+                                          int batch, int human_num, void *stream)
+{
+    if (!o || !qt || !c || !alpha) return fail(CN_ERR_ARG, "cn_attention_train_forward: NULL pointer");
+    const int rc = cn_launch_attention_train_forward(o, qt, cst, c, alpha, scale, batch, human_num, (cudaStream_t)stream);
+    if (rc == -1) return fail(CN_ERR_ARG, "cn_attention_train_forward: batch %d / human_num %d (1..32) / 16-byte alignment", batch, human_num);
+    if (rc != 0) return fail(CN_ERR_CUDA, "attention_train_forward_kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    return CN_OK;
+}
+
+extern "C" int cn_attention_train_backward(const float *o, const float *qt, const float *alpha, const float *dc, float *d_o, float *d_qt,
+                                           float *d_cst, float scale, int batch, int human_num, void *stream)
+{
+    if (!o || !qt || !alpha || !dc || !d_o || !d_qt) return fail(CN_ERR_ARG, "cn_attention_train_backward: NULL pointer");
+    const int rc = cn_launch_attention_train_backward(o, qt, alpha, dc, d_o, d_qt, d_cst, scale, batch, human_num, (cudaStream_t)stream);
+    if (rc == -1) return fail(CN_ERR_ARG, "cn_attention_train_backward: batch %d / human_num %d (1..32) / 16-byte alignment", batch, human_num);
+    if (rc != 0) return fail(CN_ERR_CUDA, "attention_train_backward_kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    return CN_OK;
+}
+
+void gemm_bf16x3_enable_timing(int enable);
+float gemm_bf16x3_time_ms(int *launches, double *flops);
+extern "C" int cn_gemm_enable_timing(int enable) { gemm_bf16x3_enable_timing(enable); return CN_OK; }
+extern "C" int cn_gemm_time_ms(float *ms, int *launches, double *flops)
+{
+    if (!ms) return fail(CN_ERR_ARG, "cn_gemm_time_ms: ms is NULL");
+    *ms = gemm_bf16x3_time_ms(launches, flops);
+    return CN_OK;
+}

@@ -147,7 +147,7 @@ struct EdgeTcArgs {
     long long in_off_s, in_off_t, out_off_s, out_off_t;
     float *ws;                         // [rows, 4, 256] r | z | n | W_hn hm + b_hn
     __nv_bfloat16 *hm_hi, *hm_lo;      // [rows, 256] masked previous state
-    __nv_bfloat16 *e_hi, *e_lo;        // [rows, 64] encoded input
+    __nv_bfloat16 *e_hi, *e_lo;        // [rows, 72] encoded input | 1 | 0 x 7
 };
 
 struct TileInfo { bool spatial; int p, row0, M; };
@@ -398,8 +398,14 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                         if (a.three_pass) *reinterpret_cast<uint32_t *>(smem + kOffALo + off) = lo;
                         if (kTrain && okb) {      // operand of dW_ih = dgi^T e (128 contiguous bytes per row and warp)
                             const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
-                            reinterpret_cast<uint32_t *>(a.e_hi + orow * 64)[lane] = hi;
-                            reinterpret_cast<uint32_t *>(a.e_lo + orow * 64)[lane] = lo;
+                            // rows of 72: 64 values, then a constant 1 (and 7 zeros) -- the "ones column" that makes the
+                            // weight-gradient product G^T [e | 1] also return the column sums of G (the bias gradients)
+                            reinterpret_cast<uint32_t *>(a.e_hi + orow * 72)[lane] = hi;
+                            reinterpret_cast<uint32_t *>(a.e_lo + orow * 72)[lane] = lo;
+                            if (lane == 0) {
+                                *reinterpret_cast<uint4 *>(a.e_hi + orow * 72 + 64) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+                                *reinterpret_cast<uint4 *>(a.e_lo + orow * 72 + 64) = make_uint4(0u, 0u, 0u, 0u);
+                            }
                         }
                     }
                     fence_proxy_async();

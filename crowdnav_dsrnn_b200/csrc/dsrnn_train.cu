@@ -166,6 +166,87 @@ split_bf16_kernel(const float *__restrict__ a, __nv_bfloat16 *__restrict__ hi, _
     st4_split(hi + 4 * i, lo + 4 * i, ld4(a + 4 * i));
 }
 
+// ------------------------------------------------------------------------------------------------ attention (training)
+// EdgeAttention over a [B = T*n] batch (srnn_model.py:256-339) with the key projection folded into the query:
+//   s_i = (o_i . qt + cst) * scale,  alpha = softmax_i(s),  c = sum_i alpha_i o_i          (qt = W_s^T q, cst = q . b_s)
+// One warp per sample; lane l owns hidden units [4l, 4l+4) and [128 + 4l, 128 + 4l + 4) (two coalesced float4 per row).
+// HBM-bound: the forward reads o once (H KB per sample) and writes c and alpha; the backward reads o (twice, the second
+// time out of L1/L2), dc, qt, alpha and writes d_o (H KB) and d_qt.
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float dot8(const float4 &a0, const float4 &a1, const float4 &b0, const float4 &b1)
+{
+    return a0.x * b0.x + a0.y * b0.y + a0.z * b0.z + a0.w * b0.w + a1.x * b1.x + a1.y * b1.y + a1.z * b1.z + a1.w * b1.w;
+}
+
+__global__ void __launch_bounds__(128)
+attention_train_forward_kernel(const float *__restrict__ o, const float *__restrict__ qt, const float *__restrict__ cst,
+                               float *__restrict__ c, float *__restrict__ alpha, float scale, int B, int H)
+{
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const float4 *q4 = reinterpret_cast<const float4 *>(qt + (size_t)b * 256);
+    const float4 q0 = q4[lane], q1 = q4[32 + lane];
+    const float k = cst ? cst[b] : 0.f;
+    const float4 *orow = reinterpret_cast<const float4 *>(o + (size_t)b * H * 256);
+    float my_s = -INFINITY;                  // lane i keeps s_i
+    float run_max = -INFINITY, run_sum = 0.f;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int i = 0; i < H; ++i) {
+        const float4 v0 = orow[i * 64 + lane], v1 = orow[i * 64 + 32 + lane];
+        const float s = (warp_sum(dot8(v0, v1, q0, q1)) + k) * scale;
+        if (lane == i) my_s = s;
+        const float m = fmaxf(run_max, s);
+        const float f = __expf(run_max - m), w = __expf(s - m);      // online softmax: rescale what was accumulated so far
+        run_sum = run_sum * f + w;
+        a0.x = a0.x * f + w * v0.x; a0.y = a0.y * f + w * v0.y; a0.z = a0.z * f + w * v0.z; a0.w = a0.w * f + w * v0.w;
+        a1.x = a1.x * f + w * v1.x; a1.y = a1.y * f + w * v1.y; a1.z = a1.z * f + w * v1.z; a1.w = a1.w * f + w * v1.w;
+        run_max = m;
+    }
+    const float inv = 1.0f / run_sum;
+    float4 *c4 = reinterpret_cast<float4 *>(c + (size_t)b * 256);
+    c4[lane] = make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv);
+    c4[32 + lane] = make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv);
+    if (lane < H) alpha[(size_t)b * H + lane] = __expf(my_s - run_max) * inv;
+}
+
+__global__ void __launch_bounds__(128)
+attention_train_backward_kernel(const float *__restrict__ o, const float *__restrict__ qt, const float *__restrict__ alpha,
+                                const float *__restrict__ dc, float *__restrict__ d_o, float *__restrict__ d_qt,
+                                float *__restrict__ d_cst, float scale, int B, int H)
+{
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const float4 *q4 = reinterpret_cast<const float4 *>(qt + (size_t)b * 256), *g4 = reinterpret_cast<const float4 *>(dc + (size_t)b * 256);
+    const float4 q0 = q4[lane], q1 = q4[32 + lane], g0 = g4[lane], g1 = g4[32 + lane];
+    const float4 *orow = reinterpret_cast<const float4 *>(o + (size_t)b * H * 256);
+    const float al = lane < H ? alpha[(size_t)b * H + lane] : 0.f;
+    float da = 0.f;                          // lane i: o_i . dc
+    for (int i = 0; i < H; ++i) {
+        const float d = warp_sum(dot8(orow[i * 64 + lane], orow[i * 64 + 32 + lane], g0, g1));
+        if (lane == i) da = d;
+    }
+    const float dot = warp_sum(al * da);
+    const float ds = al * (da - dot) * scale;            // dL/d(o_i . qt + cst), lane i
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+    float4 *drow = reinterpret_cast<float4 *>(d_o + (size_t)b * H * 256);
+    for (int i = 0; i < H; ++i) {
+        const float a_i = __shfl_sync(0xffffffffu, al, i), s_i = __shfl_sync(0xffffffffu, ds, i);
+        const float4 v0 = orow[i * 64 + lane], v1 = orow[i * 64 + 32 + lane];
+        drow[i * 64 + lane] = make_float4(a_i * g0.x + s_i * q0.x, a_i * g0.y + s_i * q0.y, a_i * g0.z + s_i * q0.z, a_i * g0.w + s_i * q0.w);
+        drow[i * 64 + 32 + lane] = make_float4(a_i * g1.x + s_i * q1.x, a_i * g1.y + s_i * q1.y, a_i * g1.z + s_i * q1.z, a_i * g1.w + s_i * q1.w);
+        t0.x += s_i * v0.x; t0.y += s_i * v0.y; t0.z += s_i * v0.z; t0.w += s_i * v0.w;
+        t1.x += s_i * v1.x; t1.y += s_i * v1.y; t1.z += s_i * v1.z; t1.w += s_i * v1.w;
+    }
+    float4 *dq4 = reinterpret_cast<float4 *>(d_qt + (size_t)b * 256);
+    dq4[lane] = t0; dq4[32 + lane] = t1;
+    if (d_cst) { const float tot = warp_sum(ds); if (lane == 0) d_cst[b] = tot; }
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
@@ -222,5 +303,21 @@ extern "C" int cn_launch_gru_gates_backward_pairs(const float *grad_h, float *d,
     const size_t n = (size_t)R * (hid >> 2);
     gru_gates_backward_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_h, d, d_live, m_next, ws, h_prev, m_cur,
         static_cast<__nv_bfloat16 *>(g_hi), static_cast<__nv_bfloat16 *>(g_lo), R, hid);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cn_launch_attention_train_forward(const float *o, const float *qt, const float *cst, float *c, float *alpha, float scale,
+                                                 int B, int H, cudaStream_t stream)
+{
+    if (B < 1 || H < 1 || H > 32 || !aligned16(o) || !aligned16(qt) || !aligned16(c)) return -1;
+    attention_train_forward_kernel<<<(B + 3) / 4, 128, 0, stream>>>(o, qt, cst, c, alpha, scale, B, H);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cn_launch_attention_train_backward(const float *o, const float *qt, const float *alpha, const float *dc, float *d_o,
+                                                  float *d_qt, float *d_cst, float scale, int B, int H, cudaStream_t stream)
+{
+    if (B < 1 || H < 1 || H > 32 || !aligned16(o) || !aligned16(qt) || !aligned16(dc) || !aligned16(d_o) || !aligned16(d_qt)) return -1;
+    attention_train_backward_kernel<<<(B + 3) / 4, 128, 0, stream>>>(o, qt, alpha, dc, d_o, d_qt, d_cst, scale, B, H);
     return (int)cudaGetLastError();
 }

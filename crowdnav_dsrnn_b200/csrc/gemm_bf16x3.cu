@@ -36,6 +36,9 @@
 
 using namespace tc;
 
+void gemm_bf16x3_enable_timing(int enable);
+float gemm_bf16x3_time_ms(int *launches, double *flops);
+
 namespace {
 
 constexpr int kMaxProblems = CN_GEMM_MAX_PROBLEMS;
@@ -395,6 +398,40 @@ static int pick_cluster(const GemmArgs &args, int n_problems, int forced)
     return 1;
 }
 
+// optional device timing of every launch (bench.py's roofline): CUDA events on the launching stream, drained by
+// gemm_bf16x3_time_ms
+#include <vector>
+namespace {
+struct GemmTimer {
+    bool enabled = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;
+    double flops = 0.0;
+} g_timer;
+}
+
+void gemm_bf16x3_enable_timing(int enable)
+{
+    gemm_bf16x3_time_ms(nullptr, nullptr);
+    g_timer.enabled = enable != 0;
+}
+
+float gemm_bf16x3_time_ms(int *launches, double *flops)
+{
+    float total = 0.f;
+    for (auto &p : g_timer.pending) {
+        cudaEventSynchronize(p.second);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.first, p.second);
+        total += ms;
+        g_timer.pool.push_back(p);
+    }
+    if (launches) *launches = (int)g_timer.pending.size();
+    if (flops) *flops = g_timer.flops;
+    g_timer.pending.clear();
+    g_timer.flops = 0.0;
+    return total;
+}
+
 // returns NULL on success or a static error string (called from c_abi.cu)
 const char *gemm_bf16x3_launch(const CnGemm *problems, int n_problems, cudaStream_t stream, int *items_out)
 {
@@ -525,7 +562,16 @@ const char *gemm_bf16x3_launch(const CnGemm *problems, int n_problems, cudaStrea
     attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (g_timer.enabled) {
+        std::pair<cudaEvent_t, cudaEvent_t> p;
+        if (!g_timer.pool.empty()) { p = g_timer.pool.back(); g_timer.pool.pop_back(); }
+        else { cudaEventCreate(&p.first); cudaEventCreate(&p.second); }
+        cudaEventRecord(p.first, stream);
+        g_timer.pending.push_back(p);
+        for (int i = 0; i < n_problems; ++i) g_timer.flops += 2.0 * problems[i].m * (double)problems[i].n * problems[i].k;
+    }
     const cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel, args);
+    if (g_timer.enabled) cudaEventRecord(g_timer.pending.back().second, stream);
     if (items_out) *items_out = args.total_items;
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }

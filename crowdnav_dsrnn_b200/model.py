@@ -579,14 +579,13 @@ class Policy(nn.Module):
         es, et = b.humanhumanEdgeRNN_spatial, b.humanhumanEdgeRNN_temporal
         edge_params = [p for m in (es, et) for p in (m.encoder_linear.weight, m.encoder_linear.bias, m.gru.weight_ih_l0,
                                                      m.gru.weight_hh_l0, m.gru.bias_ih_l0, m.gru.bias_hh_l0)]
-        hs = native.EdgeGruSequence.apply(self, se.reshape(T, S, 2), inputs["temporal_edges"].reshape(T, N, 2), h0, mk, *edge_params)
-        o_s, o_t = hs[:T * S].view(T, S, 256), hs[T * S:].view(T, N, 256)
+        o_s, o_t = native.EdgeGruSequence.apply(self, se.reshape(T, S, 2), inputs["temporal_edges"].reshape(T, N, 2), h0, mk, *edge_params)
+        o_s, o_t = o_s.view(T, S, 256), o_t.view(T, N, 256)
         o_t2, o_s3 = o_t.reshape(T * N, 256), o_s.view(T * N, H, 256)
         q = native.linear(o_t2, b.attn.temporal_edge_layer[0])                                   # [TN, 64]
         qt = native.matmul_nt(q, b.attn.spatial_edge_layer[0].weight.t())                        # [TN, 256] = q W_s
-        const = (q * b.attn.spatial_edge_layer[0].bias).sum(-1, keepdim=True)                    # q.b_s (no effect on the softmax)
-        alpha = torch.softmax((torch.bmm(o_s3, qt.unsqueeze(-1)).squeeze(-1) + const) * (H / math.sqrt(64.0)), dim=-1)
-        c = torch.bmm(alpha.unsqueeze(1), o_s3).squeeze(1)
+        const = (q * b.attn.spatial_edge_layer[0].bias).sum(-1)                                  # q.b_s (no effect on the softmax)
+        c = native.AttentionMix.apply(o_s3, qt, const, H / math.sqrt(64.0))
         enc = torch.relu(b.humanNodeRNN.encoder_linear(b.robot_linear(rn)))                      # K = 7 / 3: CUDA cores
         emb = native.linear(torch.cat([o_t2, c], -1), b.humanNodeRNN.edge_attention_embed, "relu")
         prev, SEQUENCE_GEMM = SEQUENCE_GEMM, "native"

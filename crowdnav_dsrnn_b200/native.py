@@ -164,11 +164,45 @@ def matmul_nt(x, w):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+class AttentionMix(torch.autograd.Function):
+    """c = sum_i softmax_i((o_i . qt + cst) * scale) o_i over a batch (srnn_model.py:256-339 with the key projection folded
+    into the query); forward and backward are one HBM-bound pass over o each (csrc/dsrnn_train.cu)."""
+
+    @staticmethod
+    def forward(ctx, o, qt, cst, scale):
+        o, qt, cst = o.contiguous(), qt.contiguous(), cst.contiguous()
+        B, H = o.shape[0], o.shape[1]
+        c = torch.empty(B, 256, dtype=torch.float32, device=o.device)
+        alpha = torch.empty(B, H, dtype=torch.float32, device=o.device)
+        with _on_device(o.device):
+            _lib.check(_lib.load().cn_attention_train_forward(_ptr(o), _ptr(qt), _ptr(cst), _ptr(c), _ptr(alpha), float(scale), B, H,
+                                                              _stream(o.device)), "cn_attention_train_forward")
+        COUNTERS["kernel_launches"] += 1
+        ctx.scale = float(scale)
+        ctx.save_for_backward(o, qt, alpha)
+        return c
+
+    @staticmethod
+    def backward(ctx, dc):
+        o, qt, alpha = ctx.saved_tensors
+        B, H = o.shape[0], o.shape[1]
+        dc = dc.contiguous()
+        d_o, d_qt = torch.empty_like(o), torch.empty_like(qt)
+        d_cst = torch.empty(B, dtype=torch.float32, device=o.device)
+        with _on_device(o.device):
+            _lib.check(_lib.load().cn_attention_train_backward(_ptr(o), _ptr(qt), _ptr(alpha), _ptr(dc), _ptr(d_o), _ptr(d_qt), _ptr(d_cst),
+                                                               ctx.scale, B, H, _stream(o.device)), "cn_attention_train_backward")
+        COUNTERS["kernel_launches"] += 1
+        return d_o, d_qt, d_cst, None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 class EdgeGruSequence(torch.autograd.Function):
     """Both edge GRUs of the DS-RNN over a [T, n] chunk.
 
     forward(policy, se [T, S, 2], te [T, n, 2], h0 [S + n, 256] (spatial rows, then temporal rows), masks [T, n],
-            12 parameters) -> hs [T*S + T*n, 256] in the sequence layout (spatial rows of all steps, then temporal rows).
+            12 parameters) -> (o_s [T*S, 256], o_t [T*n, 256]): the two halves of ONE buffer in the sequence layout (spatial
+            rows of all steps, then temporal rows), returned separately so that their gradients arrive separately.
     """
 
     @staticmethod
@@ -184,7 +218,7 @@ class EdgeGruSequence(torch.autograd.Function):
         hs = torch.empty(rows, 256, **f32)
         ws = torch.empty(rows, 1024, **f32)
         hm_hi, hm_lo = torch.empty(rows, 256, dtype=BF16, device=dev), torch.empty(rows, 256, dtype=BF16, device=dev)
-        e_hi, e_lo = torch.empty(rows, 64, dtype=BF16, device=dev), torch.empty(rows, 64, dtype=BF16, device=dev)
+        e_hi, e_lo = torch.empty(rows, 72, dtype=BF16, device=dev), torch.empty(rows, 72, dtype=BF16, device=dev)   # [e | 1 | 0 x 7]
         se, te, h0, masks = se.contiguous(), te.contiguous(), h0.contiguous(), masks.contiguous()
         stream = _stream(dev)
         io = abi.CnEdgeSeqStep()
@@ -200,10 +234,10 @@ class EdgeGruSequence(torch.autograd.Function):
         COUNTERS["kernel_launches"] += T
         ctx.dims = (T, S, n, H)
         ctx.save_for_backward(se, te, h0, masks, hs, ws, hm_hi, hm_lo, e_hi, e_lo, s_w_ih, s_w_hh, t_w_ih, t_w_hh)
-        return hs
+        return hs[:T * S], hs[T * S:]
 
     @staticmethod
-    def backward(ctx, grad_hs):
+    def backward(ctx, grad_os, grad_ot):
         se, te, h0, masks, hs, ws, hm_hi, hm_lo, e_hi, e_lo, s_w_ih, s_w_hh, t_w_ih, t_w_hh = ctx.saved_tensors
         T, S, n, H = ctx.dims
         dev = hs.device
@@ -211,21 +245,23 @@ class EdgeGruSequence(torch.autograd.Function):
         stream = _stream(dev)
         rows = T * (S + n)
         TS = T * S
-        grad_hs = grad_hs.contiguous()
+        zeros = lambda r: torch.zeros(r, 256, dtype=torch.float32, device=dev)
+        grad_seg = ((zeros(TS) if grad_os is None else grad_os.contiguous()), (zeros(rows - TS) if grad_ot is None else grad_ot.contiguous()))
         g_hi = torch.empty(rows, 1024, dtype=BF16, device=dev)
         g_lo = torch.empty(rows, 1024, dtype=BF16, device=dev)
         d = torch.empty(S + n, 256, dtype=torch.float32, device=dev)        # dL/d(masked state of the step), spatial | temporal rows
         m_sp = masks.view(T, n, 1).expand(T, n, H).reshape(T, S).contiguous()   # per-row masks of the spatial rows
         whh_s, whh_t = split(s_w_hh), split(t_w_hh)                         # [768, 256] = [K, N]: MN-major B of d += G[:, 256:] W_hh
-        seg = ((0, 0, S, m_sp, whh_s), (TS, S, n, masks, whh_t))            # (first row in the sequence layout, first row in d / h0, rows per step, masks, W_hh)
+        # (first row in the sequence layout, first row in d / h0, rows per step, masks, W_hh, incoming gradient)
+        seg = ((0, 0, S, m_sp, whh_s, grad_seg[0]), (TS, S, n, masks, whh_t, grad_seg[1]))
         for t in range(T - 1, -1, -1):
             probs = []
             live = 1 if t + 1 < T else 0
-            for base, doff, R, mk, whh in seg:
+            for base, doff, R, mk, whh, gseg in seg:
                 lo_, hi_ = base + t * R, base + (t + 1) * R
                 hprev = h0[doff:doff + R] if t == 0 else hs[lo_ - R:lo_]
                 dseg = d[doff:doff + R]
-                _lib.check(lib.cn_gru_gates_backward_pairs(_ptr(grad_hs[lo_:hi_]), _ptr(dseg), live, _ptr(mk[t + 1]) if live else None,
+                _lib.check(lib.cn_gru_gates_backward_pairs(_ptr(gseg[t * R:(t + 1) * R]), _ptr(dseg), live, _ptr(mk[t + 1]) if live else None,
                                                            _ptr(ws[lo_:hi_]), _ptr(hprev), _ptr(mk[t]), _ptr(g_hi[lo_:hi_]),
                                                            _ptr(g_lo[lo_:hi_]), R, 256, stream), "cn_gru_gates_backward_pairs")
                 probs.append(dict(a=(g_hi[lo_:hi_, 256:], g_lo[lo_:hi_, 256:]), b=whh, b_mn=True, c=dseg, accumulate=True))
@@ -240,17 +276,18 @@ class EdgeGruSequence(torch.autograd.Function):
         de = torch.empty(rows, 64, dtype=torch.float32, device=dev)
         gemm([dict(a=(gs[0][:, :768], gs[1][:, :768]), b=split(perm(s_w_ih)), b_mn=True, c=de[:TS]),
               dict(a=(gt[0][:, :768], gt[1][:, :768]), b=split(perm(t_w_ih)), b_mn=True, c=de[TS:])])
-        dw = torch.zeros(2, 768, 320, dtype=torch.float32, device=dev)       # [:, :, :256] dW_hh, [:, :, 256:] dW_ih (rows n|r|z)
-        gemm([dict(a=(gs[0][:, 256:], gs[1][:, 256:]), a_mn=True, b=(hm_hi[:TS], hm_lo[:TS]), b_mn=True, c=dw[0, :, :256], split_k=0),
-              dict(a=(gt[0][:, 256:], gt[1][:, 256:]), a_mn=True, b=(hm_hi[TS:], hm_lo[TS:]), b_mn=True, c=dw[1, :, :256], split_k=0),
-              dict(a=(gs[0][:, :768], gs[1][:, :768]), a_mn=True, b=(e_hi[:TS], e_lo[:TS]), b_mn=True, c=dw[0, :, 256:], split_k=0),
-              dict(a=(gt[0][:, :768], gt[1][:, :768]), a_mn=True, b=(e_hi[TS:], e_lo[TS:]), b_mn=True, c=dw[1, :, 256:], split_k=0)])
+        dwh = torch.zeros(2, 768, 256, dtype=torch.float32, device=dev)      # dW_hh
+        dwx = torch.zeros(2, 1024, 72, dtype=torch.float32, device=dev)      # G^T [e | 1]: [:, :768, :64] dW_ih (rows n|r|z), [:, :, 64] column sums of G
+        gemm([dict(a=(gs[0][:, 256:], gs[1][:, 256:]), a_mn=True, b=(hm_hi[:TS], hm_lo[:TS]), b_mn=True, c=dwh[0], split_k=0),
+              dict(a=(gt[0][:, 256:], gt[1][:, 256:]), a_mn=True, b=(hm_hi[TS:], hm_lo[TS:]), b_mn=True, c=dwh[1], split_k=0)])
+        gemm([dict(a=gs, a_mn=True, b=(e_hi[:TS], e_lo[:TS]), b_mn=True, c=dwx[0], split_k=0),
+              dict(a=gt, a_mn=True, b=(e_hi[TS:], e_lo[TS:]), b_mn=True, c=dwx[1], split_k=0)])
         unperm = lambda w: torch.cat([w[256:], w[:256]], 0)                  # n | r | z -> r | z | n
         grads = []
         for k, (x, sl) in enumerate(((se.view(TS, 2), slice(0, TS)), (te.view(T * n, 2), slice(TS, rows)))):
-            colsum = torch.sum(g_hi[sl], 0, dtype=torch.float32) + torch.sum(g_lo[sl], 0, dtype=torch.float32)   # [1024]: n | r | z | nr
+            colsum = dwx[k, :, 64]                                           # [1024]: sums of pn | pr | pz | pn*r over all rows
             db_ih = torch.cat([colsum[256:768], colsum[:256]])
             db_hh = colsum[256:]
-            dem = de[sl] * (e_hi[sl] > 0)                                    # ReLU of the edge encoder
-            grads.append((dem.t() @ x, dem.sum(0), unperm(dw[k, :, 256:]), dw[k, :, :256], db_ih, db_hh))
+            dem = de[sl] * (e_hi[sl, :64] > 0)                               # ReLU of the edge encoder
+            grads.append((dem.t() @ x, dem.sum(0), unperm(dwx[k, :768, :64]), dwh[k], db_ih, db_hh))
         return (None, None, None, grad_h0, None) + grads[0] + grads[1]

@@ -294,7 +294,8 @@ typedef struct CnEdgeSeqStep {
     float *h_out;                  /* [*, 256]  h_t */
     float *ws;                     /* [*, 1024] r | z | n | W_hn hm + b_hn */
     void *hm_hi, *hm_lo;           /* bf16 [*, 256] split masked previous state m_t h_{t-1} (operand of dW_hh) */
-    void *e_hi, *e_lo;             /* bf16 [*, 64]  split encoded input (operand of dW_ih) */
+    void *e_hi, *e_lo;             /* bf16 [*, 72]  split encoded input, then a constant 1 and seven 0: B operand of
+                                      G^T [e | 1] = [dW_ih | column sums of G (bias gradients)] */
 } CnEdgeSeqStep;
 int cn_dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, const CnEdgeSeqStep *io, void *stream);
 
@@ -305,6 +306,15 @@ int cn_dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, const CnE
  *   hm = m_cur[row] * h_prev[row] is the masked state the step started from (h_prev == NULL: zero state). */
 int cn_gru_gates_backward_pairs(const float *grad_h, float *d, int d_live, const float *m_next, const float *ws, const float *h_prev,
                                 const float *m_cur, void *g_hi, void *g_lo, int rows, int hid, void *stream);
+
+/* EdgeAttention of the update over a batch of T*n samples (srnn_model.py:256-339), key projection folded into the query:
+ *   alpha = softmax_i((o_i . qt + cst) * scale), c = sum_i alpha_i o_i;  o [batch, human_num, 256], qt [batch, 256] = W_s^T q,
+ *   cst [batch] = q . b_s (may be NULL), scale = human_num / sqrt(attention_size).  The backward returns d_o, d_qt and
+ *   d_cst (may be NULL) from dc.  fp32, 16-byte aligned, human_num <= 32; HBM-bound (one pass over o forward, one backward). */
+int cn_attention_train_forward(const float *o, const float *qt, const float *cst, float *c, float *alpha, float scale,
+                               int batch, int human_num, void *stream);
+int cn_attention_train_backward(const float *o, const float *qt, const float *alpha, const float *dc, float *d_o, float *d_qt,
+                                float *d_cst, float scale, int batch, int human_num, void *stream);
 
 /* Generic split-bf16 3-pass tensor-core GEMM (tcgen05, TMA-fed, fp32 accumulation in TMEM):
  *   C[m, n] (=, +=, or atomically += for split-K)  (A_hi + A_lo)(B_hi + B_lo) minus the lo*lo term  (+ bias[n], activation).
@@ -329,6 +339,11 @@ typedef struct CnGemm {
                               to C with atomics -- C must hold the initial value (zeros); no bias / activation */
 } CnGemm;
 int cn_gemm_bf16x3(const CnGemm *problems, int n_problems, void *stream);
+/* Optional device timing of every cn_gemm_bf16x3 launch of this process (bench.py's roofline): CUDA events on the launching
+ * stream; cn_gemm_time_ms synchronises them and returns the accumulated milliseconds, launch count and algorithmic FLOPs
+ * (2 m n k per problem) since the last call, and resets them. */
+int cn_gemm_enable_timing(int enable);
+int cn_gemm_time_ms(float *ms, int *launches, double *flops);
 
 #ifdef __cplusplus
 }

@@ -151,9 +151,13 @@ def sequence_impls_agree(dtype, device, tol, impls=("per_step", "batched"), case
     for x, y in list(zip(a[:4], b[:4])) + list(zip(a[5], b[5])):
         assert (x - y).abs().max().item() <= tol * max(1.0, x.abs().max().item())
     assert sorted(a[4]) == sorted(b[4]) and len(a[4]) >= 40
+    bad = []
     for k in a[4]:
         scale = max(a[4][k].abs().max().item(), 1e-3)
-        assert (a[4][k] - b[4][k]).abs().max().item() <= tol * scale, k
+        err = (a[4][k] - b[4][k]).abs().max().item()
+        if not err <= tol * scale:
+            bad.append("%s: err %.3e scale %.3e" % (k, err, scale))
+    assert not bad, bad
 
 
 def test_batched_sequence_forward_equals_per_step_graph_on_cpu():

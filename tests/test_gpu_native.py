@@ -141,3 +141,43 @@ def test_ppo_update_native_matches_reference_golden_on_cuda():
     cpu_policy = _policy()
     cpu_policy.load_state_dict({k: v.detach().cpu() for k, v in policy.state_dict().items()})
     _check_update(g, cpu_policy, before, losses)
+
+
+@pytest.mark.parametrize("B,H", [(3, 1), (130, 5), (1000, 20), (7, 32)])
+def test_attention_mix_matches_torch_autograd(B, H):
+    """cn_attention_train_forward / _backward against softmax attention written with torch ops in float64."""
+    o = _rand(B, H, 256, seed=30).requires_grad_(True)
+    qt = _rand(B, 256, seed=31, scale=0.2).requires_grad_(True)
+    cst = _rand(B, seed=32).requires_grad_(True)
+    scale = H / 8.0
+    c = native.AttentionMix.apply(o, qt, cst, scale)
+    gc = _rand(B, 256, seed=33)
+    c.backward(gc)
+    got = (c.detach(), o.grad.clone(), qt.grad.clone(), cst.grad.clone())
+    od, qd, cd = o.detach().double().requires_grad_(True), qt.detach().double().requires_grad_(True), cst.detach().double().requires_grad_(True)
+    alpha = torch.softmax(((od * qd.unsqueeze(1)).sum(-1) + cd.unsqueeze(1)) * scale, dim=-1)
+    ref = (alpha.unsqueeze(-1) * od).sum(1)
+    g = torch.autograd.grad(ref, (od, qd, cd), gc.double())
+    for a, b in zip(got, (ref.detach(),) + g):
+        assert (a.double() - b).abs().max().item() <= 5e-5 * max(1.0, b.abs().max().item())
+
+
+def test_native_gradients_are_reproducible_across_repeated_passes():
+    """Race detector: the same native forward + backward eight times; every gradient must agree with the first pass up to
+    the order of the split-K atomics (1e-4 of its scale)."""
+    from test_config_host import _sequence_case
+
+    policy, obs, masks, action, h0 = _sequence_case(torch.float32, DEV, n=40, H=20, T=5, seed=3)
+    policy.sequence_impl = "native"
+    first = None
+    for rep in range(8):
+        policy.zero_grad(set_to_none=True)
+        value, logp, _, out = policy.evaluate_actions(obs, {k: v.clone() for k, v in h0.items()}, masks, action)
+        (value.sum() + 0.3 * logp.sum()).backward()
+        grads = {k: q.grad.clone() for k, q in policy.named_parameters() if q.grad is not None}
+        if first is None:
+            first = grads
+            continue
+        bad = ["%s (pass %d): %.3e of %.3e" % (k, rep, (grads[k] - first[k]).abs().max().item(), first[k].abs().max().item())
+               for k in first if (grads[k] - first[k]).abs().max().item() > 1e-4 * max(first[k].abs().max().item(), 1e-3)]
+        assert not bad, bad

@@ -75,6 +75,15 @@ def main():
             if bad.any():
                 r, c = [int(v) for v in torch.nonzero(bad)[0]]
                 print("   e.g. B[k=%d, n=%d]: got %g want %g" % (r, c, got[r, c].item(), w[r, c].item()), flush=True)
+    if which in ("all", "ext"):       # the G^T [e | 1] product of the edge-GRU backward: M = 1024, N = 72 (ld 72)
+        for rows in (42, 210, 5000):
+            gfull, e = rand(rows, 1024, seed=9), rand(rows, 72, seed=10)
+            e[:, 64] = 1.0
+            e[:, 65:] = 0.0
+            c = torch.zeros(1024, 72, device=DEV)
+            native.gemm([dict(a=native.split(gfull), a_mn=True, b=native.split(e), b_mn=True, c=c, split_k=0)])
+            torch.cuda.synchronize()
+            report("G^T [e|1] rows %d -> 1024x72" % rows, c, gfull.double().t() @ e.double())
     if which in ("all", "mnk"):
         for rows, m, n in ((64, 128, 64), (1000, 384, 128)):
             dy, x = rand(rows, m, seed=7), rand(n, rows, seed=8)
