@@ -34,6 +34,9 @@ WORKLOADS = {
                weights="unicycle_55554", label="c2: unicycle, 10 humans, mixed scenarios, dt 0.1, 1024 envs"),
     "c1": dict(human_num=5, envs_per_gpu=16, kinematics="holonomic", over={"sim.train_val_sim": ["circle_crossing"]},
                weights="holonomic_27776", label="c1: reference defaults, 5 humans circle_crossing, 16 envs"),
+    # BASELINE.json configs[4]: PPO training, 65536 envs x 20 humans in total, sharded over the GPUs (strong scaling)
+    "c5": dict(human_num=20, envs_total=65536, kinematics="holonomic", over={}, weights="holonomic_27776", train=True,
+               label="c5: PPO training, 65536 envs x 20 humans in total, T=30, 5 epochs x 2 minibatches, native update"),
 }
 
 
@@ -368,11 +371,169 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ training workload (c5)
+def run_train(args, wl):
+    """One "step" = one PPO update cycle: T = ppo.num_steps rollout steps of every env (CUDA crowd step + DS-RNN forward,
+    device resident), bootstrap value, returns, and the PPO update (5 epochs x 2 minibatches) on the library's native
+    kernels, gradients averaged over the ranks with NCCL.  value = env-steps/s of the whole job."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from crowdnav_dsrnn_b200 import _lib, native
+    from crowdnav_dsrnn_b200.envs import CrowdVecEnv
+    from crowdnav_dsrnn_b200.model import Policy
+    from crowdnav_dsrnn_b200.ppo import PPO
+    from crowdnav_dsrnn_b200.spaces import crowd_spaces
+    from crowdnav_dsrnn_b200.storage import SRNNRolloutStorage
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    total = args.envs_total or wl["envs_total"]
+    N = total // world
+    H = wl["human_num"]
+    cfg = make_config(wl)
+    cfg.training.num_processes = N
+    T = int(cfg.ppo.num_steps)
+    torch.manual_seed(1234 + rank)
+    venv = CrowdVecEnv(cfg, N, dev, seed=0, phase="train", env_id_offset=rank * N, nenv=N * world)
+    obs_space, act_space = crowd_spaces(H)
+    policy = Policy(obs_space.spaces, act_space, base="srnn", base_kwargs=cfg)
+    policy.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights(wl["weights"]).items()})
+    policy = policy.to(dev)
+    rollouts = SRNNRolloutStorage(T, N, obs_space.spaces, act_space, 128, 256, "GRU", device=dev, keep_hidden_history=False)
+    per_pass = min(args.envs_per_pass, N // cfg.ppo.num_mini_batch)
+    agent = PPO(policy, cfg.ppo.clip_param, cfg.ppo.epoch, cfg.ppo.num_mini_batch, cfg.ppo.value_loss_coef, cfg.ppo.entropy_coef,
+                lr=cfg.training.lr, eps=cfg.training.eps, max_grad_norm=cfg.training.max_grad_norm, max_envs_per_pass=per_pass,
+                native=True)
+    obs = venv.reset()
+    for k in rollouts.obs:
+        rollouts.obs[k][0].copy_(obs[k])
+    timing = {"rollout": [], "update": []}
+
+    def cycle(record=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
+        if record:
+            ev[0].record()
+        for step in range(T):
+            value, action, log_prob, hx = policy.act(rollouts.obs_at(step), dict(rollouts.hidden_at(step)), rollouts.masks[step])
+            o, reward, done, buf = venv.step_device(action)
+            rollouts.insert(o, hx, action, log_prob, value, reward, buf.not_done, None)
+        next_value = policy.get_value(rollouts.obs_at(-1), dict(rollouts.hidden_at(-1)), rollouts.masks[-1]).detach()
+        rollouts.compute_returns(next_value, cfg.ppo.use_gae, cfg.reward.gamma, cfg.ppo.gae_lambda, cfg.training.use_proper_time_limits)
+        if record:
+            ev[1].record()
+        losses = agent.update(rollouts, sync=False)
+        rollouts.after_update()
+        if record:
+            ev[2].record()
+            timing["pending"] = ev
+        return losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        cycle()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = venv.engine.launches + policy.gpu_launches + native.COUNTERS["gemm_launches"] + native.COUNTERS["kernel_launches"]
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        losses = cycle()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = venv.engine.launches + policy.gpu_launches + native.COUNTERS["gemm_launches"] + native.COUNTERS["kernel_launches"] - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # one more cycle with the library's GEMM timing on: the roofline of the dominant kernel and the rollout / update split
+    lib.cn_gemm_enable_timing(1)
+    cycle(record=True)
+    torch.cuda.synchronize()
+    gemm_ms, gemm_n, gemm_flops = C.c_float(), C.c_int(), C.c_double()
+    lib.cn_gemm_time_ms(C.byref(gemm_ms), C.byref(gemm_n), C.byref(gemm_flops))
+    lib.cn_gemm_enable_timing(0)
+    ev = timing["pending"]
+    rollout_ms, update_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    # end to end through the public training API (train.train): same loop plus its per-update host reads (episode
+    # statistics and losses cross PCIe once per update)
+    from crowdnav_dsrnn_b200.train import train as train_api
+
+    cfg.training.num_env_steps = 10 ** 12
+    cfg.training.log_interval = 1
+    cfg.training.save_interval = 10 ** 9
+    e2e_updates = max(1, min(args.steps, 2))
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    train_api(cfg, dev, num_updates=1, output_dir=None, actor_critic=policy, log=None, max_envs_per_pass=per_pass, native_update=True)
+    barrier()
+    t0.record()
+    train_api(cfg, dev, num_updates=e2e_updates, output_dir=None, actor_critic=policy, log=None, max_envs_per_pass=per_pass, native_update=True)
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([float(launches)], device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    value = N * world * T * args.steps / (ms * 1e-3)
+    e2e_value = N * world * T * e2e_updates / (e2e_ms * 1e-3)
+    roof = {"bound": "tensor", "kernel": "gemm_bf16x3_kernel", "achieved": gemm_flops.value / (gemm_ms.value * 1e-3) / 1e12,
+            "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "ms_per_launch": gemm_ms.value / max(1, gemm_n.value),
+            "launches_per_step": gemm_n.value, "ms_per_step": gemm_ms.value, "traffic": None, "tensor_passes": 3,
+            "algorithmic_flops_per_step": gemm_flops.value, "share_of_step": gemm_ms.value / (rollout_ms + update_ms),
+            "note": "all cn_gemm_bf16x3 launches of one update cycle (recurrent products, weight gradients, linears); algorithmic "
+                    "FLOPs = 2 m n k, three bf16 tensor passes are issued per product"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    line = {
+        "metric": "env_steps_per_sec_ppo_training", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16x3 (3-pass split bf16, fp32 accumulate) for every contraction; fp32 elsewhere",
+        "data": "synthetic scenarios (device reset, counter-based RNG); initial weights of the shipped checkpoint %s" % wl["weights"],
+        "config": {"workload": wl["label"], "human_num": H, "global_envs": N * world, "envs_per_gpu": N, "num_steps": T,
+                   "ppo_epoch": cfg.ppo.epoch, "num_mini_batch": cfg.ppo.num_mini_batch, "envs_per_pass": per_pass,
+                   "parallelism": "env-sharded x%d, NCCL all-reduce of the gradients (2 buckets, the first overlapped with backward)" % world,
+                   "l2": "inputs larger than L2 (activations of one pass: %.1f GB)" % (per_pass * (H + 1) * T * 11.3e3 / 1e9),
+                   "rollout_ms": rollout_ms, "update_ms": update_ms, "peaks": peaks["source"]},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 5 * 8 + 3 * 4,
+                "steps": e2e_updates, "ms_per_step": e2e_ms / e2e_updates,
+                "note": "crowdnav_dsrnn_b200.train.train(): the same cycle through the public API, with its per-update host reads"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 200; 3 update cycles for c5)")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed steps (default 20; 3 for c5)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16", "fp16"])
@@ -382,11 +543,21 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager loop instead of the CUDA-graph replay")
+    ap.add_argument("--envs-total", type=int, default=0, help="c5: total envs over all GPUs (default 65536)")
+    ap.add_argument("--envs-per-pass", type=int, default=4096, help="c5: env trajectories per forward/backward pass of the update")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.steps is None:
+        args.steps = 3 if wl.get("train") else 200
+    if args.warmup is None:
+        args.warmup = 3 if wl.get("train") else 20
     if args.warmup < 3:
         args.warmup = 3
-    wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if wl.get("train"):
+        if args.impl == "reference":
+            raise SystemExit("--impl reference times the rollout workloads (c1/c2/c3); the training workload has no CPU arm")
+        run_train(args, wl)
+    elif args.impl == "reference":
         run_reference_arm(args, wl)
     else:
         run_ours(args, wl)

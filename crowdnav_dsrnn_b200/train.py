@@ -30,7 +30,7 @@ def _rank_world():
 
 
 def train(config, device=None, num_updates=None, output_dir=None, actor_critic=None, log=print, max_envs_per_pass=None,
-          keep_hidden_history=False, tf32_update=False, bf16x3_update=False):
+          keep_hidden_history=False, tf32_update=False, bf16x3_update=False, native_update=False):
     rank, world = _rank_world()
     device = torch.device(device if device is not None else "cuda:0")
     torch.manual_seed(config.env.seed + rank)
@@ -50,7 +50,8 @@ def train(config, device=None, num_updates=None, output_dir=None, actor_critic=N
                                   keep_hidden_history=keep_hidden_history)
     agent = PPO(actor_critic, config.ppo.clip_param, config.ppo.epoch, config.ppo.num_mini_batch, config.ppo.value_loss_coef,
                 config.ppo.entropy_coef, lr=config.training.lr, eps=config.training.eps,
-                max_grad_norm=config.training.max_grad_norm, max_envs_per_pass=max_envs_per_pass, tf32=tf32_update, bf16x3=bf16x3_update)
+                max_grad_norm=config.training.max_grad_norm, max_envs_per_pass=max_envs_per_pass, tf32=tf32_update, bf16x3=bf16x3_update,
+                native=native_update)
     obs = envs.reset()
     for k in rollouts.obs:
         rollouts.obs[k][0].copy_(obs[k])
