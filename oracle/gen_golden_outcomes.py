@@ -30,6 +30,12 @@ CASES = {
     "default_h5_unicycle": dict(over={"action_space.kinematics": "unicycle", "env.time_step": 0.1,
                                       "reward.discomfort_penalty_factor": 1.0},
                                 ckpt="data/example_model_unicycle/checkpoints/55554.pt", episodes=2000),
+    # BASELINE.json configs[1]: unicycle robot, 10 humans, the four mixed scenarios, dt 0.1 (the reference still terminates
+    # at H=10: the unbounded goal re-sampling loop of crowd_sim.py:787-806 only becomes prohibitive near H=20)
+    "c2_h10_unicycle": dict(over={"action_space.kinematics": "unicycle", "env.time_step": 0.1, "sim.human_num": 10,
+                                  "reward.discomfort_penalty_factor": 1.0,
+                                  "sim.test_sim": ["circle_crossing", "square_crossing", "parallel_traffic", "perpendicular_traffic"]},
+                            ckpt="data/example_model_unicycle/checkpoints/55554.pt", episodes=1200),
     # BASELINE.json configs[3], second half: side-preference scenarios (1 human, circle_radius 4, 200 episodes each;
     # 2000 here to tighten the noise), config.py:27-40,51-54,87-92
     "sidepref_passing": dict(over={"test.side_preference": True, "sim.test_sim": ["side_pref_passing"], "sim.circle_radius": 4,
