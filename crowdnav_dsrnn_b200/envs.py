@@ -133,11 +133,14 @@ class CrowdVecEnv(object):
         # VecPyTorch.step_wait keeps reward on the CPU and done as a numpy array (envs.py:231-239): both cross PCIe in
         # ONE synchronisation through pinned staging buffers (fresh host tensors are returned, like the reference)
         if self._pin_reward is None:
-            self._pin_reward = torch.empty(self.num_envs, dtype=torch.float32).pin_memory()
-            self._pin_done = torch.empty(self.num_envs, dtype=torch.uint8).pin_memory()
+            self._pin_reward = torch.empty(self.num_envs, dtype=torch.float32)
+            self._pin_done = torch.empty(self.num_envs, dtype=torch.uint8)
+            if self.device.type == "cuda":
+                self._pin_reward, self._pin_done = self._pin_reward.pin_memory(), self._pin_done.pin_memory()
         self._pin_reward.copy_(buf.reward, non_blocking=True)
         self._pin_done.copy_(buf.done, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
         reward = self._pin_reward.clone().unsqueeze(1)
         done = self._pin_done.numpy().astype(bool)
         return buf.obs(), reward, done, LazyInfos(buf, self._side, self._t0)

@@ -2,6 +2,8 @@
 class names, `__str__` texts and the `Danger.min_dist` attribute, so callers'
 `isinstance(info["info"]["event"], ReachGoal)` checks (train.py:268-276,
 evaluation.py:211-260) keep working."""
+import sys
+
 from . import abi
 
 
@@ -33,15 +35,25 @@ class Nothing(object):
         return ""
 
 
+def _classes():
+    """When the caller is the reference code base itself (its `crowd_sim.envs.utils.info` is loaded), events are instances
+    of ITS classes, so the `isinstance` checks of the unmodified train.py / evaluation.py hold; otherwise the twins above."""
+    ref = sys.modules.get("crowd_sim.envs.utils.info")
+    if ref is not None and all(hasattr(ref, n) for n in ("Timeout", "ReachGoal", "Danger", "Collision", "Nothing")):
+        return ref
+    return sys.modules[__name__]
+
+
 def make_event(code, dmin):
+    m = _classes()
     if code == abi.EV_NOTHING:
-        return Nothing()
+        return m.Nothing()
     if code == abi.EV_DANGER:
-        return Danger(dmin)
+        return m.Danger(dmin)
     if code == abi.EV_REACH_GOAL:
-        return ReachGoal()
+        return m.ReachGoal()
     if code == abi.EV_COLLISION:
-        return Collision()
+        return m.Collision()
     if code == abi.EV_TIMEOUT:
-        return Timeout()
+        return m.Timeout()
     raise ValueError("unknown event code %r" % (code,))

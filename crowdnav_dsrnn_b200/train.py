@@ -10,7 +10,11 @@ Under `torch.distributed` every rank runs this function with its own shard of `t
 (env ids offset by rank so the episode seeds do not collide) and `PPO` averages the gradients; rank 0 writes artefacts.
 """
 import csv
+import inspect
+import logging
 import os
+import shutil
+import sys
 import time
 
 import torch
@@ -27,6 +31,46 @@ def _rank_world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+def write_run_artefacts(config, out_dir):
+    """What the reference's train.py writes before the loop starts (train.py:47-75): the config snapshot
+    `<out>/configs/train_config.py` (+ `configs/config.py` pointing at the live file, a symlink there) -- test.py re-imports
+    it as `<model_dir>.configs.train_config` (test.py:60-98) -- and `<out>/output.log`.  Returns the file logger."""
+    cfg_dir = os.path.join(out_dir, "configs")
+    os.makedirs(cfg_dir, exist_ok=True)
+    try:
+        src = inspect.getsourcefile(type(config))
+    except TypeError:
+        src = None
+    if src and os.path.exists(src):
+        shutil.copyfile(src, os.path.join(cfg_dir, "train_config.py"))
+        link = os.path.join(cfg_dir, "config.py")
+        if not os.path.lexists(link):
+            os.symlink(os.path.abspath(src), link)
+    # the values actually used (the class file above only holds the defaults when the caller edited the instance)
+    with open(os.path.join(cfg_dir, "train_config_values.txt"), "w") as f:
+        for sec, bag in sorted(vars(config).items()):
+            for k, v in sorted(vars(bag).items()) if hasattr(bag, "__dict__") else ():
+                f.write("%s.%s = %r\n" % (sec, k, v))
+    logger = logging.getLogger("crowdnav_dsrnn_b200.train.%d" % os.getpid())
+    logger.setLevel(logging.INFO)
+    logger.propagate = False
+    for h in list(logger.handlers):
+        logger.removeHandler(h)
+    handler = logging.FileHandler(os.path.join(out_dir, "output.log"), mode="a" if getattr(config.training, "resume", False) else "w")
+    handler.setFormatter(logging.Formatter("%(asctime)s, %(levelname)s: %(message)s", datefmt="%Y-%m-%d %H:%M:%S"))
+    logger.addHandler(handler)
+    return logger
+
+
+def _tensorboard_writer(out_dir):
+    """TensorBoard scalars of train.py:211,376-386 when the `tensorboard` package is importable (it is optional here)."""
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+    except Exception:  # noqa: BLE001
+        return None
+    return SummaryWriter(log_dir=os.path.join(out_dir, "events"))
 
 
 def train(config, device=None, num_updates=None, output_dir=None, actor_critic=None, log=print, max_envs_per_pass=None,
@@ -59,8 +103,11 @@ def train(config, device=None, num_updates=None, output_dir=None, actor_critic=N
     if num_updates is None:
         num_updates = total_updates
     out_dir = output_dir if output_dir is not None else config.training.output_dir
+    file_log = tboard = None
     if rank == 0 and out_dir:
         os.makedirs(os.path.join(out_dir, "checkpoints"), exist_ok=True)
+        file_log = write_run_artefacts(config, out_dir)
+        tboard = _tensorboard_writer(out_dir)
     # device-side episode statistics: [success, collision, timeout, episodes, return sum], reduced ONCE per update from the
     # per-step event / done / episode-return records (three small copies per step instead of ~20 reduction launches)
     stats = torch.zeros(5, dtype=torch.float64, device=device)
@@ -112,10 +159,59 @@ def train(config, device=None, num_updates=None, output_dir=None, actor_critic=N
                     if fresh:
                         w.writeheader()
                     w.writerow(row)
-        if rank == 0 and log is not None and j % config.training.log_interval == 0:
-            log("Updates %d, num timesteps %d, FPS %d, episodes %d: mean reward %.3f, success %.3f, collision %.3f, timeout %.3f, "
-                "entropy %.4f, value loss %.4f, policy loss %.5f" % (j, total_steps, row["fps"], row["episodes"], row["eprewmean"],
-                                                                      row["success"], row["collision"], row["timeout"], entropy,
-                                                                      value_loss, action_loss))
+        if rank == 0 and j % config.training.log_interval == 0:
+            msg = ("Updates %d, num timesteps %d, FPS %d, episodes %d: mean reward %.3f, success %.3f, collision %.3f, timeout %.3f, "
+                   "entropy %.4f, value loss %.4f, policy loss %.5f" % (j, total_steps, row["fps"], row["episodes"], row["eprewmean"],
+                                                                         row["success"], row["collision"], row["timeout"], entropy,
+                                                                         value_loss, action_loss))
+            if log is not None:
+                log(msg)
+            if file_log is not None:
+                file_log.info(msg)
+            if tboard is not None:          # train.py:376-386
+                tboard.add_scalar("mean_reward", row["eprewmean"], total_steps)
+                tboard.add_scalar("policy_entropy (dist_entropy)", entropy, total_steps)
+                tboard.add_scalar("policy_loss (action_loss)", action_loss, total_steps)
+                tboard.add_scalar("value_loss", value_loss, total_steps)
+    if file_log is not None:
+        for h in list(file_log.handlers):
+            h.close()
+            file_log.removeHandler(h)
+    if tboard is not None:
+        tboard.close()
     envs.close()
     return actor_critic, history
+
+
+def main(argv=None):
+    """`python -m crowdnav_dsrnn_b200.train [--output_dir DIR] [--num_updates K] [--envs N] [--humans H] [--native]`:
+    the reference's `python train.py` on the batched backend (its settings come from the config file; here the ones that
+    matter for a batch of thousands of envs can be given on the command line)."""
+    import argparse
+
+    from .config import Config
+
+    ap = argparse.ArgumentParser("crowdnav_dsrnn_b200.train")
+    ap.add_argument("--output_dir", default=None)
+    ap.add_argument("--num_updates", type=int, default=None)
+    ap.add_argument("--envs", type=int, default=None, help="training.num_processes (envs per GPU)")
+    ap.add_argument("--humans", type=int, default=None)
+    ap.add_argument("--kinematics", default="holonomic", choices=["holonomic", "unicycle"])
+    ap.add_argument("--envs_per_pass", type=int, default=4096)
+    ap.add_argument("--native", action="store_true", help="PPO update on the library's own tensor-core kernels")
+    args = ap.parse_args(argv)
+    cfg = Config(kinematics=args.kinematics, human_num=args.humans)
+    if args.envs:
+        cfg.training.num_processes = args.envs
+    if args.output_dir:
+        cfg.training.output_dir = args.output_dir
+    if dist.is_available() and "RANK" in os.environ and not dist.is_initialized():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    train(cfg, device, num_updates=args.num_updates, max_envs_per_pass=args.envs_per_pass, native_update=args.native)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

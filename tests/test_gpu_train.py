@@ -53,6 +53,30 @@ def test_training_loop_runs_and_writes_reference_artefacts(tmp_path):
     assert list(rows[0]) == ["misc/nupdates", "misc/total_timesteps", "fps", "eprewmean", "loss/policy_entropy",
                              "loss/policy_loss", "loss/value_loss"] and len(rows) == 4
     assert int(rows[-1]["misc/total_timesteps"]) == 4 * 256 * 30
+    # train.py:47-75: config snapshot (what test.py re-imports as <model_dir>.configs.train_config) and output.log
+    assert os.path.exists(tmp_path / "configs" / "train_config.py") and os.path.lexists(tmp_path / "configs" / "config.py")
+    assert "training.num_processes = 256" in (tmp_path / "configs" / "train_config_values.txt").read_text()
+    assert (tmp_path / "output.log").read_text().count("Updates ") == 4
+
+
+def test_test_cli_writes_the_reference_log(tmp_path, monkeypatch):
+    """`python -m crowdnav_dsrnn_b200.test` (test.py:25-214): flags, model-directory layout, log file name, log lines."""
+    import re
+
+    from crowdnav_dsrnn_b200 import test as test_cli
+
+    w = np.load(os.path.join(GOLDEN, "weights_holonomic_27776.npz"))
+    ckpt_dir = tmp_path / "data" / "m" / "checkpoints"
+    ckpt_dir.mkdir(parents=True)
+    torch.save({k: torch.from_numpy(w[k]) for k in w.files}, ckpt_dir / "27776.pt")
+    monkeypatch.chdir(tmp_path)
+    assert test_cli.main(["--model_dir", "data/m", "--test_model", "27776.pt", "--test_name", "cli"]) == 0
+    log = (tmp_path / "data" / "m" / "test" / "model_27776_test_cli_.log").read_text()
+    assert "Using model" in log and "robot FOV" in log
+    rates = [float(re.search(r"%s rate: ([0-9.]+)" % k, log).group(1)) for k in ("success", "collision", "timeout")]
+    assert abs(sum(rates) - 1.0) < 2e-3 and rates[0] > 0.85          # reference: 0.93 / 0.055 / 0.012 over 2000 episodes
+    with pytest.raises(NotImplementedError):
+        test_cli.main(["--model_dir", "data/m", "--viz"])
 
 
 def test_cuda_forward_tracks_optimizer_updates():
