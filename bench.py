@@ -40,9 +40,32 @@ WORKLOADS = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from ONE `ncu --set full` capture of the bench loop at the
-# default sizes (profiles/r1_ncu_full_loop_summary.txt); only valid for that workload / batch, else null
-NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 361.40e6 + 309.38e6, "crowd_step_kernel": 16.97e6 + 4.86e6}}   # profiles/r1_ncu_final_kernels.txt
+# dram__bytes_read.sum + dram__bytes_write.sum per launch.  NOT sampled in this run: constants copied from ONE earlier
+# `ncu --set full` capture of the same kernels at the default sizes (the file named in `traffic_source`); only reported for that
+# workload / batch, null otherwise
+NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 361.40e6 + 309.38e6, "crowd_step_kernel": 16.97e6 + 4.86e6}}
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_final_kernels.txt (one ncu --set full capture, round 1; not re-measured by this run)"
+
+
+def reference_python_baseline(workload):
+    """The BASELINE.md section-3 CPU path -- the reference's own Python env under its own ShmemVecEnv + Policy.act, rvo2
+    restated -- cannot travel to the GPU box (it is Python from /root/reference); it is timed in the build container by
+    oracle/bench_reference_python.py and its committed result is quoted here, labelled as such."""
+    path = os.path.join(ROOT, "profiles", "r2_reference_python_cpu.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        with open(path) as f:
+            doc = json.load(f)
+    except ValueError:
+        return None
+    for r in doc.get("results", []):
+        if r.get("workload") == workload:
+            return {"value": r["env_steps_per_s"], "unit": "env-steps/s", "cores": r["processes"], "kind": "reference-python",
+                    "sample": "%d lock-step steps of %d reference CrowdSimDict processes under ShmemVecEnv + reference Policy.act in %.0f s%s"
+                              % (r["timed_steps"], r["processes"], r["elapsed_s"], " (wall-capped)" if r.get("wall_capped") else ""),
+                    "measured_on": doc.get("where"), "source": "profiles/r2_reference_python_cpu.json (oracle/bench_reference_python.py)"}
+    return None
 
 
 def step_bytes(H):          # SURVEY 8(d): algorithmic HBM bytes of the step kernel per env-step
@@ -324,10 +347,11 @@ def run_ours(args, wl):
                  "unit": "GB/s", "kernel": "crowd_step_kernel", "ms_per_launch": step_avg_ms, "traffic": None,
                  "algorithmic_bytes_per_env_step": step_bytes(H), "share_of_step": step_avg_ms / (ms / args.steps)}
     roof_step["frac"] = roof_step["achieved"] / roof_step["peak"]
-    roof_step["note"] = ("ORCA is O(H^2) branchy fp32: at H=20 the kernel is instruction-issue bound (ncu issue slots 75 % busy, "
-                         "dram 0.4 %), see profiles/README.md")
+    roof_step["note"] = ("nominally HBM-bound (SURVEY 8(d)); measured: instruction-issue bound at every H (H=1..20: 0.012-0.015 of "
+                         "the HBM peak, profiles/r2_k1_sweep.txt; at H=20 ncu shows issue slots 77 % busy, dram 0.4 %)")
     traffic = NCU_TRAFFIC_BYTES.get((args.workload, N), {})
     roof_step["traffic"] = traffic.get("crowd_step_kernel")
+    roof_step["traffic_source"] = NCU_TRAFFIC_SOURCE if traffic else None
     edge_kernel = "edge_gru_simt_kernel" if args.precision == "fp32" else "edge_gru_tc_kernel"
     passes = 3 if args.precision == "bf16x3" else 1
     roof_edge = {"bound": "tensor", "achieved": N * edge_stage_flops(H) / (edge_avg_ms * 1e-3) / 1e12,
@@ -336,6 +360,7 @@ def run_ours(args, wl):
                  "tensor_passes": passes, "share_of_step": edge_avg_ms / (ms / args.steps)}
     roof_edge["frac"] = roof_edge["achieved"] / roof_edge["peak"]
     roof_edge["traffic"] = traffic.get(edge_kernel)
+    roof_edge["traffic_source"] = NCU_TRAFFIC_SOURCE if traffic.get(edge_kernel) else None
     dominant = roof_edge if edge_avg_ms >= step_avg_ms else roof_step
     other = roof_step if dominant is roof_edge else roof_edge
 
@@ -365,6 +390,7 @@ def run_ours(args, wl):
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": dominant, "roofline_other": other, "cpu_baseline": cpu,
+        "cpu_baseline_reference_python": reference_python_baseline(args.workload),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -502,3 +502,14 @@ extern "C" int cn_gemm_time_ms(float *ms, int *launches, double *flops)
     *ms = gemm_bf16x3_time_ms(launches, flops);
     return CN_OK;
 }
+
+extern "C" int cn_launch_encoder_grad(const float *de, const void *e_hi, int ld_e, const float *x, float *dw, float *db, long long rows,
+                                      cudaStream_t stream);
+extern "C" int cn_encoder_grad(const float *de, const void *e_hi, int ld_e, const float *x, float *dw, float *db, long long rows, void *stream)
+{
+    if (!de || !e_hi || !x || !dw || !db) return fail(CN_ERR_ARG, "cn_encoder_grad: NULL pointer");
+    const int rc = cn_launch_encoder_grad(de, e_hi, ld_e, x, dw, db, rows, (cudaStream_t)stream);
+    if (rc == -1) return fail(CN_ERR_ARG, "cn_encoder_grad: rows %lld / ld_e %d (>= 64) / alignment", rows, ld_e);
+    if (rc != 0) return fail(CN_ERR_CUDA, "encoder_grad_kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    return CN_OK;
+}

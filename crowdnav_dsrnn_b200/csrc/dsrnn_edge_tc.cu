@@ -334,7 +334,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(empty_remote + 8u * buf);
+                if (lane == 0) mbar_arrive_remote_cta(empty_remote + 8u * buf);
                 PROF_ADD(p_epi, t_e);
             }
         }
@@ -396,21 +396,29 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                         const int off = sw128_offset(r, 2 * lane);
                         *reinterpret_cast<uint32_t *>(smem + kOffAHi + off) = hi;
                         if (a.three_pass) *reinterpret_cast<uint32_t *>(smem + kOffALo + off) = lo;
-                        if (kTrain && okb) {      // operand of dW_ih = dgi^T e (128 contiguous bytes per row and warp)
-                            const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
-                            // rows of 72: 64 values, then a constant 1 (and 7 zeros) -- the "ones column" that makes the
-                            // weight-gradient product G^T [e | 1] also return the column sums of G (the bias gradients)
-                            reinterpret_cast<uint32_t *>(a.e_hi + orow * 72)[lane] = hi;
-                            reinterpret_cast<uint32_t *>(a.e_lo + orow * 72)[lane] = lo;
-                            if (lane == 0) {
-                                *reinterpret_cast<uint4 *>(a.e_hi + orow * 72 + 64) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-                                *reinterpret_cast<uint4 *>(a.e_lo + orow * 72 + 64) = make_uint4(0u, 0u, 0u, 0u);
-                            }
-                        }
                     }
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(ready_remote);
+                    if (kTrain) {
+                        // operand of dW_ih = dgi^T e, copied back out of the staged image AFTER the hand-over (the arrive's
+                        // release fence would otherwise wait for these global stores).  Rows of 72: 64 values, then a
+                        // constant 1 and 7 zeros -- the "ones column" that makes the weight-gradient product G^T [e | 1]
+                        // also return the column sums of G (the bias gradients)
+#pragma unroll 4
+                        for (int b = 0; b < 16; ++b) {
+                            const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
+                            if (__shfl_sync(0xffffffffu, (int)ok_l, b)) {
+                                const int off = sw128_offset(sw * 16 + b, 2 * lane);
+                                reinterpret_cast<uint32_t *>(a.e_hi + orow * 72)[lane] = *reinterpret_cast<const uint32_t *>(smem + kOffAHi + off);
+                                reinterpret_cast<uint32_t *>(a.e_lo + orow * 72)[lane] = *reinterpret_cast<const uint32_t *>(smem + kOffALo + off);
+                                if (lane == 0) {
+                                    *reinterpret_cast<uint4 *>(a.e_hi + orow * 72 + 64) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+                                    *reinterpret_cast<uint4 *>(a.e_lo + orow * 72 + 64) = make_uint4(0u, 0u, 0u, 0u);
+                                }
+                            }
+                        }
+                    }
                 }
                 PROF_T0(t_f);
                 if (it > 0) {
@@ -432,17 +440,22 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     else { split_bf16x2(h4.x, h4.y, hi.x, lo.x); split_bf16x2(h4.z, h4.w, hi.y, lo.y); }
                     *reinterpret_cast<uint2 *>(smem + kOffAHi + off) = hi;
                     if (a.three_pass) *reinterpret_cast<uint2 *>(smem + kOffALo + off) = lo;
-                    if (kTrain) {                 // operand of dW_hh = dgh^T hm
-                        const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
-                        if (__shfl_sync(0xffffffffu, (int)ok_l, b)) {
-                            *reinterpret_cast<uint2 *>(a.hm_hi + orow * 256 + e0) = hi;
-                            *reinterpret_cast<uint2 *>(a.hm_lo + orow * 256 + e0) = lo;
-                        }
-                    }
                 }
                 fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(ready_remote + 8u * (1 + half));   // k-blocks 1-2, then 3-4, of this CTA's rows
+                if (kTrain) {                      // operand of dW_hh = dgh^T hm: out of the staged image, after the hand-over
+#pragma unroll 4
+                    for (int b = 0; b < 16; ++b) {
+                        const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
+                        if (__shfl_sync(0xffffffffu, (int)ok_l, b)) {
+                            const int e0 = half * 128 + lane * 4;
+                            const int off = (1 + (e0 >> 6)) * kABlockBytes + sw128_offset(sw * 16 + b, e0 & 63);
+                            *reinterpret_cast<uint2 *>(a.hm_hi + orow * 256 + e0) = *reinterpret_cast<const uint2 *>(smem + kOffAHi + off);
+                            *reinterpret_cast<uint2 *>(a.hm_lo + orow * 256 + e0) = *reinterpret_cast<const uint2 *>(smem + kOffALo + off);
+                        }
+                    }
+                }
                 PROF_ADD(p_stage, t_s);
             }
             // pull the NEXT tile's hidden-state rows into L2 while this one is being multiplied (16 rows x 8 lines per warp)

@@ -247,6 +247,33 @@ attention_train_backward_kernel(const float *__restrict__ o, const float *__rest
     if (d_cst) { const float tot = warp_sum(ds); if (lane == 0) d_cst[b] = tot; }
 }
 
+// ------------------------------------------------------------------------------------------------ edge-encoder gradient
+// e = ReLU(W_enc x + b) with x [rows, 2] (HumanHumanEdgeRNN.encoder_linear, srnn_model.py:201-215).  Given de = dL/de
+// [rows, 64] (fp32) and the sign of e (its bf16 hi image, row stride ld_e):  dW_enc[k, j] = sum_rows [e_k > 0] de_k x_j,
+// db_enc[k] = sum_rows [e_k > 0] de_k.  One pass over de: HBM-bound.  Block = 4 rows x 64 columns per iteration; block sums are
+// combined in shared memory and added to the outputs with 64 x 3 atomics per block.
+__global__ void __launch_bounds__(256)
+encoder_grad_kernel(const float *__restrict__ de, const __nv_bfloat16 *__restrict__ e_hi, int ld_e, const float *__restrict__ x,
+                    float *__restrict__ dw, float *__restrict__ db, long long rows)
+{
+    __shared__ float part[4][64][3];
+    const int col = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (long long row = (long long)blockIdx.x * 4 + rsub; row < rows; row += (long long)gridDim.x * 4) {
+        const float v = de[row * 64 + col];
+        const bool on = __bfloat162float(e_hi[row * ld_e + col]) > 0.0f;
+        const float2 xv = *reinterpret_cast<const float2 *>(x + row * 2);
+        if (on) { s0 += v * xv.x; s1 += v * xv.y; s2 += v; }
+    }
+    part[rsub][col][0] = s0; part[rsub][col][1] = s1; part[rsub][col][2] = s2;
+    __syncthreads();
+    if (threadIdx.x < 192) {
+        const int c = threadIdx.x / 3, k = threadIdx.x - 3 * c;
+        const float t = part[0][c][k] + part[1][c][k] + part[2][c][k] + part[3][c][k];
+        if (k < 2) atomicAdd(dw + c * 2 + k, t); else atomicAdd(db + c, t);
+    }
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
@@ -319,5 +346,15 @@ extern "C" int cn_launch_attention_train_backward(const float *o, const float *q
 {
     if (B < 1 || H < 1 || H > 32 || !aligned16(o) || !aligned16(qt) || !aligned16(dc) || !aligned16(d_o) || !aligned16(d_qt)) return -1;
     attention_train_backward_kernel<<<(B + 3) / 4, 128, 0, stream>>>(o, qt, alpha, dc, d_o, d_qt, d_cst, scale, B, H);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cn_launch_encoder_grad(const float *de, const void *e_hi, int ld_e, const float *x, float *dw, float *db, long long rows,
+                                      cudaStream_t stream)
+{
+    if (rows < 1 || ld_e < 64 || !aligned16(de) || !aligned8(x)) return -1;
+    long long blocks = (rows + 3) / 4;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    encoder_grad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(de, static_cast<const __nv_bfloat16 *>(e_hi), ld_e, x, dw, db, rows);
     return (int)cudaGetLastError();
 }

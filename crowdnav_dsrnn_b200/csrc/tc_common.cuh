@@ -76,6 +76,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// remote arrive with release at CTA scope (what cutlass::arch::ClusterBarrier::arrive(cta_id) emits): enough to hand a TMEM
+// buffer back to the MMA thread of the peer CTA -- the tcgen05.ld's are complete (tcgen05.wait::ld) and ordered by
+// tcgen05.fence::before_thread_sync -- without the gpu-scope MEMBAR of .release.cluster, which waits for every global
+// store the thread has in flight
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 {
     uint32_t done;

@@ -288,6 +288,8 @@ class EdgeGruSequence(torch.autograd.Function):
             colsum = dwx[k, :, 64]                                           # [1024]: sums of pn | pr | pz | pn*r over all rows
             db_ih = torch.cat([colsum[256:768], colsum[:256]])
             db_hh = colsum[256:]
-            dem = de[sl] * (e_hi[sl, :64] > 0)                               # ReLU of the edge encoder
-            grads.append((dem.t() @ x, dem.sum(0), unperm(dwx[k, :768, :64]), dwh[k], db_ih, db_hh))
+            dw_enc, db_enc = torch.zeros(64, 2, dtype=torch.float32, device=dev), torch.zeros(64, dtype=torch.float32, device=dev)
+            _lib.check(lib.cn_encoder_grad(_ptr(de[sl]), _ptr(e_hi[sl]), 72, _ptr(x), _ptr(dw_enc), _ptr(db_enc), x.shape[0], stream),
+                       "cn_encoder_grad")                                    # ReLU mask + the two reductions in one pass over de
+            grads.append((dw_enc, db_enc, unperm(dwx[k, :768, :64]), dwh[k], db_ih, db_hh))
         return (None, None, None, grad_h0, None) + grads[0] + grads[1]

@@ -316,6 +316,11 @@ int cn_attention_train_forward(const float *o, const float *qt, const float *cst
 int cn_attention_train_backward(const float *o, const float *qt, const float *alpha, const float *dc, float *d_o, float *d_qt,
                                 float *d_cst, float scale, int batch, int human_num, void *stream);
 
+/* Gradient of the edge encoder e = ReLU(W_enc x + b), x [rows, 2] (srnn_model.py:201-215): from de = dL/de [rows, 64] (fp32) and
+ * the sign of e (bf16 image with row stride ld_e):  dw[64, 2] += sum_rows [e > 0] de x^T,  db[64] += sum_rows [e > 0] de.
+ * dw / db must hold the initial value (zeros).  One HBM-bound pass over de. */
+int cn_encoder_grad(const float *de, const void *e_hi, int ld_e, const float *x, float *dw, float *db, long long rows, void *stream);
+
 /* Generic split-bf16 3-pass tensor-core GEMM (tcgen05, TMA-fed, fp32 accumulation in TMEM):
  *   C[m, n] (=, +=, or atomically += for split-K)  (A_hi + A_lo)(B_hi + B_lo) minus the lo*lo term  (+ bias[n], activation).
  * An operand is K-major (row-major [m|n, k] array) or MN-major (row-major [k, m|n] array); lo == NULL drops that operand's

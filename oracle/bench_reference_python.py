@@ -94,15 +94,22 @@ def main():
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--warmup-steps", type=int, default=200)
     ap.add_argument("--workloads", default="c1,c2,c3")
+    ap.add_argument("--out", default=None, help="JSON file, rewritten after every workload")
     args = ap.parse_args()
     from . import crowd_oracle
 
     crowd_oracle.build()
     n_cpu = os.cpu_count() or 1
-    rows = [run(w, args.seconds, args.warmup_steps, n_cpu) for w in args.workloads.split(",")]
-    print(json.dumps({"what": "reference-equivalent CPU path (reference Python env + ShmemVecEnv + Policy.act, rvo2 restated)",
-                      "where": "build container, %d vCPU (%s)" % (n_cpu, platform.processor() or platform.machine()),
-                      "kind": "reference-python", "results": rows}, indent=1))
+    rows = []
+    for w in args.workloads.split(","):
+        rows.append(run(w, args.seconds, args.warmup_steps, n_cpu))
+        doc = {"what": "reference-equivalent CPU path (reference Python env + ShmemVecEnv + Policy.act, rvo2 restated)",
+               "where": "build container, %d vCPU (%s)" % (n_cpu, platform.processor() or platform.machine()),
+               "kind": "reference-python", "results": rows}
+        if args.out:                      # written after every workload: the H=20 one may have to be killed from outside
+            with open(args.out, "w") as f:
+                json.dump(doc, f, indent=1)
+    print(json.dumps(doc, indent=1))
 
 
 if __name__ == "__main__":
