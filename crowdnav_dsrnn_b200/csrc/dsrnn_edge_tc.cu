@@ -321,7 +321,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                             // 32-byte form halves the LSU work of the epilogue
                             if (q & 1) {
                                 st_global_v8(orow + c0 + (q - 1) * 4, o8);
-                                if (kTrain) {
+                                if (kTrain && !DBG(16)) {
                                     float *w8 = wsrow + c0 + (q - 1) * 4;
                                     st_global_v8(w8, r8); st_global_v8(w8 + 256, z8); st_global_v8(w8 + 512, n8); st_global_v8(w8 + 768, h8);
                                 }
@@ -400,25 +400,6 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(ready_remote);
-                    if (kTrain) {
-                        // operand of dW_ih = dgi^T e, copied back out of the staged image AFTER the hand-over (the arrive's
-                        // release fence would otherwise wait for these global stores).  Rows of 72: 64 values, then a
-                        // constant 1 and 7 zeros -- the "ones column" that makes the weight-gradient product G^T [e | 1]
-                        // also return the column sums of G (the bias gradients)
-#pragma unroll 4
-                        for (int b = 0; b < 16; ++b) {
-                            const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
-                            if (__shfl_sync(0xffffffffu, (int)ok_l, b)) {
-                                const int off = sw128_offset(sw * 16 + b, 2 * lane);
-                                reinterpret_cast<uint32_t *>(a.e_hi + orow * 72)[lane] = *reinterpret_cast<const uint32_t *>(smem + kOffAHi + off);
-                                reinterpret_cast<uint32_t *>(a.e_lo + orow * 72)[lane] = *reinterpret_cast<const uint32_t *>(smem + kOffALo + off);
-                                if (lane == 0) {
-                                    *reinterpret_cast<uint4 *>(a.e_hi + orow * 72 + 64) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-                                    *reinterpret_cast<uint4 *>(a.e_lo + orow * 72 + 64) = make_uint4(0u, 0u, 0u, 0u);
-                                }
-                            }
-                        }
-                    }
                 }
                 PROF_T0(t_f);
                 if (it > 0) {
@@ -444,19 +425,34 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                 fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(ready_remote + 8u * (1 + half));   // k-blocks 1-2, then 3-4, of this CTA's rows
-                if (kTrain) {                      // operand of dW_hh = dgh^T hm: out of the staged image, after the hand-over
-#pragma unroll 4
-                    for (int b = 0; b < 16; ++b) {
-                        const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
-                        if (__shfl_sync(0xffffffffu, (int)ok_l, b)) {
-                            const int e0 = half * 128 + lane * 4;
-                            const int off = (1 + (e0 >> 6)) * kABlockBytes + sw128_offset(sw * 16 + b, e0 & 63);
-                            *reinterpret_cast<uint2 *>(a.hm_hi + orow * 256 + e0) = *reinterpret_cast<const uint2 *>(smem + kOffAHi + off);
-                            *reinterpret_cast<uint2 *>(a.hm_lo + orow * 256 + e0) = *reinterpret_cast<const uint2 *>(smem + kOffALo + off);
-                        }
+                PROF_ADD(p_stage, t_s);
+            }
+            if (kTrain && !DBG(32)) {
+                // Records of the backward, copied out of the staged A image AFTER all three pieces were handed to the MMA thread
+                // (the image stays valid until this warp restages it; an arrive's release fence would otherwise wait for these
+                // global stores): the split masked state (operand of dW_hh = dgh^T hm) and the split encoder output in rows of
+                // 72 = 64 values, a constant 1 and 7 zeros -- the "ones column" that makes G^T [e | 1] also return the column
+                // sums of G (the bias gradients).
+#pragma unroll 2
+                for (int b = 0; b < 16; ++b) {
+                    const long long orow = __shfl_sync(0xffffffffu, orow_l, b);
+                    if (!__shfl_sync(0xffffffffu, (int)ok_l, b)) continue;
+                    const int r = sw * 16 + b;
+                    const int offe = sw128_offset(r, 2 * lane);
+                    reinterpret_cast<uint32_t *>(a.e_hi + orow * 72)[lane] = *reinterpret_cast<const uint32_t *>(smem + kOffAHi + offe);
+                    reinterpret_cast<uint32_t *>(a.e_lo + orow * 72)[lane] = *reinterpret_cast<const uint32_t *>(smem + kOffALo + offe);
+                    if (lane == 0) {
+                        *reinterpret_cast<uint4 *>(a.e_hi + orow * 72 + 64) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(a.e_lo + orow * 72 + 64) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int e0 = half * 128 + lane * 4;
+                        const int off = (1 + (e0 >> 6)) * kABlockBytes + sw128_offset(r, e0 & 63);
+                        *reinterpret_cast<uint2 *>(a.hm_hi + orow * 256 + e0) = *reinterpret_cast<const uint2 *>(smem + kOffAHi + off);
+                        *reinterpret_cast<uint2 *>(a.hm_lo + orow * 256 + e0) = *reinterpret_cast<const uint2 *>(smem + kOffALo + off);
                     }
                 }
-                PROF_ADD(p_stage, t_s);
             }
             // pull the NEXT tile's hidden-state rows into L2 while this one is being multiplied (16 rows x 8 lines per warp)
             const int next = pair + num_clusters;
@@ -721,6 +717,9 @@ const char *dsrnn_tc_edge_sequence_step(void *state, int n_envs, int H, const Cn
     a.pairs_spatial = (a.tiles_spatial + 1) / 2;
     a.pairs_total = a.pairs_spatial + (a.tiles_temporal + 1) / 2;
     a.three_pass = 1; a.fp16 = 0; a.debug = 0;
+#ifdef EDGE_PROFILE
+    if (const char *dbg = getenv("CN_EDGE_DEBUG")) a.debug = atoi(dbg);
+#endif
     a.train = 1;
     a.in_off_s = io->in_row_spatial; a.in_off_t = io->in_row_temporal;
     a.out_off_s = io->out_row_spatial; a.out_off_t = io->out_row_temporal;
