@@ -64,16 +64,21 @@ def test_flatten_config_equals_reference_config():
 
 
 class _FakeBuf:
+    """A StepBuffers stand-in on the CPU: the same info block layout, filled by hand."""
+
     def __init__(self):
-        n = 3
-        self.event = torch.tensor([abi.EV_NOTHING, abi.EV_DANGER, abi.EV_COLLISION], dtype=torch.int32)
-        self.scenario = torch.tensor([0, 2, 3], dtype=torch.int32)
-        self.info = torch.zeros(n, abi.INFO_DIM)
+        from crowdnav_dsrnn_b200.engine import StepBuffers
+        n = self.n = 3
+        self.info_block = torch.zeros(StepBuffers.info_block_bytes(n), dtype=torch.uint8)
+        for name, view in StepBuffers.carve_info(self.info_block, n).items():
+            setattr(self, name, view)
+        self.event.copy_(torch.tensor([abi.EV_NOTHING, abi.EV_DANGER, abi.EV_COLLISION], dtype=torch.int32))
+        self.scenario.copy_(torch.tensor([0, 2, 3], dtype=torch.int32))
         self.info[1, abi.INFO_COLUMNS["dmin"]] = 0.125
         self.info[:, abi.INFO_COLUMNS["aggregate_nav_time"]] = torch.tensor([6.0, 5.0, 4.0])
-        self.done = torch.tensor([0, 0, 1], dtype=torch.uint8)
-        self.episode_return = torch.tensor([0.0, 0.0, -17.5])
-        self.episode_length = torch.tensor([0, 0, 42], dtype=torch.int32)
+        self.done.copy_(torch.tensor([0, 0, 1], dtype=torch.uint8))
+        self.episode_return.copy_(torch.tensor([0.0, 0.0, -17.5]))
+        self.episode_length.copy_(torch.tensor([0, 0, 42], dtype=torch.int32))
 
 
 def test_lazy_infos_reference_shape():
