@@ -375,6 +375,13 @@ extern "C" int cn_dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env)
     return CN_OK;
 }
 
+extern "C" int cn_dsrnn_set_edge_event(CnDsrnn *m, void *event)
+{
+    if (!m) return fail(CN_ERR_ARG, "model is NULL");
+    dsrnn_set_edge_event(m, event);
+    return CN_OK;
+}
+
 extern "C" int cn_dsrnn_enable_timing(CnDsrnn *m, int enable)
 {
     if (!m) return fail(CN_ERR_ARG, "model is NULL");

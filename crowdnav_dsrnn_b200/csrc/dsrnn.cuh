@@ -16,4 +16,5 @@ int dsrnn_device(const CnDsrnn *m);
 const char *dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, const CnEdgeSeqStep *io, cudaStream_t stream);
 void dsrnn_enable_timing(CnDsrnn *m, int enable);
 void dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env);
+void dsrnn_set_edge_event(CnDsrnn *m, void *event);
 float dsrnn_time_ms(CnDsrnn *m, int *count);

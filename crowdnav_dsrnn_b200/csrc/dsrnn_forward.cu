@@ -34,6 +34,7 @@ struct CnDsrnn {
     void *node_state = nullptr;   // packed weights of the fused node / heads kernel (dsrnn_node_tc.cu)
     bool unfused_node = false;    // CN_NODE_UNFUSED=1: one launch per layer (development A/B switch)
     CnEnv *refill_env = nullptr;  // cn_dsrnn_set_refill_env: start this env's spare-episode refill beside the attention kernel
+    cudaEvent_t edge_done = nullptr;   // cn_dsrnn_set_edge_event: recorded behind the edge stage of the next forwards
     bool timing;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;   // events around the edge stage
     int num_sms;
@@ -489,6 +490,7 @@ const char *dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, cons
     return dsrnn_tc_edge_sequence_step(m->tc_state, n_envs, human_num, io, stream);
 }
 void dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env) { m->refill_env = env; }
+void dsrnn_set_edge_event(CnDsrnn *m, void *event) { m->edge_done = (cudaEvent_t)event; }
 
 // one linear layer, on CUDA cores (fp32) or tensor cores (bf16x3 / bf16)
 struct LinearRun {
@@ -549,6 +551,9 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
         if (msg) return msg;
     }
     if (m->timing) cudaEventRecord(m->pending.back().second, s);
+    // the machine-filling part of the forward ends here; what follows (projection, attention, node / heads) leaves most SMs
+    // idle, so a caller that pipelines half batches (rollout.PipelinedRollout) starts the other half's crowd step on this event
+    if (m->edge_done && cudaEventRecord(m->edge_done, s) != cudaSuccess) return "cudaEventRecord (edge event) failed";
 
     LinearRun run{m, precision, s, &launches};
 

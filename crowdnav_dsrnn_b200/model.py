@@ -408,10 +408,19 @@ class Policy(nn.Module):
             _lib.check(_lib.load().cn_dsrnn_set_refill_env(self._handle, engine.handle if engine is not None else None),
                        "cn_dsrnn_set_refill_env")
 
-    def cuda_forward(self, inputs, rnn_hxs, masks, need_features=True, out=None):
+    def set_edge_event(self, event):
+        """Have the next forwards record `event` (a torch.cuda.Event, None clears it) right behind their edge-GRU stage, so
+        that another stream can start independent work beside the rest of the forward (rollout.PipelinedRollout)."""
+        if self._handle is None:
+            raise _lib.CrowdNavLibraryError("set_edge_event needs the library handle: run one forward first")
+        _lib.check(_lib.load().cn_dsrnn_set_edge_event(self._handle, C.c_void_p(event.cuda_event) if event is not None else None),
+                   "cn_dsrnn_set_edge_event")
+
+    def cuda_forward(self, inputs, rnn_hxs, masks, need_features=True, out=None, workspace=None):
         """One rollout-step forward on the GPU. Returns (value[N,1], mean[N,2], features[N,256]|None, h_node, h_edge).
         `out` = dict of preallocated outputs (h_node, h_edge, value, mean) for callers that need static addresses
-        (CUDA-graph capture, rollout.py)."""
+        (CUDA-graph capture, rollout.py); `workspace` = a caller-owned uint8 scratch tensor of at least
+        `cn_dsrnn_workspace_bytes(N, H)` bytes for forwards that run concurrently on several streams."""
         rn, te, se = inputs["robot_node"], inputs["temporal_edges"], inputs["spatial_edges"]
         device = se.device
         if device.type != "cuda":
@@ -435,17 +444,19 @@ class Policy(nn.Module):
                 if t_.numel() != numel or t_.dtype != torch.float32 or t_.device != device or not t_.is_contiguous():
                     raise ValueError("preallocated forward outputs have the wrong shape / dtype / device")
         feat = torch.empty(N, 256, **opts) if need_features else None
-        ws_key = (N, H, device)
-        if self.__dict__.get("_workspace_key") != ws_key:
-            nbytes = lib.cn_dsrnn_workspace_bytes(N, H)
-            if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
-                self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            self.__dict__["_workspace_key"] = ws_key
+        if workspace is None:
+            ws_key = (N, H, device)
+            if self.__dict__.get("_workspace_key") != ws_key:
+                nbytes = lib.cn_dsrnn_workspace_bytes(N, H)
+                if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
+                    self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                self.__dict__["_workspace_key"] = ws_key
+            workspace = self._workspace
         io = abi.CnDsrnnIO(_ptr(rn), _ptr(te), _ptr(se), _ptr(hn), _ptr(he), _ptr(mk), _ptr(hn_out), _ptr(he_out),
                            _ptr(value), _ptr(mean), _ptr(feat))
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         _lib.check(lib.cn_dsrnn_forward(self._handle, N, H, C.byref(io), abi.PRECISIONS[self.precision],
-                                        _ptr(self._workspace), self._workspace.numel(), stream), "cn_dsrnn_forward")
+                                        _ptr(workspace), workspace.numel(), stream), "cn_dsrnn_forward")
         self.gpu_launches += lib.cn_dsrnn_last_launches(self._handle)
         return value, mean, feat, hn_out, he_out
 

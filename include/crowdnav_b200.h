@@ -235,6 +235,10 @@ int cn_dsrnn_forward(CnDsrnn *m, int n_envs, int human_num, const CnDsrnnIO *io,
  * the persistent tensor-core kernels, whose register / shared-memory footprint is a whole SM).  Pair
  * cn_dsrnn_set_refill_env(m, env) with cn_env_step(..., auto_reset = 2, ...); env == NULL clears it. */
 int cn_dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env);
+/* Half-batch pipelining (rollout.PipelinedRollout): `event` (a cudaEvent_t owned by the caller, NULL clears it) is recorded on
+ * the forward's stream right behind the edge-GRU stage -- the last part of a forward that fills the machine -- so another
+ * stream can start the crowd step of an independent half batch beside the projection / attention / node kernels. */
+int cn_dsrnn_set_edge_event(CnDsrnn *m, void *event);
 /* number of kernels the last forward / step call launched (bench.py's gpu_launches claim) */
 int cn_dsrnn_last_launches(const CnDsrnn *m);
 int cn_env_last_launches(const CnEnv *env);
