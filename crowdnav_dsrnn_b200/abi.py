@@ -8,13 +8,15 @@ CrowdSim.configure (crowd_sim/envs/crowd_sim.py:93-246) and Agent.__init__
 import ctypes as C
 import math
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_HUMANS = 32
 MAX_SCENARIOS = 8
 STEP_TABLE_WORDS = 128
 INFO_DIM = 12
 
 HOLONOMIC, UNICYCLE = 0, 1
+POLICY_ORCA, POLICY_SOCIAL_FORCE = 0, 1
+HUMAN_POLICIES = {"orca": POLICY_ORCA, "social_force": POLICY_SOCIAL_FORCE}
 PHASE_TRAIN, PHASE_VAL, PHASE_TEST = 0, 1, 2
 PHASES = {"train": PHASE_TRAIN, "val": PHASE_VAL, "test": PHASE_TEST}
 EV_NOTHING, EV_DANGER, EV_REACH_GOAL, EV_COLLISION, EV_TIMEOUT = 0, 1, 2, 3, 4
@@ -53,6 +55,9 @@ class CnConfig(C.Structure):
         ("goal_change_chance", C.c_double), ("end_goal_change_chance", C.c_double),
         ("orca_neighbor_dist", C.c_float), ("orca_safety_space", C.c_float), ("orca_time_horizon", C.c_float),
         ("reserved1", C.c_float),
+        ("human_policy", C.c_int32), ("random_policy_changing", C.c_int32), ("random_unobservability", C.c_int32),
+        ("random_radii", C.c_int32), ("random_v_pref", C.c_int32), ("reserved2", C.c_int32),
+        ("unobservable_chance", C.c_double), ("sf_A", C.c_double), ("sf_B", C.c_double), ("sf_KI", C.c_double),
     ]
 
 
@@ -183,13 +188,21 @@ def flatten_config(config, n_envs, phase=None, seed=None, env_id_offset=0, nenv=
     """Build the CnConfig the C ABI consumes from a reference-shaped Config object."""
     c = CnConfig()
     c.abi_version = ABI_VERSION
-    if config.humans.policy != "orca":
-        raise NotImplementedError("humans.policy=%r (only 'orca' is on the hot path)" % (config.humans.policy,))
+    if config.humans.policy not in HUMAN_POLICIES:      # crowd_sim.py:106-127 raises for anything else too
+        raise NotImplementedError("humans.policy=%r (the reference's humans are 'orca' or 'social_force')" % (config.humans.policy,))
     if getattr(config.sim, "group_human", False) and not config.test.side_preference:
         raise NotImplementedError("sim.group_human=True is out of scope (SURVEY 8(f) N4)")
-    for flag in ("random_radii", "random_v_pref", "random_unobservability", "random_policy_changing"):
-        if getattr(config.humans, flag, False):
-            raise NotImplementedError("humans.%s=True is out of scope (SURVEY 8(f) N4)" % flag)
+    # optional human behaviours (SURVEY 8(f) N4)
+    c.human_policy = HUMAN_POLICIES[config.humans.policy]
+    c.random_policy_changing = int(bool(getattr(config.humans, "random_policy_changing", False)))
+    c.random_unobservability = int(bool(getattr(config.humans, "random_unobservability", False)))
+    c.random_radii = int(bool(getattr(config.humans, "random_radii", False)))
+    c.random_v_pref = int(bool(getattr(config.humans, "random_v_pref", False)))
+    c.unobservable_chance = float(getattr(config.humans, "unobservable_chance", 0.3))
+    sf = getattr(config, "sf", None)
+    c.sf_A = float(getattr(sf, "A", 2.0))
+    c.sf_B = float(getattr(sf, "B", 1.0))
+    c.sf_KI = float(getattr(sf, "KI", 1.0))
     if getattr(config.noise, "add_noise", False) or getattr(config.reward, "norm_zones", False):
         raise NotImplementedError("noise.add_noise / reward.norm_zones are out of scope (SURVEY 8(f) N4)")
     if getattr(config.lidar, "enable", False):

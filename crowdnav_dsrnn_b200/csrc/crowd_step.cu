@@ -159,11 +159,14 @@ __device__ __forceinline__ float2 preferred_velocity(float4 pv, float4 gr)
     return make_float2((float)(gsp > 1.0 ? gdx / gsp : gdx), (float)(gsp > 1.0 ? gdy / gsp : gdy));
 }
 
-// One human's ORCA solve by one G-lane group.  s_pv/s_gr/s_th: this env's humans (pre-step).
-template <int G>
+// One human's action by one G-lane group: the ORCA solve, or (kOpt builds only) the social-force step.
+// s_pv/s_gr/s_th: this env's humans (pre-step).  kOpt compiles the optional behaviours of SURVEY 8(f) N4 in
+// (humans.policy = social_force, random_policy_changing, random_unobservability); the default kernel has none of them.
+template <int G, bool kOpt>
 __device__ __forceinline__ float2 orca_group(const CnConfig &cfg, const GroupOps<G> &g, int i, int H,
                                              const float4 *s_pv, const float4 *s_gr, const float *s_th, float2 pref,
-                                             float4 rob_pv, float rob_radius, float rob_theta, float4 *s_scratch)
+                                             float4 rob_pv, float rob_radius, float rob_theta, float4 *s_scratch,
+                                             const EnvParams &P, int e)
 {
     const float4 me = s_pv[i];
     const float4 me_g = s_gr[i];
@@ -174,24 +177,58 @@ __device__ __forceinline__ float2 orca_group(const CnConfig &cfg, const GroupOps
     const int M = H - 1 + (cfg.robot_visible ? 1 : 0);
     const bool have = g.gl < M;
     float ox = 0.f, oy = 0.f, ovx = 0.f, ovy = 0.f, orad = 0.f;
+    double raw_r = 0.0;
+    int4 ctr = make_int4(0, 0, 0, 0);
+    if (kOpt) ctr = P.a.ctr[e];
     if (have) {
         const bool limited = cfg.human_fov < 2.0 * CN_PI;
         const double my_th = (limited && cfg.kinematics != CN_HOLONOMIC) ? (double)s_th[i] : 0.0;
         bool vis = true;
-        double raw_r;
+        // humans.random_unobservability (crowd_sim.py:1121-1153): human 0 misses each neighbour with unobservable_chance,
+        // one draw per (step, neighbour slot)
+        bool blind = false;
+        if (kOpt && cfg.random_unobservability && i == 0)
+            blind = u01(philox4x32(step_key(cfg, ctr.y, e), (uint32_t)g.gl, 0u, (uint32_t)ctr.x, RNG_UNOBS).x) <= cfg.unobservable_chance;
         if (g.gl < H - 1) {
             const int j = g.gl + (g.gl >= i ? 1 : 0);
             const float4 o = s_pv[j];
             ox = o.x; oy = o.y; ovx = o.z; ovy = o.w; raw_r = (double)s_gr[j].z;
             if (limited) vis = detect_visible_d(cfg.kinematics, me.x, me.y, me.z, me.w, my_th, ox, oy, cfg.human_fov);
+            if (kOpt && blind) vis = false;
             if (!vis) raw_r = cfg.human_radius;
         } else {
             ox = rob_pv.x; oy = rob_pv.y; ovx = rob_pv.z; ovy = rob_pv.w; raw_r = (double)rob_radius;
             if (limited) vis = detect_visible_d(cfg.kinematics, me.x, me.y, me.z, me.w, my_th, ox, oy, cfg.human_fov);
+            if (kOpt && blind) vis = false;
             if (!vis) raw_r = cfg.robot_radius;
         }
         if (!vis) { ox = 7.0f; oy = 7.0f; ovx = 0.0f; ovy = 0.0f; }   // dummy_human, crowd_sim.py:161-163
         orad = (float)(raw_r + 0.01 + (double)cfg.orca_safety_space);
+    }
+    if (kOpt && human_policy_of(cfg, ctr.z, e, i) == CN_POLICY_SOCIAL_FORCE) {
+        // SOCIAL_FORCE.predict (crowd_nav/policy/social_force.py:11-63), Python floats -> fp64.  Lane k owns the push of
+        // neighbour slot k; the sum runs in slot order like the reference's loop.
+        double tx = 0.0, ty = 0.0;
+        if (have) {
+            const double ddx = (double)me.x - (double)ox, ddy = (double)me.y - (double)oy;
+            const double dist = sqrt(ddx * ddx + ddy * ddy);
+            const double f = cfg.sf_A * exp(((double)me_g.z + raw_r - dist) / cfg.sf_B);
+            tx = f * (ddx / dist); ty = f * (ddy / dist);
+        }
+        double ivx = 0.0, ivy = 0.0;
+        for (int k = 0; k < M; ++k) {
+            const double ax = __hiloint2double(g.shfl_i(__double2hiint(tx), k), g.shfl_i(__double2loint(tx), k));
+            const double ay = __hiloint2double(g.shfl_i(__double2hiint(ty), k), g.shfl_i(__double2loint(ty), k));
+            ivx += ax; ivy += ay;
+        }
+        const double gdx = (double)me_g.x - (double)me.x, gdy = (double)me_g.y - (double)me.y;
+        const double gdist = sqrt(gdx * gdx + gdy * gdy);
+        const double vp = (double)me_g.w;
+        const double cdx = cfg.sf_KI * ((gdx / gdist) * vp - (double)me.z), cdy = cfg.sf_KI * ((gdy / gdist) * vp - (double)me.w);
+        const double nvx = (double)me.z + (cdx + ivx) * cfg.time_step, nvy = (double)me.w + (cdy + ivy) * cfg.time_step;
+        const double nrm = sqrt(nvx * nvx + nvy * nvy);
+        if (nrm > vp) return make_float2((float)(nvx / nrm * vp), (float)(nvy / nrm * vp));
+        return make_float2((float)nvx, (float)nvy);
     }
     (void)rob_theta;
 
@@ -574,6 +611,7 @@ __device__ __noinline__ void swap_in_spare(const EnvParams &P, const CnStepOut &
 }
 
 // one warp finishes one env: reward/done/info, integration, observation, goal updates
+template <bool kOpt>
 __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &out, const float *__restrict__ action, int e,
                                          int lane, float4 *s_pv, float4 *s_gr, const float2 *s_nv, int auto_reset)
 {
@@ -775,9 +813,18 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
         }
         for (unsigned todo = __ballot_sync(FULL, reached); todo; todo &= todo - 1u) {
             const int i = __ffs(todo) - 1;
-            const float4 gi = s_gr[i];
+            float4 gi = s_gr[i];
             const uint4 dec = philox4x32(key, RNG_DECISION, (uint32_t)i, su, RNG_GOAL_END);
             if (!(u01(dec.x) <= cfg.end_goal_change_chance)) continue;
+            if (kOpt && (cfg.random_radii | cfg.random_v_pref)) {
+                // humans.random_radii / random_v_pref (crowd_sim.py:779-786): the human that gets a new end goal also gets
+                // radius / v_pref += uniform(-0.1, 0.1); the goal search below already uses the new values
+                if (cfg.random_radii) gi.z = (float)((double)gi.z + (-0.1 + 0.2 * u01(dec.y)));
+                if (cfg.random_v_pref) gi.w = (float)((double)gi.w + (-0.1 + 0.2 * u01(dec.z)));
+                __syncwarp();
+                if (lane == 0) { s_gr[i] = gi; P.a.hum_gr[(size_t)e * H + i] = gi; }
+                __syncwarp();
+            }
             for (int t0 = 0; t0 < cfg.max_goal_tries; t0 += 32) {
                 const int t = t0 + lane;
                 const uint4 xa = philox4x32(key, (uint32_t)(2 * t), (uint32_t)i, su, RNG_GOAL_END);
@@ -844,7 +891,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
 // ---------------------------------------------------------------------------------------------- the kernel
 // grid: ceil(N / E) CTAs of 256 threads, each owning E consecutive envs.
 // dynamic smem: E*H*(float4 pv + float4 gr + float2 nv + float th) + 256 float4 sort scratch
-template <int G>
+template <int G, bool kOpt>
 __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS)
 crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnStepOut out,
                   const float *__restrict__ action, int E, int auto_reset)
@@ -898,7 +945,8 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
             if (i >= H) { i -= H; ++el; }
             const float4 rob = cfg.robot_visible ? s_rob_pv[el] : make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 rrt = cfg.robot_visible ? s_rob_rt[el] : make_float2(0.f, 0.f);
-            const float2 nv = orca_group<G>(cfg, g, i, H, s_pv + el * H, s_gr + el * H, s_th + el * H, s_nv[task], rob, rrt.x, rrt.y, scratch);
+            const float2 nv = orca_group<G, kOpt>(cfg, g, i, H, s_pv + el * H, s_gr + el * H, s_th + el * H, s_nv[task], rob, rrt.x, rrt.y,
+                                                  scratch, P, e0 + el);
             if (g.gl == 0) s_nv[task] = nv;
         }
     }
@@ -908,7 +956,7 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int el = warp; el < ne; el += STEP_THREADS / 32)
-            env_tail(P, out, action, e0 + el, lane, s_pv + el * H, s_gr + el * H, s_nv + el * H, auto_reset);
+            env_tail<kOpt>(P, out, action, e0 + el, lane, s_pv + el * H, s_gr + el * H, s_nv + el * H, auto_reset);
     }
 }
 
@@ -1013,7 +1061,7 @@ crowd_step_seq_kernel(const __grid_constant__ EnvParams P, const __grid_constant
 
     // phase B: one warp per env
     for (int el = threadIdx.x >> 5; el < ne; el += STEP_THREADS / 32)
-        env_tail(P, out, action, e0 + el, lane, s_pv + el * H, s_gr + el * H, s_nv + el * H, auto_reset);
+        env_tail<false>(P, out, action, e0 + el, lane, s_pv + el * H, s_gr + el * H, s_nv + el * H, auto_reset);
 }
 
 static inline int pick_group(int M)
@@ -1032,8 +1080,11 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     // CN_STEP_SEQ=1: the thread-per-human form of phase A.  Same bits; measured at 16384 envs x 20 humans it executes 30 %
     // fewer instructions than the group form but is latency-bound at the ~15 solver warps per SM its 400 B of shared memory
     // per human allow, so it is no faster (0.49-0.53 vs 0.51 ms, profiles/README.md) and stays a development switch.
+    // the optional human behaviours of SURVEY 8(f) N4 live in their own instantiation of the group form
+    const bool opt = P->cfg.human_policy != CN_POLICY_ORCA || P->cfg.random_policy_changing || P->cfg.random_unobservability ||
+                     P->cfg.random_radii || P->cfg.random_v_pref;
     bool seq = false;
-    if (const char *dbg = getenv("CN_STEP_SEQ")) seq = atoi(dbg) != 0 && M >= 1 && M <= 32;
+    if (const char *dbg = getenv("CN_STEP_SEQ")) seq = atoi(dbg) != 0 && M >= 1 && M <= 32 && !opt;
     if (seq) {
         int E = STEP_THREADS / H;           // one solve per thread
         E = E < 1 ? 1 : (E > 64 ? 64 : E);
@@ -1062,11 +1113,20 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     if (const char *dbg = getenv("CN_STEP_ENVS_PER_CTA")) { const int v = atoi(dbg); if (v >= 1 && v <= 64) E = v; }   // tuning knob
     const size_t smem = (size_t)E * H * (16 + 16 + 8 + 4) + STEP_THREADS * 16;
     const int grid = (P->n_envs + E - 1) / E;
+    if (opt) {
+        switch (G) {
+        case 4: crowd_step_kernel<4, true><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        case 8: crowd_step_kernel<8, true><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        case 16: crowd_step_kernel<16, true><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        default: crowd_step_kernel<32, true><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        }
+        return (int)cudaGetLastError();
+    }
     switch (G) {
-    case 4: crowd_step_kernel<4><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
-    case 8: crowd_step_kernel<8><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
-    case 16: crowd_step_kernel<16><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
-    default: crowd_step_kernel<32><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    case 4: crowd_step_kernel<4, false><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    case 8: crowd_step_kernel<8, false><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    case 16: crowd_step_kernel<16, false><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    default: crowd_step_kernel<32, false><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
     }
     return (int)cudaGetLastError();
 }

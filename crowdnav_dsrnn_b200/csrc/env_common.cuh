@@ -88,7 +88,7 @@ static inline size_t cn_carve(EnvArrays *a, void *base, int n, int H)
 }
 
 // ---------------------------------------------------------------- Philox4x32-10 (counter-based RNG contract)
-enum { RNG_RESET = 0, RNG_ATTR = 1, RNG_SPAWN = 2, RNG_GOAL_RANDOM = 3, RNG_GOAL_END = 4 };
+enum { RNG_RESET = 0, RNG_ATTR = 1, RNG_SPAWN = 2, RNG_GOAL_RANDOM = 3, RNG_GOAL_END = 4, RNG_UNOBS = 5, RNG_POLICY = 6 };
 #define RNG_DECISION 0xFFFFFFFFu
 
 __device__ __forceinline__ uint4 philox4x32(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
@@ -111,6 +111,23 @@ __device__ __forceinline__ uint64_t episode_key(const CnConfig &cfg, int case_co
 {
     return cfg.seed_offset + (uint64_t)(uint32_t)case_counter + cfg.base_seed +
            (uint64_t)(uint32_t)(cfg.env_id_offset + env_local);
+}
+
+// key of the episode an env is IN: reset() used episode_key(case_counter) and then advanced case_counter by nenv
+// (crowd_sim_dict.py:162-164), so the running episode's key is one stride back
+__device__ __forceinline__ uint64_t running_episode_key(const CnConfig &cfg, int case_counter, int env_local)
+{
+    const uint64_t cs = cfg.case_size;
+    const uint64_t prev = ((uint64_t)(uint32_t)case_counter + cs - (uint64_t)(uint32_t)cfg.nenv % cs) % cs;
+    return cfg.seed_offset + prev + cfg.base_seed + (uint64_t)(uint32_t)(cfg.env_id_offset + env_local);
+}
+
+// humans.random_policy_changing (crowd_sim.py:463-473): every human of an episode is ORCA or social force with equal
+// chance.  The choice is a pure function of (episode key, human), so it is recomputed where needed instead of stored.
+__device__ __forceinline__ int human_policy_of(const CnConfig &cfg, int case_counter, int env_local, int i)
+{
+    if (!cfg.random_policy_changing) return cfg.human_policy;
+    return (int)(philox4x32(running_episode_key(cfg, case_counter, env_local), 0u, (uint32_t)i, 0u, RNG_POLICY).x & 1u);
 }
 
 __device__ __forceinline__ uint64_t step_key(const CnConfig &cfg, int scenario_counter, int env_local)

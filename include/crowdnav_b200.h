@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CN_ABI_VERSION 2
+#define CN_ABI_VERSION 3
 #define CN_MAX_HUMANS 32          /* one 32-lane group per ORCA solve */
 #define CN_MAX_SCENARIOS 8
 #define CN_STEP_TABLE_WORDS 128   /* bit table over step indices: up to 4096 steps per episode */
@@ -39,6 +39,8 @@ enum {
     CN_SCN_PERPENDICULAR_TRAFFIC = 3, CN_SCN_SIDE_PREF_PASSING = 4, CN_SCN_SIDE_PREF_OVERTAKING = 5,
     CN_SCN_SIDE_PREF_CROSSING = 6
 };
+/* config.humans.policy (crowd_nav/policy/policy_factory.py): the humans' reactive policy */
+enum { CN_POLICY_ORCA = 0, CN_POLICY_SOCIAL_FORCE = 1 };
 /* event classes of crowd_sim/envs/utils/info.py:1-38 */
 enum { CN_EV_NOTHING = 0, CN_EV_DANGER = 1, CN_EV_REACH_GOAL = 2, CN_EV_COLLISION = 3, CN_EV_TIMEOUT = 4 };
 /* env.phase (pytorchBaselines/a2c_ppo_acktr/envs.py:70-73) */
@@ -101,6 +103,17 @@ typedef struct CnConfig {
     float orca_safety_space;
     float orca_time_horizon;
     float reserved1;
+    /* --- optional human behaviours (all off in the reference's default config) --- */
+    int32_t human_policy;             /* humans.policy: CN_POLICY_ORCA / CN_POLICY_SOCIAL_FORCE */
+    int32_t random_policy_changing;   /* humans.random_policy_changing: each human is ORCA or social force, drawn per episode
+                                         (crowd_sim.py:463-473, crowd_sim_dict.py:157-159) */
+    int32_t random_unobservability;   /* humans.random_unobservability: human 0 misses each neighbour with unobservable_chance
+                                         at every step (crowd_sim.py:1121-1153) */
+    int32_t random_radii;             /* humans.random_radii / random_v_pref: radius / v_pref += U(-0.1, 0.1) whenever a human */
+    int32_t random_v_pref;            /*   is given a new end goal (crowd_sim.py:779-786) */
+    int32_t reserved2;
+    double unobservable_chance;       /* humans.unobservable_chance */
+    double sf_A, sf_B, sf_KI;         /* sf.A, sf.B, sf.KI (crowd_nav/policy/social_force.py:22-27) */
 } CnConfig;
 
 /*

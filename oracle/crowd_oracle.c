@@ -6,7 +6,9 @@
  *
  *   clip_action            crowd_nav/policy/srnn.py:18-48
  *   unicycle accumulation  crowd_sim/envs/crowd_sim_dict.py:211-217
- *   get_human_actions      crowd_sim/envs/crowd_sim.py:1121-1161  (+ ORCA.predict, crowd_nav/policy/orca.py:64-139)
+ *   get_human_actions      crowd_sim/envs/crowd_sim.py:1121-1161  (+ ORCA.predict, crowd_nav/policy/orca.py:64-139;
+ *                          SOCIAL_FORCE.predict, crowd_nav/policy/social_force.py:11-63; random_unobservability;
+ *                          random_policy_changing, crowd_sim.py:463-473)
  *   detect_visible         crowd_sim/envs/crowd_sim.py:820-847
  *   calc_reward            crowd_sim/envs/crowd_sim.py:907-1094
  *   Agent.step             crowd_sim/envs/utils/agent.py:172-212
@@ -59,7 +61,7 @@ static void philox_u01(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, uint
     for (int i = 0; i < 4; ++i) u[i] = (double)x[i] * (1.0 / 4294967296.0);
 }
 
-enum { RNG_RESET = 0, RNG_ATTR = 1, RNG_SPAWN = 2, RNG_GOAL_RANDOM = 3, RNG_GOAL_END = 4 };
+enum { RNG_RESET = 0, RNG_ATTR = 1, RNG_SPAWN = 2, RNG_GOAL_RANDOM = 3, RNG_GOAL_END = 4, RNG_UNOBS = 5, RNG_POLICY = 6 };
 #define RNG_DECISION 0xFFFFFFFFu
 
 /* ------------------------------------------------------------------ per-env views */
@@ -163,43 +165,89 @@ static int inside_world(double px, double py, double r, double t)
     return 1;
 }
 
-/* ORCA.predict for human i (orca.py:64-139; get_human_actions crowd_sim.py:1121-1161) */
-static void human_orca(const Env *e, int i, float out[2])
+static uint64_t step_key(const Env *e);
+static uint64_t running_episode_key(const Env *e);
+
+/* what human i is shown of the others (get_human_actions, crowd_sim.py:1121-1157): the other humans in index order, then the
+ * robot when it is visible to humans; anyone outside the human's FOV -- or, for human 0 under humans.random_unobservability,
+ * missed with unobservable_chance (one draw per step and neighbour slot) -- is replaced by the dummy agent parked at (7, 7) */
+static size_t observed_others(const Env *e, int i, orc_v2 *o_pos, orc_v2 *o_vel, double *o_raw_r)
 {
     const CnConfig *cfg = e->cfg;
     const int H = e->H;
     const float *self = e->hum + 9 * i;
-    orc_v2 o_pos[ORC_MAX_LINES], o_vel[ORC_MAX_LINES];
-    float o_rad[ORC_MAX_LINES];
-    size_t m = 0;
     const int limited = cfg->human_fov < 2.0 * PI;
-    for (int j = 0; j < H; ++j) {
+    size_t m = 0;
+    for (int j = 0; j <= H; ++j) {
         if (j == i) continue;
-        const float *o = e->hum + 9 * j;
-        if (!limited || detect_visible(cfg, self, o, cfg->human_fov)) {
+        if (j == H && !cfg->robot_visible) break;
+        const float *o = (j == H) ? e->rob : e->hum + 9 * j;
+        int visible = !limited || detect_visible(cfg, self, o, cfg->human_fov);
+        if (cfg->random_unobservability && i == 0) {
+            double u[4];
+            philox_u01(step_key(e), (uint32_t)m, 0, (uint32_t)e->ctr[0], RNG_UNOBS, u);
+            if (u[0] <= cfg->unobservable_chance) visible = 0;
+        }
+        if (visible) {
             o_pos[m] = orc_mk(o[PX], o[PY]);
             o_vel[m] = orc_mk(o[VX], o[VY]);
-            o_rad[m] = (float)((double)o[RAD] + 0.01 + (double)cfg->orca_safety_space);
-        } else { /* dummy_human.set(7,7,7,7,0,0,0), crowd_sim.py:161-163 */
+            o_raw_r[m] = (double)o[RAD];
+        } else { /* dummy_human / dummy_robot .set(7,7,7,7,0,0,0), crowd_sim.py:161-168 */
             o_pos[m] = orc_mk(7.0f, 7.0f);
             o_vel[m] = orc_mk(0.0f, 0.0f);
-            o_rad[m] = (float)(cfg->human_radius + 0.01 + (double)cfg->orca_safety_space);
+            o_raw_r[m] = (j == H) ? cfg->robot_radius : cfg->human_radius;
         }
         ++m;
     }
-    if (cfg->robot_visible) {
-        const float *o = e->rob;
-        if (!limited || detect_visible(cfg, self, o, cfg->human_fov)) {
-            o_pos[m] = orc_mk(o[PX], o[PY]);
-            o_vel[m] = orc_mk(o[VX], o[VY]);
-            o_rad[m] = (float)((double)o[RAD] + 0.01 + (double)cfg->orca_safety_space);
-        } else {
-            o_pos[m] = orc_mk(7.0f, 7.0f);
-            o_vel[m] = orc_mk(0.0f, 0.0f);
-            o_rad[m] = (float)(cfg->robot_radius + 0.01 + (double)cfg->orca_safety_space);
-        }
-        ++m;
+    return m;
+}
+
+/* humans.random_policy_changing (crowd_sim.py:463-473): ORCA or social force per human and episode, equal chance; a pure
+ * function of (key of the running episode, human) */
+static int human_policy_of(const Env *e, int i)
+{
+    if (!e->cfg->random_policy_changing) return e->cfg->human_policy;
+    uint32_t x[4];
+    oracle_philox(running_episode_key(e), 0, (uint32_t)i, 0, RNG_POLICY, x);
+    return (int)(x[0] & 1u);
+}
+
+/* SOCIAL_FORCE.predict (social_force.py:11-63), Python floats -> double; the action is narrowed to the float32 state */
+static void human_social_force(const Env *e, int i, size_t m, const orc_v2 *o_pos, const double *o_raw_r, float out[2])
+{
+    const CnConfig *cfg = e->cfg;
+    const float *self = e->hum + 9 * i;
+    const double gdx = (double)self[GX] - (double)self[PX], gdy = (double)self[GY] - (double)self[PY];
+    const double gdist = sqrt(gdx * gdx + gdy * gdy);
+    const double vp = (double)self[VPREF];
+    const double cdx = cfg->sf_KI * ((gdx / gdist) * vp - (double)self[VX]);
+    const double cdy = cfg->sf_KI * ((gdy / gdist) * vp - (double)self[VY]);
+    double ivx = 0.0, ivy = 0.0;
+    for (size_t k = 0; k < m; ++k) {
+        const double ddx = (double)self[PX] - (double)o_pos[k].x, ddy = (double)self[PY] - (double)o_pos[k].y;
+        const double dist = sqrt(ddx * ddx + ddy * ddy);
+        const double f = cfg->sf_A * exp(((double)self[RAD] + o_raw_r[k] - dist) / cfg->sf_B);
+        ivx += f * (ddx / dist);
+        ivy += f * (ddy / dist);
     }
+    const double nvx = (double)self[VX] + (cdx + ivx) * cfg->time_step;
+    const double nvy = (double)self[VY] + (cdy + ivy) * cfg->time_step;
+    const double nrm = sqrt(nvx * nvx + nvy * nvy);
+    if (nrm > vp) { out[0] = (float)(nvx / nrm * vp); out[1] = (float)(nvy / nrm * vp); }
+    else { out[0] = (float)nvx; out[1] = (float)nvy; }
+}
+
+/* human i's action: ORCA.predict (orca.py:64-139) or SOCIAL_FORCE.predict on what it observes */
+static void human_action(const Env *e, int i, float out[2])
+{
+    const CnConfig *cfg = e->cfg;
+    const float *self = e->hum + 9 * i;
+    orc_v2 o_pos[ORC_MAX_LINES], o_vel[ORC_MAX_LINES];
+    double o_raw_r[ORC_MAX_LINES];
+    float o_rad[ORC_MAX_LINES];
+    const size_t m = observed_others(e, i, o_pos, o_vel, o_raw_r);
+    if (human_policy_of(e, i) == CN_POLICY_SOCIAL_FORCE) { human_social_force(e, i, m, o_pos, o_raw_r, out); return; }
+    for (size_t k = 0; k < m; ++k) o_rad[k] = (float)(o_raw_r[k] + 0.01 + (double)cfg->orca_safety_space);
     const double gx = (double)self[GX] - (double)self[PX], gy = (double)self[GY] - (double)self[PY];
     const double speed = norm2(gx, gy);
     double pvx = gx, pvy = gy;
@@ -326,6 +374,14 @@ static uint64_t episode_key(const Env *e)
     return e->cfg->seed_offset + (uint64_t)(uint32_t)e->ctr[2] + e->cfg->base_seed + e->env_gid;
 }
 
+/* reset() used episode_key() and then advanced case_counter by nenv: the key of the episode the env is IN is one stride back */
+static uint64_t running_episode_key(const Env *e)
+{
+    const uint64_t cs = e->cfg->case_size;
+    const uint64_t prev = ((uint64_t)(uint32_t)e->ctr[2] + cs - (uint64_t)(uint32_t)e->cfg->nenv % cs) % cs;
+    return e->cfg->seed_offset + prev + e->cfg->base_seed + e->env_gid;
+}
+
 static uint64_t step_key(const Env *e)
 {
     return (e->cfg->base_seed + e->env_gid) ^ ((uint64_t)(uint32_t)e->ctr[1] << 32) ^ 0x5EEDC0DE00000000ull;
@@ -385,6 +441,9 @@ static uint32_t goal_updates(const Env *e)
             if (!(norm2((double)h[GX] - (double)h[PX], (double)h[GY] - (double)h[PY]) < (double)h[RAD])) continue;
             philox_u01(key, RNG_DECISION, (uint32_t)i, s, RNG_GOAL_END, u);
             if (!(u[0] <= cfg->end_goal_change_chance)) continue;
+            /* humans.random_radii / random_v_pref (crowd_sim.py:779-786): += np.random.uniform(-0.1, 0.1) */
+            if (cfg->random_radii) h[RAD] = (float)((double)h[RAD] + (-0.1 + 0.2 * u[1]));
+            if (cfg->random_v_pref) h[VPREF] = (float)((double)h[VPREF] + (-0.1 + 0.2 * u[2]));
             for (int t = 0; t < cfg->max_goal_tries; ++t) {
                 double ua[4], ub[4], u6[6], px, py, gx, gy, hd, vp;
                 philox_u01(key, (uint32_t)(2 * t), (uint32_t)i, s, RNG_GOAL_END, ua);
@@ -522,7 +581,7 @@ static void step_env(const Env *e, int idx, const float *action, const CnStepOut
 
     /* human actions on the pre-step state */
     float hact[CN_MAX_HUMANS][2];
-    for (int i = 0; i < H; ++i) human_orca(e, i, hact[i]);
+    for (int i = 0; i < H; ++i) human_action(e, i, hact[i]);
 
     /* calc_reward on the pre-step state (crowd_sim.py:907-1094) */
     double dmin = INFINITY;

@@ -43,6 +43,12 @@ CASES = {
     # limited HUMAN field of view (dummy-human substitution, crowd_sim.py:1139-1142)
     "x_human_fov_h6": ({"humans.FOV": 1.0, "sim.human_num": 6}, 48, 707),
     "x_unicycle_fov_h5": ({"action_space.kinematics": "unicycle", "robot.FOV": 1.0}, 48, 808),
+    # social-force humans (crowd_nav/policy/social_force.py), plain and with limited human FOV + visible robot
+    "n4_social_force_h5": ({"humans.policy": "social_force"}, 96, 909),
+    "n4_social_force_fov_h8": ({"humans.policy": "social_force", "humans.FOV": 1.0, "robot.visible": True,
+                                "sim.human_num": 8}, 48, 1010),
+    "n4_social_force_uni_h10": ({"humans.policy": "social_force", "action_space.kinematics": "unicycle", "sim.human_num": 10,
+                                 "env.time_step": 0.1, "reward.discomfort_penalty_factor": 10 * 0.1}, 48, 1111),
 }
 COMMON = {"humans.random_goal_changing": False, "humans.end_goal_changing": False}
 

@@ -21,6 +21,13 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
 
 CASES = {
+    # the optional human behaviours -- social-force humans; human 0 randomly blind with radius / v_pref
+    # drifting at every new end goal.  (humans.random_policy_changing cannot run in the reference: crowd_sim.py:472-473 calls
+    # the policy constructors without their config and a Human.set_policy that does not exist.)
+    "n4_social_force_h5": dict(over={"humans.policy": "social_force"}, ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),
+    "n4_options_h5": dict(over={"humans.random_unobservability": True, "humans.unobservable_chance": 0.5,
+                                "humans.random_radii": True, "humans.random_v_pref": True},
+                          ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),
     # BASELINE.json configs[3]: test.social_metrics=True (circle_radius 4, sequential scenarios), holonomic, 5 humans
     "social_h5_holonomic": dict(over={"test.social_metrics": True, "sim.circle_radius": 4, "env.test_size": 2000},
                                 ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),

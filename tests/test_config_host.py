@@ -35,10 +35,15 @@ def test_step_tables_replay_float64_accumulation():
 
 
 def test_flatten_config_rejects_out_of_scope_flags():
+    for sec, attr, val in (("humans", "policy", "cadrl"), ("sim", "group_human", True), ("noise", "add_noise", True),
+                           ("reward", "norm_zones", True), ("lidar", "enable", True)):
+        c = Config()
+        setattr(getattr(c, sec), attr, val)
+        with pytest.raises(NotImplementedError):
+            abi.flatten_config(c, 4)
     c = Config()
-    c.humans.policy = "social_force"
-    with pytest.raises(NotImplementedError):
-        abi.flatten_config(c, 4)
+    c.humans.policy = "social_force"                          # supported since round 2
+    assert abi.flatten_config(c, 4).human_policy == abi.POLICY_SOCIAL_FORCE
     c = Config()
     c.sim.train_val_sim = "circle_crossing"
     with pytest.raises(TypeError):                            # crowd_sim.py:138-142

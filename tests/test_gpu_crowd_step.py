@@ -57,6 +57,14 @@ RANDOM_CASES = [
     ("h17", dict(human_num=17), 512),
     ("h32", dict(human_num=32), 256),
     ("h31_robot_visible", dict(human_num=31, **{"robot.visible": True}), 256),
+    # the optional human behaviours (their own instantiation of the kernel)
+    ("n4_social_force_h7", dict(human_num=7, **{"humans.policy": "social_force"}), 1024),
+    ("n4_mixed_policies_h12", dict(human_num=12, **{"humans.random_policy_changing": True, "robot.visible": True}), 512),
+    ("n4_unobservability_h6", dict(human_num=6, **{"humans.random_unobservability": True, "humans.unobservable_chance": 0.5}), 1024),
+    ("n4_random_radii_vpref_h5", dict(human_num=5, **{"humans.random_radii": True, "humans.random_v_pref": True}), 2048),
+    ("n4_everything_h20_uni", dict(human_num=20, kinematics="unicycle",
+                                   **{"humans.random_policy_changing": True, "humans.random_unobservability": True,
+                                      "humans.random_radii": True, "humans.random_v_pref": True, "humans.FOV": 1.5}), 512),
 ]
 
 
@@ -110,7 +118,10 @@ def test_reset_matches_oracle(kw):
 
 
 @pytest.mark.parametrize("kw,steps", [(dict(human_num=5), 120), (dict(human_num=10, kinematics="unicycle"), 60),
-                                      (dict(human_num=20, **{"robot.FOV": 0.5}), 40)], ids=["h5", "h10_uni", "h20_fov"])
+                                      (dict(human_num=20, **{"robot.FOV": 0.5}), 40),
+                                      (dict(human_num=8, **{"humans.random_policy_changing": True, "humans.random_unobservability": True,
+                                                            "humans.random_radii": True, "humans.random_v_pref": True}), 100)],
+                         ids=["h5", "h10_uni", "h20_fov", "n4_options_h8"])
 def test_rollout_tracks_oracle(kw, steps):
     """Multi-step trajectory (auto-reset + goal re-sampling on) with a fixed action tape: the CUDA path and the
     oracle must stay in lock-step; flags are compared every step."""
