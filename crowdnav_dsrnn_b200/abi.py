@@ -11,6 +11,7 @@ import math
 ABI_VERSION = 3
 MAX_HUMANS = 32
 MAX_SCENARIOS = 8
+MAX_GROUPS = 8
 STEP_TABLE_WORDS = 128
 INFO_DIM = 12
 
@@ -56,7 +57,7 @@ class CnConfig(C.Structure):
         ("orca_neighbor_dist", C.c_float), ("orca_safety_space", C.c_float), ("orca_time_horizon", C.c_float),
         ("reserved1", C.c_float),
         ("human_policy", C.c_int32), ("random_policy_changing", C.c_int32), ("random_unobservability", C.c_int32),
-        ("random_radii", C.c_int32), ("random_v_pref", C.c_int32), ("reserved2", C.c_int32),
+        ("random_radii", C.c_int32), ("random_v_pref", C.c_int32), ("group_human", C.c_int32),
         ("unobservable_chance", C.c_double), ("sf_A", C.c_double), ("sf_B", C.c_double), ("sf_KI", C.c_double),
     ]
 
@@ -66,7 +67,7 @@ _fp = C.c_void_p
 
 class CnStateView(C.Structure):
     _fields_ = [("robot", _fp), ("humans", _fp), ("belief", _fp), ("extras", _fp), ("counters", _fp),
-                ("episode_return", _fp)]
+                ("episode_return", _fp), ("groups", _fp)]
 
 
 class CnObsOut(C.Structure):
@@ -190,21 +191,22 @@ def flatten_config(config, n_envs, phase=None, seed=None, env_id_offset=0, nenv=
     c.abi_version = ABI_VERSION
     if config.humans.policy not in HUMAN_POLICIES:      # crowd_sim.py:106-127 raises for anything else too
         raise NotImplementedError("humans.policy=%r (the reference's humans are 'orca' or 'social_force')" % (config.humans.policy,))
-    if getattr(config.sim, "group_human", False) and not config.test.side_preference:
-        raise NotImplementedError("sim.group_human=True is out of scope (SURVEY 8(f) N4)")
     # optional human behaviours
     c.human_policy = HUMAN_POLICIES[config.humans.policy]
     c.random_policy_changing = int(bool(getattr(config.humans, "random_policy_changing", False)))
     c.random_unobservability = int(bool(getattr(config.humans, "random_unobservability", False)))
     c.random_radii = int(bool(getattr(config.humans, "random_radii", False)))
     c.random_v_pref = int(bool(getattr(config.humans, "random_v_pref", False)))
+    c.group_human = int(bool(getattr(config.sim, "group_human", False)) and not config.test.side_preference)   # crowd_sim.py:123-125
     c.unobservable_chance = float(getattr(config.humans, "unobservable_chance", 0.3))
     sf = getattr(config, "sf", None)
     c.sf_A = float(getattr(sf, "A", 2.0))
     c.sf_B = float(getattr(sf, "B", 1.0))
     c.sf_KI = float(getattr(sf, "KI", 1.0))
-    if getattr(config.noise, "add_noise", False) or getattr(config.reward, "norm_zones", False):
-        raise NotImplementedError("noise.add_noise / reward.norm_zones are out of scope (SURVEY 8(f) N4)")
+    # noise.add_noise is accepted and has no effect, exactly as in the reference: only the base CrowdSim.generate_ob applies
+    # apply_noise (crowd_sim.py:1115-1116); CrowdSimDict overrides generate_ob without it (crowd_sim_dict.py:71-103)
+    if getattr(config.reward, "norm_zones", False):
+        raise NotImplementedError("reward.norm_zones is degenerate in the reference (DESIGN.md section 4) and not reproduced")
     if getattr(config.lidar, "enable", False):
         raise NotImplementedError("lidar is out of scope (SURVEY section 2 row 18)")
     c.human_num = int(config.sim.human_num)

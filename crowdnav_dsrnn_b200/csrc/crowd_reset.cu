@@ -27,6 +27,133 @@ __device__ __forceinline__ int cta_first_ok(bool ok, int *s_vote)
     return first == 0x7fffffff ? -1 : first;
 }
 
+// generate_robot_humans of the GROUP environment (sim.group_human, crowd_sim.py:559-622): circles of 4-9 static humans
+// (generate_circle_group_obstacle, :476-518) around random centres in [-3, 3]^2 until at most 4 humans are left, those walk
+// (generate_circle_crossing_human with the group collision rule, :371-372); the robot starts on the circle of radius 5.5 at a
+// random angle and its goal lies opposite, both stepped by 0.2 rad past the groups.  Same CTA-parallel bounded tries and Philox
+// contract as the plain spawn (oracle/crowd_oracle.c restates it sequentially).
+__device__ __noinline__ void reset_group_env(const EnvParams &P, int e, uint64_t key, int scenario, float4 *dst_pv, float4 *dst_gr,
+                                             float *dst_th, float4 *dst_grp, int *s_vote, double *s_pick, float4 &rpv_out, float4 &rgr_out)
+{
+    __shared__ float4 s_grp[CN_MAX_GROUPS];
+    __shared__ float4 s_pv[CN_MAX_HUMANS], s_gr[CN_MAX_HUMANS];
+    const CnConfig &cfg = P.cfg;
+    const int H = cfg.human_num, tid = threadIdx.x;
+    __syncthreads();
+    if (tid < CN_MAX_GROUPS) s_grp[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    int left = H, idx = 0, ng = 0;
+    while (left > 0) {
+        if (left <= 4) {
+            for (; idx < H; ++idx) {
+                double v_pref = cfg.human_v_pref, radius = cfg.human_radius;
+                if (cfg.randomize_attributes) {
+                    const uint4 x = philox4x32(key, 0, (uint32_t)idx, 0, RNG_ATTR);
+                    v_pref = 0.5 + (1.5 - 0.5) * u01(x.x);
+                    radius = 0.3 + (0.5 - 0.3) * u01(x.y);
+                }
+                const float radius_f = (float)radius;
+                SpawnCand c;
+                c.px = c.py = c.gx = c.gy = c.heading = c.v_pref = 0.0;
+                for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += RESET_THREADS) {
+                    const int t = t0 + tid;
+                    const uint4 xa = philox4x32(key, (uint32_t)t, (uint32_t)idx, 0, RNG_SPAWN);
+                    const uint4 xb = philox4x32(key, (uint32_t)t, (uint32_t)idx, 1, RNG_SPAWN);
+                    const double u6[6] = {u01(xa.x), u01(xa.y), u01(xa.z), u01(xa.w), u01(xb.x), u01(xb.y)};
+                    c = agent_attributes(cfg, scenario, (double)radius_f, v_pref, (double)(float)cfg.robot_radius, u6);
+                    const bool ok = t < cfg.max_spawn_tries &&
+                                    !collides_with_groups(s_grp, c.px, c.py, (double)radius_f, 2 * 0.5, s_pv, s_gr, idx, true);
+                    int src = cta_first_ok(ok, s_vote);
+                    if (src < 0 && t0 + RESET_THREADS >= cfg.max_spawn_tries) src = (cfg.max_spawn_tries - 1) - t0;     // keep the last try
+                    if (src >= 0) {
+                        if (tid == src) { s_pick[0] = c.px; s_pick[1] = c.py; s_pick[2] = c.gx; s_pick[3] = c.gy; s_pick[4] = c.heading; s_pick[5] = c.v_pref; }
+                        __syncthreads();
+                        c.px = s_pick[0]; c.py = s_pick[1]; c.gx = s_pick[2]; c.gy = s_pick[3]; c.heading = s_pick[4]; c.v_pref = s_pick[5];
+                        break;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    const size_t hi = (size_t)e * H + idx;
+                    s_pv[idx] = make_float4((float)c.px, (float)c.py, 0.0f, 0.0f);
+                    s_gr[idx] = make_float4((float)c.gx, (float)c.gy, radius_f, (float)c.v_pref);
+                    dst_pv[hi] = s_pv[idx]; dst_gr[hi] = s_gr[idx]; dst_th[hi] = (float)c.heading;
+                }
+                __syncthreads();
+            }
+            left = 0;
+        } else {
+            const int max_rand = left < 10 ? left : 10;
+            int circum = 4 + (int)(u01(philox4x32(key, (uint32_t)ng, 0, 0, RNG_GROUP).x) * (double)(max_rand - 4));     // randint(4, max_rand)
+            if (circum > max_rand - 1) circum = max_rand - 1;
+            const double g_radius = cfg.human_radius * 2.0 * circum / (2.0 * CN_PI);
+            double cx = 0.0, cy = 0.0;
+            for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += RESET_THREADS) {
+                const int t = t0 + tid;
+                const uint4 x = philox4x32(key, (uint32_t)t, (uint32_t)ng, 1, RNG_GROUP);
+                cx = -3.0 + 6.0 * u01(x.x); cy = -3.0 + 6.0 * u01(x.y);
+                bool ok = t < cfg.max_spawn_tries;
+                for (int g = 0; g < ng; ++g) {
+                    const float4 q = s_grp[g];
+                    if (norm2d(cx - (double)q.y, cy - (double)q.z) < g_radius + (double)q.x + 2.0 * cfg.human_radius) ok = false;
+                }
+                int src = cta_first_ok(ok, s_vote);
+                if (src < 0 && t0 + RESET_THREADS >= cfg.max_spawn_tries) src = (cfg.max_spawn_tries - 1) - t0;
+                if (src >= 0) {
+                    if (tid == src) { s_pick[0] = cx; s_pick[1] = cy; }
+                    __syncthreads();
+                    cx = s_pick[0]; cy = s_pick[1];
+                    break;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_grp[ng] = make_float4((float)g_radius, (float)cx, (float)cy, 1.0f);
+            __syncthreads();
+            if (tid < circum) {
+                const float4 q = s_grp[ng];
+                const double angle = (2.0 * CN_PI / circum) * tid;
+                const float px = (float)((double)q.y + (double)q.x * cos(angle)), py = (float)((double)q.z + (double)q.x * sin(angle));
+                const size_t hi = (size_t)e * H + idx + tid;
+                s_pv[idx + tid] = make_float4(px, py, 0.0f, 0.0f);
+                s_gr[idx + tid] = make_float4(px, py, (float)cfg.human_radius, 0.0f);      // static: goal = position, v_pref = 0
+                dst_pv[hi] = s_pv[idx + tid]; dst_gr[hi] = s_gr[idx + tid]; dst_th[hi] = 0.0f;
+            }
+            __syncthreads();
+            idx += circum; left -= circum; ++ng;
+        }
+    }
+    if (tid < CN_MAX_GROUPS) dst_grp[tid] = s_grp[tid];
+    // robot start / goal: thread t evaluates the t-th 0.2 rad increment (accumulated like the reference's `+= 0.2`)
+    const double rand_angle = u01(philox4x32(key, 0, 0, 2, RNG_GROUP).x) * CN_PI * 2.0;
+    double inc = 0.0;
+    for (int k = 0; k < tid && k < 63; ++k) inc = inc + 0.2;
+    double px = cos(rand_angle + inc) * 5.5, py = sin(rand_angle + inc) * 5.5;
+    {
+        const bool ok = tid < 64 && !collides_with_groups(s_grp, px, py, cfg.robot_radius, 2 * 0.5, s_pv, s_gr, H, true);
+        int src = cta_first_ok(ok, s_vote);
+        const bool none = src < 0;
+        if (none) src = 63;
+        if (tid == src) { s_pick[0] = px; s_pick[1] = py; s_pick[2] = none ? inc + 0.2 : inc; }
+        __syncthreads();
+        px = s_pick[0]; py = s_pick[1]; inc = s_pick[2];
+        __syncthreads();
+    }
+    inc = inc + CN_PI;
+    for (int k = 0; k < tid && k < 63; ++k) inc = inc + 0.2;
+    double gx = cos(rand_angle + inc) * 5.5, gy = sin(rand_angle + inc) * 5.5;
+    {
+        const bool ok = tid < 64 && !collides_with_groups(s_grp, gx, gy, cfg.robot_radius, 4 * 0.5, s_pv, s_gr, H, false);
+        int src = cta_first_ok(ok, s_vote);
+        if (src < 0) src = 63;
+        if (tid == src) { s_pick[0] = gx; s_pick[1] = gy; }
+        __syncthreads();
+        gx = s_pick[0]; gy = s_pick[1];
+        __syncthreads();
+    }
+    rpv_out = make_float4((float)px, (float)py, 0.0f, 0.0f);
+    rgr_out = make_float4((float)gx, (float)gy, (float)cfg.robot_radius, (float)cfg.robot_v_pref);
+}
+
 // grid: one CTA of RESET_THREADS threads per env (envs whose mask byte is 0 exit at once); thread t evaluates try
 // t, t+RESET_THREADS, ... of each bounded rejection loop, so a typical spawn needs a single round per human.
 // (-DRESET_PROFILE prints per-env cycle counts of the phases; tools/reset_stats.py summarises them.)
@@ -40,6 +167,7 @@ __device__ __forceinline__ int cta_first_ok(bool ok, int *s_vote)
 //                      a small grid instead of one (mostly idle) CTA per env
 enum { CN_RESET_LIVE = 0, CN_RESET_SPARE = 1, CN_RESET_SYNC = 2, CN_RESET_SPARE_LIST = 3 };
 
+template <bool kGroup>      // kGroup: the group environment (its own instantiation: the plain reset keeps its registers)
 __global__ void __launch_bounds__(RESET_THREADS)
 crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnObsOut obs,
                    const uint8_t *mask, int mode)
@@ -86,8 +214,16 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
     const int scenario = cfg.scenarios[scn_idx];
     const double R = cfg.circle_radius;
 
+    float4 rpv, rgr;
+    double rth;
+    if (kGroup) {
+        // ---- the group environment spawns its humans first and the robot around them (crowd_sim.py:559-622)
+        reset_group_env(P, e, key, scenario, dst_pv, dst_gr, dst_th, (spare ? P.a.sp_grp : P.a.grp) + (size_t)e * CN_MAX_GROUPS,
+                        s_vote, s_pick, rpv, rgr);
+        rth = CN_PI / 2.0;
+    } else {
     // ---- robot (crowd_sim.py:626-660)
-    double rpx, rpy, rgx = 0.0, rgy = 0.0, rth;
+    double rpx, rpy, rgx = 0.0, rgy = 0.0;
     if (cfg.kinematics == CN_UNICYCLE || !(cfg.social_metrics || cfg.side_preference)) {
         const bool uni = cfg.kinematics == CN_UNICYCLE;
         const double angle = u01(g0.y) * CN_PI * 2.0;
@@ -116,8 +252,8 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
     } else {
         rpx = 0.0; rpy = -R; rgx = 0.0; rgy = R; rth = CN_PI / 2.0;
     }
-    const float4 rpv = make_float4((float)rpx, (float)rpy, 0.0f, 0.0f);
-    const float4 rgr = make_float4((float)rgx, (float)rgy, (float)cfg.robot_radius, (float)cfg.robot_v_pref);
+    rpv = make_float4((float)rpx, (float)rpy, 0.0f, 0.0f);
+    rgr = make_float4((float)rgx, (float)rgy, (float)cfg.robot_radius, (float)cfg.robot_v_pref);
 
 #ifdef RESET_PROFILE
     const long long pt1 = clock64();
@@ -210,6 +346,7 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
         }
         __syncthreads();
     }
+    }   // !group_human
 
 #ifdef RESET_PROFILE
     if (tid == 0 && e < 1500) printf("reset e=%d scn=%d robot %lld first-half %lld second-half %lld cycles, %d rounds | draw %lld collide %lld vote %lld\n", e, scenario,
@@ -320,6 +457,14 @@ __global__ void state_convert_kernel(const __grid_constant__ EnvParams P, const 
             if (dir == 0) rx.w = v.episode_return[idx]; else v.episode_return[idx] = rx.w;
         }
         if (dir == 0) P.a.rob_x[idx] = rx;
+        if (v.groups) {
+            for (int g = 0; g < CN_MAX_GROUPS; ++g) {
+                float *q = v.groups + (idx * CN_MAX_GROUPS + g) * 4;
+                float4 &d = P.a.grp[idx * CN_MAX_GROUPS + g];
+                if (dir == 0) d = make_float4(q[0], q[1], q[2], q[3]);
+                else { q[0] = d.x; q[1] = d.y; q[2] = d.z; q[3] = d.w; }
+            }
+        }
         if (v.counters) {
             int32_t *c = v.counters + idx * 4;
             if (dir == 0) P.a.ctr[idx] = make_int4(c[0], c[1], c[2], c[3]);
@@ -334,7 +479,8 @@ extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, co
     // the fall-back normally finds nothing to do: a small grid that strides over the envs keeps its launch cheap
     const int small = mode == CN_RESET_SPARE_LIST ? 1184 : 592;
     const int grid = (mode == CN_RESET_SYNC || mode == CN_RESET_SPARE_LIST) ? (P->n_envs < small ? P->n_envs : small) : P->n_envs;
-    crowd_reset_kernel<<<grid, RESET_THREADS, 0, stream>>>(*P, obs ? *obs : none, mask, mode);
+    if (P->cfg.group_human) crowd_reset_kernel<true><<<grid, RESET_THREADS, 0, stream>>>(*P, obs ? *obs : none, mask, mode);
+    else crowd_reset_kernel<false><<<grid, RESET_THREADS, 0, stream>>>(*P, obs ? *obs : none, mask, mode);
     return (int)cudaGetLastError();
 }
 

@@ -546,9 +546,12 @@ __device__ __forceinline__ bool inside_world_d(double px, double py, double r, d
 }
 
 // does goal (gx,gy) of human i come within min_dist of any other agent's position or goal (crowd_sim.py:750-759)
+// (kOpt builds, group environment: check_collision_group instead, crowd_sim.py:747-748, 792-793)
+template <bool kOpt>
 __device__ __forceinline__ bool goal_collides(const CnConfig &cfg, int H, int i, double gx, double gy, const float4 *s_pv,
-                                              const float4 *s_gr, float4 rob_pv, float4 rob_gr)
+                                              const float4 *s_gr, float4 rob_pv, float4 rob_gr, const float4 *grp)
 {
+    if (kOpt && cfg.group_human) return collides_with_groups(grp, gx, gy, (double)s_gr[i].z, 2 * 0.5, s_pv, s_gr, H, true);
     const double ri = (double)s_gr[i].z, dd = cfg.discomfort_dist;
     {
         const double md = ri + (double)rob_gr.z + dd;
@@ -580,6 +583,7 @@ __device__ __noinline__ void swap_in_spare(const EnvParams &P, const CnStepOut &
             P.a.hum_gr[hi] = P.a.sp_gr[hi];
             P.a.hum_th[hi] = P.a.sp_th[hi];
         }
+        if (cfg.group_human && lane < CN_MAX_GROUPS) P.a.grp[(size_t)e * CN_MAX_GROUPS + lane] = P.a.sp_grp[(size_t)e * CN_MAX_GROUPS + lane];
         const float4 npv = P.a.sp_rob_pv[e], ngr = P.a.sp_rob_gr[e];
         const float nth = P.a.sp_theta[e];
         ctr.x = 0;
@@ -772,6 +776,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
 
     // ---- goal re-sampling (crowd_sim_dict.py:261-269; crowd_sim.py:724-811), bounded tries, lane t <-> try t
     unsigned changed = 0u;
+    const float4 *grp = P.a.grp + (size_t)e * CN_MAX_GROUPS;      // group environment only (kOpt builds)
     const uint32_t su = (uint32_t)ctr.x;
     const uint64_t key = step_key(cfg, ctr.y, e);
     if (cfg.random_goal_changing && su < 32u * CN_STEP_TABLE_WORDS && ((cfg.goal_change_steps[su >> 5] >> (su & 31)) & 1u)) {
@@ -787,7 +792,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
                 const double vp = (double)gi.w;
                 const double gx = cfg.circle_radius * cos(angle) + (u01(x.y) - 0.5) * vp;
                 const double gy = cfg.circle_radius * sin(angle) + (u01(x.z) - 0.5) * vp;
-                const bool ok = t < cfg.max_goal_tries && !goal_collides(cfg, H, i, gx, gy, s_pv, s_gr, rpv, rgr);
+                const bool ok = t < cfg.max_goal_tries && !goal_collides<kOpt>(cfg, H, i, gx, gy, s_pv, s_gr, rpv, rgr, grp);
                 const unsigned okb = __ballot_sync(FULL, ok);
                 if (okb) {
                     const int src = __ffs(okb) - 1;
@@ -831,7 +836,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
                 const uint4 xb = philox4x32(key, (uint32_t)(2 * t + 1), (uint32_t)i, su, RNG_GOAL_END);
                 const double u6[6] = {u01(xa.x), u01(xa.y), u01(xa.z), u01(xa.w), u01(xb.x), u01(xb.y)};
                 const SpawnCand c = agent_attributes(cfg, ctr.w, (double)gi.z, (double)gi.w, (double)rgr.z, u6);
-                const bool ok = t < cfg.max_goal_tries && !goal_collides(cfg, H, i, c.gx, c.gy, s_pv, s_gr, rpv, rgr);
+                const bool ok = t < cfg.max_goal_tries && !goal_collides<kOpt>(cfg, H, i, c.gx, c.gy, s_pv, s_gr, rpv, rgr, grp);
                 const unsigned okb = __ballot_sync(FULL, ok);
                 if (okb) {
                     const int src = __ffs(okb) - 1;
@@ -1082,7 +1087,7 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     // per human allow, so it is no faster (0.49-0.53 vs 0.51 ms, profiles/README.md) and stays a development switch.
     // the optional human behaviours of SURVEY 8(f) N4 live in their own instantiation of the group form
     const bool opt = P->cfg.human_policy != CN_POLICY_ORCA || P->cfg.random_policy_changing || P->cfg.random_unobservability ||
-                     P->cfg.random_radii || P->cfg.random_v_pref;
+                     P->cfg.random_radii || P->cfg.random_v_pref || P->cfg.group_human;
     bool seq = false;
     if (const char *dbg = getenv("CN_STEP_SEQ")) seq = atoi(dbg) != 0 && M >= 1 && M <= 32 && !opt;
     if (seq) {

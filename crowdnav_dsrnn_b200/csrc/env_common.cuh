@@ -18,6 +18,7 @@
 //   sp_meta int4[N]        valid, case_counter and scenario_counter the spare was generated for, scenario
 //   need_spare / need_sync uint8[N], sync_count int[4], refill_list int[N]   work flags / list for the refill and the
 //                          synchronous fall-back
+//   grp / sp_grp float4[N*CN_MAX_GROUPS]  group environment: the circle groups of the running / spare episode
 // Humans of one env are contiguous, envs are contiguous: a CTA that owns E
 // consecutive envs reads E*H consecutive float4 (fully coalesced 16 B accesses).
 #pragma once
@@ -41,6 +42,7 @@ struct EnvArrays {
     uint8_t *need_spare, *need_sync;
     int *sync_count;          // [0] envs flagged in need_sync, [1] CTAs done (sync), [2] entries of refill_list, [3] CTAs done (refill)
     int *refill_list;         // envs whose spare was consumed by the last step (compact: the refill launches a small grid)
+    float4 *grp, *sp_grp;     // group environment: [N * CN_MAX_GROUPS] radius, centre x, centre y, valid of the episode's circle groups
 };
 
 struct EnvParams {
@@ -83,12 +85,14 @@ static inline size_t cn_carve(EnvArrays *a, void *base, int n, int H)
     CN_TAKE(need_sync, uint8_t, n);
     CN_TAKE(sync_count, int, 4);
     CN_TAKE(refill_list, int, n);
+    CN_TAKE(grp, float4, (size_t)n * CN_MAX_GROUPS);
+    CN_TAKE(sp_grp, float4, (size_t)n * CN_MAX_GROUPS);
 #undef CN_TAKE
     return off;
 }
 
 // ---------------------------------------------------------------- Philox4x32-10 (counter-based RNG contract)
-enum { RNG_RESET = 0, RNG_ATTR = 1, RNG_SPAWN = 2, RNG_GOAL_RANDOM = 3, RNG_GOAL_END = 4, RNG_UNOBS = 5, RNG_POLICY = 6 };
+enum { RNG_RESET = 0, RNG_ATTR = 1, RNG_SPAWN = 2, RNG_GOAL_RANDOM = 3, RNG_GOAL_END = 4, RNG_UNOBS = 5, RNG_POLICY = 6, RNG_GROUP = 7 };
 #define RNG_DECISION 0xFFFFFFFFu
 
 __device__ __forceinline__ uint4 philox4x32(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
@@ -172,6 +176,27 @@ __device__ __forceinline__ bool detect_visible_d(int kinematics, double p1x, dou
     if (d != d) return false;
     d = d < -1.0 ? -1.0 : (d > 1.0 ? 1.0 : d);
     return fabs(acos(d)) <= fov / 2.0;
+}
+
+// check_collision_group (crowd_sim.py:520-538): does a disc of `radius` at (x, y) touch a circle group (centre distance <=
+// group radius + radius + margin; the reference uses 2 * 0.5 for positions / human goals, 4 * 0.5 for the robot goal) or,
+// when `movers` is set, a moving (non-obstacle: v_pref != 0) human among the first n_h entries of pv / gr
+__device__ __forceinline__ bool collides_with_groups(const float4 *grp, double x, double y, double radius, double margin,
+                                                     const float4 *pv, const float4 *gr, int n_h, bool movers)
+{
+    for (int g = 0; g < CN_MAX_GROUPS; ++g) {
+        const float4 q = grp[g];
+        if (q.w == 0.0f) break;
+        if (norm2d(x - (double)q.y, y - (double)q.z) <= (double)q.x + radius + margin) return true;
+    }
+    if (movers)
+        for (int k = 0; k < n_h; ++k) {
+            const float4 g4 = gr[k];
+            if (g4.w == 0.0f) continue;                         // isObstacle: static humans have v_pref 0
+            const float4 p = pv[k];
+            if (norm2d(x - (double)p.x, y - (double)p.y) <= (double)g4.z + radius) return true;
+        }
+    return false;
 }
 
 // observation right after a reset (one warp per env, lane i <-> human i); used by the reset kernel and by the step

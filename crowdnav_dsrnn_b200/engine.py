@@ -67,7 +67,7 @@ class StepBuffers:
 
 
 class CrowdEngine:
-    STATE_FIELDS = ("robot", "humans", "belief", "extras", "counters", "episode_return")
+    STATE_FIELDS = ("robot", "humans", "belief", "extras", "counters", "episode_return", "groups")
 
     def __init__(self, config, n_envs, device, phase=None, seed=None, env_id_offset=0, nenv=None, **tries):
         device = torch.device(device)
@@ -156,6 +156,7 @@ class CrowdEngine:
             "belief": torch.zeros(self.n, self.h, 5, **f32), "extras": torch.zeros(self.n, 4, **f32),
             "counters": torch.zeros(self.n, 4, dtype=torch.int32, device=self.device),
             "episode_return": torch.zeros(self.n, **f32),
+            "groups": torch.zeros(self.n, abi.MAX_GROUPS, 4, **f32),      # group environment: radius, cx, cy, valid
         }
 
     def get_state(self):

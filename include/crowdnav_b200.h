@@ -27,6 +27,7 @@ extern "C" {
 #define CN_ABI_VERSION 3
 #define CN_MAX_HUMANS 32          /* one 32-lane group per ORCA solve */
 #define CN_MAX_SCENARIOS 8
+#define CN_MAX_GROUPS 8            /* circle groups per episode: every group takes at least 4 of the <= 32 humans */
 #define CN_STEP_TABLE_WORDS 128   /* bit table over step indices: up to 4096 steps per episode */
 
 enum { CN_OK = 0, CN_ERR_ARG = -1, CN_ERR_CUDA = -2, CN_ERR_UNSUPPORTED = -3, CN_ERR_STATE = -4 };
@@ -111,7 +112,7 @@ typedef struct CnConfig {
                                          at every step (crowd_sim.py:1121-1153) */
     int32_t random_radii;             /* humans.random_radii / random_v_pref: radius / v_pref += U(-0.1, 0.1) whenever a human */
     int32_t random_v_pref;            /*   is given a new end goal (crowd_sim.py:779-786) */
-    int32_t reserved2;
+    int32_t group_human;              /* sim.group_human (and not test.side_preference): the group environment, crowd_sim.py:476-622 */
     double unobservable_chance;       /* humans.unobservable_chance */
     double sf_A, sf_B, sf_KI;         /* sf.A, sf.B, sf.KI (crowd_nav/policy/social_force.py:22-27) */
 } CnConfig;
@@ -128,6 +129,8 @@ typedef struct CnStateView {
     float *extras;     /* [N, 4]  desiredVelocity[0], potential, last_acceleration x,y */
     int32_t *counters; /* [N, 4]  step_count, scenario_counter, case_counter, current_scenario */
     float *episode_return; /* [N]  running sum of rewards (bench.Monitor) */
+    float *groups;     /* [N, CN_MAX_GROUPS, 4] group environment only (may be NULL): radius, centre x, centre y, valid (1/0) of the
+                          static circle groups of the episode (self.circle_groups, crowd_sim.py:476-505) */
 } CnStateView;
 
 /* Observation dict of CrowdSimDict.generate_ob (crowd_sim_dict.py:72-103), float32. */

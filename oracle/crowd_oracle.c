@@ -15,6 +15,7 @@
  *   generate_ob            crowd_sim/envs/crowd_sim_dict.py:72-103, crowd_sim.py:429-455, 851-865
  *   goal updates           crowd_sim/envs/crowd_sim.py:724-811, crowd_sim_dict.py:261-269
  *   reset                  crowd_sim/envs/crowd_sim_dict.py:105-203, crowd_sim.py:296-393, 555-663
+ *   group environment      crowd_sim/envs/crowd_sim.py:476-622 (circle groups of static humans, sim.group_human)
  *
  * Pinning: the deterministic part (everything except the RNG-driven reset and
  * goal re-sampling) is checked against the reference's own Python executed in
@@ -61,7 +62,7 @@ static void philox_u01(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, uint
     for (int i = 0; i < 4; ++i) u[i] = (double)x[i] * (1.0 / 4294967296.0);
 }
 
-enum { RNG_RESET = 0, RNG_ATTR = 1, RNG_SPAWN = 2, RNG_GOAL_RANDOM = 3, RNG_GOAL_END = 4, RNG_UNOBS = 5, RNG_POLICY = 6 };
+enum { RNG_RESET = 0, RNG_ATTR = 1, RNG_SPAWN = 2, RNG_GOAL_RANDOM = 3, RNG_GOAL_END = 4, RNG_UNOBS = 5, RNG_POLICY = 6, RNG_GROUP = 7 };
 #define RNG_DECISION 0xFFFFFFFFu
 
 /* ------------------------------------------------------------------ per-env views */
@@ -74,6 +75,7 @@ typedef struct {
     float *ext;   /* 4: desired_v, potential, last_ax, last_ay */
     int32_t *ctr; /* 4: step_count, scenario_counter, case_counter, scenario */
     float *ep_ret;
+    float *grp;   /* CN_MAX_GROUPS * 4: radius, cx, cy, valid */
     uint64_t env_gid;
 } Env;
 
@@ -387,9 +389,29 @@ static uint64_t step_key(const Env *e)
     return (e->cfg->base_seed + e->env_gid) ^ ((uint64_t)(uint32_t)e->ctr[1] << 32) ^ 0x5EEDC0DE00000000ull;
 }
 
+/* check_collision_group (crowd_sim.py:520-538) / check_collision_group_goal (:541-552): a disc of `radius` at (x, y) against
+ * the circle groups (<= group radius + radius + margin) and, when `movers`, the first n_h humans that are not obstacles */
+static int collides_with_groups(const Env *e, double x, double y, double radius, double margin, int n_h, int movers)
+{
+    for (int g = 0; g < CN_MAX_GROUPS; ++g) {
+        const float *q = e->grp + 4 * g;
+        if (q[3] == 0.0f) break;
+        if (norm2(x - (double)q[1], y - (double)q[2]) <= (double)q[0] + radius + margin) return 1;
+    }
+    if (movers)
+        for (int k = 0; k < n_h; ++k) {
+            const float *a = e->hum + 9 * k;
+            if (a[VPREF] == 0.0f) continue;       /* isObstacle */
+            if (norm2(x - (double)a[PX], y - (double)a[PY]) <= (double)a[RAD] + radius) return 1;
+        }
+    return 0;
+}
+
 /* does goal (gx,gy) of human i collide with any other agent's position or goal (crowd_sim.py:750-759, 795-804) */
 static int goal_collides(const Env *e, int i, double gx, double gy)
 {
+    if (e->cfg->group_human)                  /* crowd_sim.py:747-748, 792-793: the human itself is not excluded there */
+        return collides_with_groups(e, gx, gy, (double)e->hum[9 * i + RAD], 2 * 0.5, e->H, 1);
     const double ri = e->hum[9 * i + RAD];
     const double dd = e->cfg->discomfort_dist;
     {
@@ -461,6 +483,92 @@ static uint32_t goal_updates(const Env *e)
     return changed;
 }
 
+/* generate_robot_humans for the group environment (crowd_sim.py:559-622) with the Philox contract and bounded tries */
+static void reset_group_env(const Env *e, int scenario, uint64_t key)
+{
+    const CnConfig *cfg = e->cfg;
+    const int H = e->H;
+    float *rob = e->rob;
+    double u[4];
+    rob[RAD] = (float)cfg->robot_radius;
+    rob[VPREF] = (float)cfg->robot_v_pref;
+    rob[VX] = 0.0f; rob[VY] = 0.0f;
+    memset(e->grp, 0, sizeof(float) * 4 * CN_MAX_GROUPS);
+    int left = H, idx = 0, ng = 0;
+    while (left > 0) {
+        if (left <= 4) {
+            /* the remaining humans walk: generate_circle_crossing_human with the group collision rule (crowd_sim.py:371-372) */
+            for (; idx < H; ++idx) {
+                float *h = e->hum + 9 * idx;
+                double v_pref = cfg->human_v_pref, radius = cfg->human_radius;
+                if (cfg->randomize_attributes) {
+                    philox_u01(key, 0, (uint32_t)idx, 0, RNG_ATTR, u);
+                    v_pref = 0.5 + (1.5 - 0.5) * u[0];
+                    radius = 0.3 + (0.5 - 0.3) * u[1];
+                }
+                const float radius_f = (float)radius;
+                double px = 0, py = 0, gx = 0, gy = 0, hd = 0, vp = v_pref;
+                for (int t = 0; t < cfg->max_spawn_tries; ++t) {
+                    double ua[4], ub[4], u6[6];
+                    philox_u01(key, (uint32_t)t, (uint32_t)idx, 0, RNG_SPAWN, ua);
+                    philox_u01(key, (uint32_t)t, (uint32_t)idx, 1, RNG_SPAWN, ub);
+                    u6[0] = ua[0]; u6[1] = ua[1]; u6[2] = ua[2]; u6[3] = ua[3]; u6[4] = ub[0]; u6[5] = ub[1];
+                    agent_attributes(cfg, scenario, (double)radius_f, v_pref, (double)rob[RAD], u6, &px, &py, &gx, &gy, &hd, &vp);
+                    if (!collides_with_groups(e, px, py, (double)radius_f, 2 * 0.5, idx, 1)) break;
+                }
+                h[PX] = (float)px; h[PY] = (float)py; h[GX] = (float)gx; h[GY] = (float)gy;
+                h[VX] = 0.0f; h[VY] = 0.0f; h[TH] = (float)hd; h[RAD] = radius_f; h[VPREF] = (float)vp;
+            }
+            left = 0;
+        } else {
+            /* a circle of circum_num = randint(4, min(left, 10)) static humans (generate_circle_group_obstacle, :476-518) */
+            const int max_rand = left < 10 ? left : 10;
+            philox_u01(key, (uint32_t)ng, 0, 0, RNG_GROUP, u);
+            int circum = 4 + (int)(u[0] * (double)(max_rand - 4));
+            if (circum > max_rand - 1) circum = max_rand - 1;
+            const double g_radius = cfg->human_radius * 2.0 * circum / (2.0 * PI);
+            double cx = 0.0, cy = 0.0;
+            for (int t = 0; t < cfg->max_spawn_tries; ++t) {
+                philox_u01(key, (uint32_t)t, (uint32_t)ng, 1, RNG_GROUP, u);
+                cx = -3.0 + 6.0 * u[0]; cy = -3.0 + 6.0 * u[1];
+                int ok = 1;
+                for (int g = 0; g < ng && ok; ++g) {
+                    const float *q = e->grp + 4 * g;
+                    if (norm2(cx - (double)q[1], cy - (double)q[2]) < g_radius + (double)q[0] + 2.0 * cfg->human_radius) ok = 0;
+                }
+                if (ok) break;
+            }
+            float *q = e->grp + 4 * ng;
+            q[0] = (float)g_radius; q[1] = (float)cx; q[2] = (float)cy; q[3] = 1.0f;
+            const double arc = 2.0 * PI / circum;
+            for (int k = 0; k < circum; ++k, ++idx) {
+                float *h = e->hum + 9 * idx;
+                const double angle = arc * k;
+                const double px = (double)q[1] + (double)q[0] * cos(angle), py = (double)q[2] + (double)q[0] * sin(angle);
+                h[PX] = (float)px; h[PY] = (float)py; h[GX] = h[PX]; h[GY] = h[PY];
+                h[VX] = 0.0f; h[VY] = 0.0f; h[TH] = 0.0f; h[RAD] = (float)cfg->human_radius; h[VPREF] = 0.0f;
+            }
+            left -= circum; ++ng;
+        }
+    }
+    /* robot on the circle of radius 5.5, its goal on the opposite side; both step by 0.2 rad past the groups (:593-620) */
+    philox_u01(key, 0, 0, 2, RNG_GROUP, u);
+    const double rand_angle = u[0] * PI * 2.0;
+    double inc = 0.0, px = 0.0, py = 0.0, gx = 0.0, gy = 0.0;
+    for (int t = 0; t < 64; ++t) {
+        px = cos(rand_angle + inc) * 5.5; py = sin(rand_angle + inc) * 5.5;
+        if (!collides_with_groups(e, px, py, cfg->robot_radius, 2 * 0.5, H, 1)) break;
+        inc = inc + 0.2;
+    }
+    inc = inc + PI;
+    for (int t = 0; t < 64; ++t) {
+        gx = cos(rand_angle + inc) * 5.5; gy = sin(rand_angle + inc) * 5.5;
+        if (!collides_with_groups(e, gx, gy, cfg->robot_radius, 4 * 0.5, H, 0)) break;
+        inc = inc + 0.2;
+    }
+    rob[PX] = (float)px; rob[PY] = (float)py; rob[GX] = (float)gx; rob[GY] = (float)gy; rob[TH] = (float)(PI / 2.0);
+}
+
 /* CrowdSimDict.reset (crowd_sim_dict.py:105-203) with the Philox contract */
 static void reset_env(const Env *e, int idx, const CnObsOut *obs)
 {
@@ -478,6 +586,7 @@ static void reset_env(const Env *e, int idx, const CnObsOut *obs)
     e->ext[0] = 0.0f;        /* desiredVelocity = [0, 0] */
     const double R = cfg->circle_radius;
     float *rob = e->rob;
+    if (cfg->group_human) { reset_group_env(e, scenario, key); goto spawned; }
     rob[RAD] = (float)cfg->robot_radius;
     rob[VPREF] = (float)cfg->robot_v_pref;
     rob[VX] = 0.0f; rob[VY] = 0.0f;
@@ -538,6 +647,7 @@ static void reset_env(const Env *e, int idx, const CnObsOut *obs)
         h[PX] = (float)px; h[PY] = (float)py; h[GX] = (float)gx; h[GY] = (float)gy;
         h[VX] = 0.0f; h[VY] = 0.0f; h[TH] = (float)hd; h[RAD] = radius_f; h[VPREF] = (float)vp;
     }
+spawned:
     /* case_counter[phase] = (case_counter + nenv) % case_size (crowd_sim_dict.py:162-164) */
     e->ctr[2] = (int32_t)(uint32_t)(((uint64_t)(uint32_t)e->ctr[2] + (uint64_t)cfg->nenv) % cfg->case_size);
     generate_ob(e, 1, idx, obs);
@@ -706,6 +816,7 @@ static Env make_env(const CnConfig *cfg, const OrStateView *st, int idx)
     e.ext = st->extras + 4 * (size_t)idx;
     e.ctr = st->counters + 4 * (size_t)idx;
     e.ep_ret = st->episode_return + idx;
+    e.grp = st->groups ? st->groups + 4 * (size_t)CN_MAX_GROUPS * idx : NULL;
     e.env_gid = (uint64_t)(uint32_t)(cfg->env_id_offset + idx);
     return e;
 }

@@ -17,6 +17,7 @@ typedef struct OrStateView {
     float *extras;     /* [N,4] */
     int32_t *counters; /* [N,4] */
     float *episode_return; /* [N] */
+    float *groups;     /* [N,CN_MAX_GROUPS,4] radius, cx, cy, valid (group environment) */
 } OrStateView;
 
 int oracle_step(const CnConfig *cfg, int n_envs, const OrStateView *st, const float *action,

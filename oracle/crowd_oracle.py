@@ -57,8 +57,9 @@ class OracleState:
         self.extras = np.zeros((n_envs, 4), np.float32)
         self.counters = np.zeros((n_envs, 4), np.int32)
         self.episode_return = np.zeros((n_envs,), np.float32)
+        self.groups = np.zeros((n_envs, abi.MAX_GROUPS, 4), np.float32)
 
-    FIELDS = ("robot", "humans", "belief", "extras", "counters", "episode_return")
+    FIELDS = ("robot", "humans", "belief", "extras", "counters", "episode_return", "groups")
 
     def view(self):
         return OrStateView(*[_ptr(getattr(self, f)) for f in self.FIELDS])

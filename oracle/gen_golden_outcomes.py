@@ -25,6 +25,8 @@ CASES = {
     # drifting at every new end goal.  (humans.random_policy_changing cannot run in the reference: crowd_sim.py:472-473 calls
     # the policy constructors without their config and a Human.set_policy that does not exist.)
     "n4_social_force_h5": dict(over={"humans.policy": "social_force"}, ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),
+    # the group environment: circles of static humans plus up to 4 walkers (crowd_sim.py:476-622)
+    "n4_group_h8": dict(over={"sim.group_human": True, "sim.human_num": 8}, ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),
     "n4_options_h5": dict(over={"humans.random_unobservability": True, "humans.unobservable_chance": 0.5,
                                 "humans.random_radii": True, "humans.random_v_pref": True},
                           ckpt="data/example_model/checkpoints/27776.pt", episodes=2000),

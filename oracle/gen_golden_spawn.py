@@ -26,6 +26,9 @@ CASES = {
     "circle_h10_unicycle": dict(over={"sim.train_val_sim": ["circle_crossing"], "sim.human_num": 10,
                                       "action_space.kinematics": "unicycle", "env.time_step": 0.1}),
     "mixed_h5": dict(over={}),          # the default four scenarios, chosen at random per episode: scenario frequencies
+    # the group environment (circle groups of static humans, crowd_sim.py:476-622)
+    "group_h8": dict(over={"sim.group_human": True, "sim.human_num": 8, "sim.train_val_sim": ["circle_crossing"]}),
+    "group_h16_mixed": dict(over={"sim.group_human": True, "sim.human_num": 16}),
 }
 
 

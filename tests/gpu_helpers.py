@@ -9,7 +9,7 @@ from oracle import crowd_oracle
 
 OUT_FIELDS = ("robot_node", "temporal_edges", "spatial_edges", "visible_mask", "reward", "done", "event", "scenario",
               "info", "episode_return", "episode_length", "goal_changed")
-STATE_FIELDS = ("robot", "humans", "belief", "extras", "counters", "episode_return")
+STATE_FIELDS = ("robot", "humans", "belief", "extras", "counters", "episode_return", "groups")
 INT_FIELDS = ("visible_mask", "done", "event", "scenario", "episode_length", "goal_changed", "counters")
 
 
@@ -44,6 +44,8 @@ def oracle_state_from(inp, n, H):
         getattr(st, f)[...] = inp[f]
     if "episode_return" in inp:
         st.episode_return[...] = inp["episode_return"]
+    if "groups" in inp:
+        st.groups[...] = inp["groups"]
     return st
 
 

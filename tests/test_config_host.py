@@ -35,14 +35,22 @@ def test_step_tables_replay_float64_accumulation():
 
 
 def test_flatten_config_rejects_out_of_scope_flags():
-    for sec, attr, val in (("humans", "policy", "cadrl"), ("sim", "group_human", True), ("noise", "add_noise", True),
-                           ("reward", "norm_zones", True), ("lidar", "enable", True)):
+    for sec, attr, val in (("humans", "policy", "cadrl"), ("reward", "norm_zones", True), ("lidar", "enable", True)):
         c = Config()
         setattr(getattr(c, sec), attr, val)
         with pytest.raises(NotImplementedError):
             abi.flatten_config(c, 4)
     c = Config()
-    c.humans.policy = "social_force"                          # supported since round 2
+    c.noise.add_noise = True                                  # no effect on the dict observation (crowd_sim_dict.py:71-103)
+    assert bytes(abi.flatten_config(c, 4)) == bytes(abi.flatten_config(Config(), 4))
+    c = Config()
+    c.sim.group_human = True                                  # supported since round 2
+    assert abi.flatten_config(c, 4).group_human == 1
+    c = Config(test_sim=["side_pref_passing"])
+    c.sim.group_human = True                                  # ... and disabled while testing side preferences (crowd_sim.py:123-125)
+    assert abi.flatten_config(c, 4, phase="test").group_human == 0
+    c = Config()
+    c.humans.policy = "social_force"
     assert abi.flatten_config(c, 4).human_policy == abi.POLICY_SOCIAL_FORCE
     c = Config()
     c.sim.train_val_sim = "circle_crossing"

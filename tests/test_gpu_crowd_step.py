@@ -88,8 +88,10 @@ def test_step_matches_oracle_random(name, kw, n, auto_reset):
 
 @pytest.mark.parametrize("kw", [dict(human_num=5), dict(human_num=10, kinematics="unicycle"),
                                 dict(human_num=20, **{"robot.FOV": 0.5}),
-                                dict(human_num=5, **{"test.social_metrics": True, "sim.circle_radius": 4})],
-                         ids=["h5", "h10_uni", "h20_fov", "social"])
+                                dict(human_num=5, **{"test.social_metrics": True, "sim.circle_radius": 4}),
+                                dict(human_num=8, **{"sim.group_human": True}),
+                                dict(human_num=23, kinematics="unicycle", **{"sim.group_human": True})],
+                         ids=["h5", "h10_uni", "h20_fov", "social", "n4_group_h8", "n4_group_h23_uni"])
 def test_reset_matches_oracle(kw):
     n = 2048
     cfg_obj = _cfg(**kw)
@@ -120,8 +122,9 @@ def test_reset_matches_oracle(kw):
 @pytest.mark.parametrize("kw,steps", [(dict(human_num=5), 120), (dict(human_num=10, kinematics="unicycle"), 60),
                                       (dict(human_num=20, **{"robot.FOV": 0.5}), 40),
                                       (dict(human_num=8, **{"humans.random_policy_changing": True, "humans.random_unobservability": True,
-                                                            "humans.random_radii": True, "humans.random_v_pref": True}), 100)],
-                         ids=["h5", "h10_uni", "h20_fov", "n4_options_h8"])
+                                                            "humans.random_radii": True, "humans.random_v_pref": True}), 100),
+                                      (dict(human_num=9, **{"sim.group_human": True}), 150)],
+                         ids=["h5", "h10_uni", "h20_fov", "n4_options_h8", "n4_group_h9"])
 def test_rollout_tracks_oracle(kw, steps):
     """Multi-step trajectory (auto-reset + goal re-sampling on) with a fixed action tape: the CUDA path and the
     oracle must stay in lock-step; flags are compared every step."""
@@ -149,6 +152,7 @@ def test_rollout_tracks_oracle(kw, steps):
     st = G.state_to_numpy(eng.get_state())
     assert np.abs(st["humans"] - ost.humans).max() <= 1e-4
     assert np.abs(st["robot"] - ost.robot).max() <= 1e-4
+    assert np.abs(st["groups"] - ost.groups).max() <= 2e-6      # circle groups of the running episodes (group environment)
     assert n_done > 0
 
 

@@ -76,3 +76,62 @@ def test_random_radii_and_v_pref_move_with_the_end_goal():
     assert np.abs(d_r).max() <= 0.1 + 1e-6 and np.abs(d_v).max() <= 0.1 + 1e-6
     assert abs(float(d_r[moved].mean())) < 0.02 and abs(float(d_v[moved].mean())) < 0.02      # centred
     assert np.std(d_r[moved]) == pytest.approx(0.2 / np.sqrt(12), rel=0.15)                  # uniform(-0.1, 0.1)
+
+
+def test_group_environment_reset_structure():
+    """sim.group_human (crowd_sim.py:559-622): circles of 4-9 static humans (v_pref 0, goal = position, config radius) whose
+    discs do not overlap other groups, at most 4 walkers that keep clear of the groups, robot start and goal on the circle
+    of radius 5.5 outside the groups.  (The distributions are pinned against the reference in test_spawn_distribution.py.)"""
+    n, H = 512, 13
+    cfg_obj = Config(human_num=H)
+    cfg_obj.sim.group_human = True
+    cfg = abi.flatten_config(cfg_obj, n, phase="train")
+    assert cfg.group_human == 1
+    st = crowd_oracle.OracleState(n, H)
+    crowd_oracle.reset(cfg, st, n_threads=4)
+    hum, grp, rob = st.humans.astype(np.float64), st.groups.astype(np.float64), st.robot.astype(np.float64)
+    static = hum[:, :, 7] == 0
+    n_static = static.sum(1)
+    assert ((H - n_static) >= 1).all() and ((H - n_static) <= 4).all()
+    assert (static[:, :-1] >= static[:, 1:]).all()                     # the static humans come first
+    assert np.all(hum[static][:, 5:7] == hum[static][:, 0:2]) and np.allclose(hum[static][:, 4], 0.3)
+    n_groups = (grp[:, :, 3] == 1).sum(1)
+    assert (n_groups >= 1).all() and (n_groups <= 3).all()
+    for e in range(n):
+        k = 0
+        for g in range(n_groups[e]):
+            r, cx, cy = grp[e, g, 0:3]
+            m = int(round(r * 2 * np.pi / 0.6))                        # group radius = 0.3 * 2 * m / (2 pi)
+            assert 4 <= m <= 9
+            d = np.linalg.norm(hum[e, k:k + m, 0:2] - [cx, cy], axis=1)
+            assert np.allclose(d, r, atol=1e-5)
+            k += m
+            for g2 in range(g):                                        # centres at least r1 + r2 + 2 * 0.3 apart
+                assert np.linalg.norm(grp[e, g, 1:3] - grp[e, g2, 1:3]) >= r + grp[e, g2, 0] + 0.6 - 1e-5
+        assert k == n_static[e]
+        for w in range(k, H):                                          # walkers: outside every group by radius + 1
+            for g in range(n_groups[e]):
+                assert np.linalg.norm(hum[e, w, 0:2] - grp[e, g, 1:3]) > grp[e, g, 0] + hum[e, w, 4] + 1.0 - 1e-5
+    assert np.allclose(np.linalg.norm(rob[:, 0:2], axis=1), 5.5, atol=1e-5)
+    assert np.allclose(np.linalg.norm(rob[:, 5:7], axis=1), 5.5, atol=1e-5)
+    assert np.all(np.linalg.norm(rob[:, 5:7] - rob[:, 0:2], axis=1) > 5.0)
+
+
+def test_group_environment_static_humans_stay_put():
+    n, H = 128, 9
+    cfg_obj = Config(human_num=H)
+    cfg_obj.sim.group_human = True
+    cfg = abi.flatten_config(cfg_obj, n, phase="train")
+    st = crowd_oracle.OracleState(n, H)
+    crowd_oracle.reset(cfg, st, n_threads=4)
+    p0, static = st.humans[:, :, 0:2].copy(), st.humans[:, :, 7] == 0
+    rng = np.random.default_rng(1)
+    alive = np.ones(n, bool)
+    for _ in range(30):
+        out = crowd_oracle.step(cfg, st, rng.normal(0, 0.7, (n, 2)).astype(np.float32), auto_reset=False, n_threads=4)
+        alive &= ~out.done.astype(bool)
+    keep = alive[:, None] & static
+    assert keep.sum() > 100
+    assert np.array_equal(st.humans[:, :, 0:2][keep], p0[keep])                     # ORCA with max speed 0: no motion
+    moved = np.linalg.norm(st.humans[:, :, 0:2] - p0, axis=-1)[alive[:, None] & ~static]
+    assert (moved > 0.5).mean() > 0.8                                                # the walkers walk

@@ -41,8 +41,15 @@ def _check(d, robot, humans, scenario):
         if q_ref[-1] - q_ref[0] < 1e-9:                       # constant in the reference (e.g. radius without randomisation)
             assert np.abs(x - q_ref[0]).max() < 1e-5, k
             continue
-        cdf = np.searchsorted(x, q_ref, side="right") / x.size          # our CDF at the reference's quantiles
-        dist = float(np.abs(cdf - grid)[1:-1].max())
+        # our CDF at the reference's quantiles (+1e-5: our state is float32, an atom such as radius 0.3 or the 11 m robot-goal distance sits an ulp or two off)
+        cdf = np.searchsorted(x, q_ref + 1e-5, side="right") / x.size
+        # an atom of the distribution (the static humans of the group environment: v_pref = 0, goal = position) repeats one
+        # value over a run of quantiles: the reference CDF at that value is the END of the run
+        last_of_run = np.r_[np.abs(q_ref[1:] - q_ref[:-1]) > 1e-5, True]
+        idx = np.arange(grid.size)
+        end = np.where(last_of_run, idx, grid.size)          # index of the run's end, propagated backwards
+        end = np.minimum.accumulate(end[::-1])[::-1]
+        dist = float(np.abs(cdf - grid[end])[1:-1].max())
         crit = 1.95 * math.sqrt((x.size + n_ref) / (x.size * n_ref)) + 1.0 / (grid.size - 1)
         if k.startswith("human_"):
             crit *= 1.5
