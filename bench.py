@@ -60,6 +60,10 @@ def reference_python_baseline(workload):
     except ValueError:
         return None
     for r in doc.get("results", []):
+        if r.get("workload") == workload and r.get("did_not_finish"):
+            return {"value": None, "unit": "env-steps/s", "cores": r["processes"], "kind": "reference-python",
+                    "sample": "did not finish: " + r["note"], "measured_on": doc.get("where"),
+                    "source": "profiles/r2_reference_python_cpu.json (oracle/bench_reference_python.py)"}
         if r.get("workload") == workload:
             return {"value": r["env_steps_per_s"], "unit": "env-steps/s", "cores": r["processes"], "kind": "reference-python",
                     "sample": "%d lock-step steps of %d reference CrowdSimDict processes under ShmemVecEnv + reference Policy.act in %.0f s%s"

@@ -139,11 +139,12 @@ class CrowdVecEnv(object):
                 self._pin_reward, self._pin_done = self._pin_reward.pin_memory(), self._pin_done.pin_memory()
         self._pin_reward.copy_(buf.reward, non_blocking=True)
         self._pin_done.copy_(buf.done, non_blocking=True)
+        infos = LazyInfos(buf, self._side, self._t0)      # its device-side snapshot is enqueued BEFORE the host waits
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
         reward = self._pin_reward.clone().unsqueeze(1)
         done = self._pin_done.numpy().astype(bool)
-        return buf.obs(), reward, done, LazyInfos(buf, self._side, self._t0)
+        return buf.obs(), reward, done, infos
 
     def step(self, actions):
         self.step_async(actions)
