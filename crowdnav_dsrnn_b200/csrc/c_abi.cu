@@ -42,6 +42,7 @@ struct DeviceGuard {
     if (guard__.err != cudaSuccess) return fail(CN_ERR_CUDA, "cudaSetDevice(%d): %s", (int)(dev), cudaGetErrorString(guard__.err))
 
 extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, int auto_reset, cudaStream_t stream);
+extern "C" int cn_crowd_step_launches(const EnvParams *P);
 extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, const uint8_t *mask, int mode, cudaStream_t stream);
 enum { CN_RESET_LIVE = 0, CN_RESET_SPARE = 1, CN_RESET_SYNC = 2, CN_RESET_SPARE_LIST = 3 };   // crowd_reset.cu
 extern "C" int cn_launch_crowd_observe(const EnvParams *P, const CnObsOut *obs, cudaStream_t stream);
@@ -252,16 +253,17 @@ extern "C" int cn_env_step(CnEnv *env, const float *action_dev, const CnStepOut 
     env->timer.begin((cudaStream_t)stream);
     CN_CUDA((cudaError_t)cn_launch_crowd_step(&env->p, out, action_dev, auto_reset ? 1 : 0, (cudaStream_t)stream));
     env->timer.end((cudaStream_t)stream);
-    env->last_launches = 1;
+    const int step_launches = cn_crowd_step_launches(&env->p);
+    env->last_launches = step_launches;
     if (auto_reset) {
         // finished episodes were replaced by their spares inside the step kernel; the fall-back handles the envs whose
         // spare was missing (normally none: it exits at once), the refill runs beside the caller's next kernels
         CN_CUDA((cudaError_t)cn_launch_crowd_reset(&env->p, &out->obs, nullptr, CN_RESET_SYNC, (cudaStream_t)stream));
-        env->last_launches = 2;
+        env->last_launches = step_launches + 1;
         if (auto_reset == 1) {                         // 2: the caller (or the forward, cn_dsrnn_set_refill_env) starts the refill
             rc = fork_refill(env, (cudaStream_t)stream);
             if (rc != CN_OK) return rc;
-            env->last_launches = 3;
+            env->last_launches = step_launches + 2;
         }
     }
     return CN_OK;

@@ -545,6 +545,59 @@ __device__ __forceinline__ bool inside_world_d(double px, double py, double r, d
     return true;
 }
 
+// ---- exact-by-construction pre-filters of the env tail.  The reference evaluates these predicates through long fp64 chains
+// (atan2 / cos / sin / acos, crowd_sim.py:820-847, helper.py:199-231); a cheap fp32 evaluation of the same GEOMETRY decides them
+// whenever the result is clear of the decision boundary by a margin far larger than its own error, and only the (rare) cases
+// inside the margin run the exact chain -- so every flag is the one the exact chain gives.
+struct QuickRect { float cx, cy, dx, dy, half_len, r; bool ok; };
+
+// VelocityRectangle of an agent as centre, unit direction, half length and half width (helper.py:199-231: width 2 r, length
+// 3 |v|, starting at the agent's front point p + r d; heading atan2(vy, vx), i.e. d = (1, 0) for v = (+0, +0))
+__device__ __forceinline__ QuickRect quick_rect(float px, float py, float vx, float vy, float r)
+{
+    QuickRect q;
+    q.r = r; q.ok = true; q.dx = 1.0f; q.dy = 0.0f; q.half_len = 0.0f;
+    const float l2 = vx * vx + vy * vy;
+    if (vx == 0.0f && vy == 0.0f) q.ok = !(signbit(vx) || signbit(vy));     // atan2 of a signed zero may be +-pi: exact path
+    else if (!(l2 > 1e-20f) || !(l2 < 1e20f)) q.ok = false;
+    else { const float inv = rsqrtf(l2); q.dx = vx * inv; q.dy = vy * inv; q.half_len = 1.5f * l2 * inv; }
+    q.cx = px + (r + q.half_len) * q.dx;
+    q.cy = py + (r + q.half_len) * q.dy;
+    return q;
+}
+
+// +1: the two rectangles surely intersect, -1: surely disjoint, 0: within 1e-3 of touching (or degenerate input): run the exact
+// test.  Separating-axis test on the four unit edge directions; coordinates are a few metres, fp32 error < 1e-5.
+__device__ __forceinline__ int quick_rects_intersect(const QuickRect &a, const QuickRect &b)
+{
+    if (!(a.ok && b.ok)) return 0;
+    const float m = 1e-3f;
+    const float ex = b.cx - a.cx, ey = b.cy - a.cy;
+    const float dd = fabsf(a.dx * b.dx + a.dy * b.dy), dn = fabsf(a.dx * b.dy - a.dy * b.dx);     // |d_a.d_b| = |n_a.n_b|, |d_a.n_b| = |n_a.d_b|
+    const float g0 = fabsf(ex * a.dx + ey * a.dy) - (a.half_len + b.half_len * dd + b.r * dn);    // axis d_a
+    const float g1 = fabsf(ey * a.dx - ex * a.dy) - (a.r + b.half_len * dn + b.r * dd);           // axis n_a
+    const float g2 = fabsf(ex * b.dx + ey * b.dy) - (b.half_len + a.half_len * dd + a.r * dn);    // axis d_b
+    const float g3 = fabsf(ey * b.dx - ex * b.dy) - (b.r + a.half_len * dn + a.r * dd);           // axis n_b
+    const float gmax = fmaxf(fmaxf(g0, g1), fmaxf(g2, g3));
+    if (gmax > m) return -1;
+    if (gmax < -m) return 1;
+    return 0;
+}
+
+// detect_visible (crowd_sim.py:820-847) of point 2 from agent 1 whose unit heading (hx, hy) is known to ~1e-6:
+// +1 visible, -1 not visible, 0 undecided (within 1e-4 of the FOV boundary in cosine space, or a degenerate heading)
+__device__ __forceinline__ int quick_visible(float hx, float hy, bool heading_ok, float p1x, float p1y, float p2x, float p2y, float cos_half_fov)
+{
+    const float dx = p2x - p1x, dy = p2y - p1y;
+    if (dx == 0.0f && dy == 0.0f) return -1;                 // coincident: the reference's nan <= fov / 2 is False
+    const float l2 = dx * dx + dy * dy;
+    if (!heading_ok || !(l2 > 1e-20f)) return 0;
+    const float c = (hx * dx + hy * dy) * rsqrtf(l2);
+    if (c > cos_half_fov + 1e-4f) return 1;
+    if (c < cos_half_fov - 1e-4f) return -1;
+    return 0;
+}
+
 // does goal (gx,gy) of human i come within min_dist of any other agent's position or goal (crowd_sim.py:750-759)
 // (kOpt builds, group environment: check_collision_group instead, crowd_sim.py:747-748, 792-793)
 template <bool kOpt>
@@ -664,10 +717,19 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
         const double other = shfl_d(FULL, dmin, lane ^ o);
         dmin = other < dmin ? other : dmin;
     }
-    double rvr[4][2], hvr[4][2];
-    velocity_rect_d(rpv.x, rpv.y, rpv.z, rpv.w, rgr.z, rvr);
-    velocity_rect_d(hpv.x, hpv.y, hpv.z, hpv.w, hgr.z, hvr);
-    const int vec_viol = __popc(__ballot_sync(FULL, counted && rects_intersect_d(rvr, hvr)));
+    // SM2 (crowd_sim.py:962-967): do the velocity rectangles of the robot and of human `lane` intersect
+    bool rects_hit = false;
+    if (counted) {
+        const int quick = quick_rects_intersect(quick_rect(rpv.x, rpv.y, rpv.z, rpv.w, rgr.z), quick_rect(hpv.x, hpv.y, hpv.z, hpv.w, hgr.z));
+        if (quick != 0) rects_hit = quick > 0;
+        else {
+            double rvr[4][2], hvr[4][2];
+            velocity_rect_d(rpv.x, rpv.y, rpv.z, rpv.w, rgr.z, rvr);
+            velocity_rect_d(hpv.x, hpv.y, hpv.z, hpv.w, hgr.z, hvr);
+            rects_hit = rects_intersect_d(rvr, hvr);
+        }
+    }
+    const int vec_viol = __popc(__ballot_sync(FULL, rects_hit));
     const bool h_reached = norm2d_lt((double)hpv.x - (double)hgr.x, (double)hpv.y - (double)hgr.y, (double)hgr.z);
     int agg_nav = __popc(__ballot_sync(FULL, counted && !h_reached));
     const double dgoal = norm2d((double)rpv.x - (double)rgr.x, (double)rpv.y - (double)rgr.y);
@@ -704,7 +766,13 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
     const double dax = ax - (double)racc.x, day = ay - (double)racc.y;
     const float jerk = (float)(dax * dax + day * day);
     racc.x = (float)ax; racc.y = (float)ay;
-    const bool inside = inside_world_d(rpv.x, rpv.y, rgr.z, cfg.square_width / 2.0);
+    // check_inside_world (helper.py:42-55): clear of every wall by more than 1e-6 -> inside without the segment distances
+    bool inside = true;
+    {
+        const double half = cfg.square_width / 2.0;
+        const double reach = fmax(fabs((double)rpv.x), fabs((double)rpv.y)) + (double)rgr.z;
+        if (!(reach < half - 1e-6)) inside = inside_world_d(rpv.x, rpv.y, rgr.z, half);
+    }
     const float speed_viol = (sqrt(avx * avx + avy * avy) > cfg.max_walking_speed) ? 1.f : 0.f;
 
     // ---- reward / done / event (crowd_sim.py:1032-1092)
@@ -750,9 +818,27 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
 
     // ---- generate_ob: FOV mask, belief, observation (crowd_sim_dict.py:72-103)
     bool vis = false;
+    // the robot's unit heading for the quick FOV test: v / |v| (holonomic: atan2(vy, vx)) or (cos, sin) of theta, in fp32
+    float fov_hx = 1.0f, fov_hy = 0.0f, fov_cos = 0.0f;
+    bool fov_ok = false;
+    if (cfg.robot_fov < 2.0 * CN_PI) {
+        fov_cos = cosf((float)(cfg.robot_fov / 2.0));
+        if (cfg.kinematics == CN_HOLONOMIC) {
+            const float l2 = rpv.z * rpv.z + rpv.w * rpv.w;
+            if (rpv.z == 0.0f && rpv.w == 0.0f) fov_ok = !(signbit(rpv.z) || signbit(rpv.w));
+            else if (l2 > 1e-20f && l2 < 1e20f) { const float inv = rsqrtf(l2); fov_hx = rpv.z * inv; fov_hy = rpv.w * inv; fov_ok = true; }
+        } else {
+            sincosf(rx.x, &fov_hy, &fov_hx);
+            fov_ok = fabsf(rx.x) < 1e4f;
+        }
+    }
     if (act) {
         if (cfg.robot_fov >= 2.0 * CN_PI) vis = !((double)npv.x - (double)rpv.x == 0.0 && (double)npv.y - (double)rpv.y == 0.0);
-        else vis = detect_visible_d(cfg.kinematics, rpv.x, rpv.y, rpv.z, rpv.w, rx.x, npv.x, npv.y, cfg.robot_fov);
+        else {
+            const int quick = quick_visible(fov_hx, fov_hy, fov_ok, rpv.x, rpv.y, npv.x, npv.y, fov_cos);
+            vis = quick != 0 ? quick > 0
+                             : detect_visible_d(cfg.kinematics, rpv.x, rpv.y, rpv.z, rpv.w, rx.x, npv.x, npv.y, cfg.robot_fov);
+        }
         const size_t hi = (size_t)e * H + lane;
         float4 bel;
         if (vis) { bel = npv; P.a.hum_br[hi] = hgr.z; }
@@ -896,8 +982,14 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
 // ---------------------------------------------------------------------------------------------- the kernel
 // grid: ceil(N / E) CTAs of 256 threads, each owning E consecutive envs.
 // dynamic smem: E*H*(float4 pv + float4 gr + float2 nv + float th) + 256 float4 sort scratch
-template <int G, bool kOpt>
-__global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS)
+// kPhase 0: the whole step in one launch (the default).  kPhase 1 / 2: the same code as TWO launches -- 1 = staging + phase A
+// (the new velocities go to hum_nv), 2 = staging (+ hum_nv) + phase B -- behind CN_STEP_SPLIT=1: no faster, but it isolates the
+// ORCA solves (issue-bound: 83 % of the issue slots) from the env tail (instruction-fetch and latency bound) in a profile.
+#ifndef STEP_TAIL_THREADS
+#define STEP_TAIL_THREADS 256       // CTA of the env-tail kernel (kPhase 2): one warp per env
+#endif
+template <int G, bool kOpt, int kPhase>
+__global__ void __launch_bounds__(kPhase == 2 ? STEP_TAIL_THREADS : STEP_THREADS, kPhase == 2 ? (1024 / STEP_TAIL_THREADS) : STEP_MIN_BLOCKS)
 crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ CnStepOut out,
                   const float *__restrict__ action, int E, int auto_reset)
 {
@@ -918,14 +1010,16 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
     // stage: coalesced float4 loads of ne*H consecutive humans
     const size_t base = (size_t)e0 * H;
     const bool need_th = cfg.human_fov < 2.0 * CN_PI && cfg.kinematics != CN_HOLONOMIC;
-    for (int k = threadIdx.x; k < ne * H; k += STEP_THREADS) {
+    const int nthreads = kPhase == 2 ? STEP_TAIL_THREADS : STEP_THREADS;
+    for (int k = threadIdx.x; k < ne * H; k += nthreads) {
         const float4 pv = P.a.hum_pv[base + k], gr = P.a.hum_gr[base + k];
         s_pv[k] = pv;
         s_gr[k] = gr;
-        s_nv[k] = preferred_velocity(pv, gr);      // phase A replaces it with the new velocity of the same human
-        if (need_th) s_th[k] = P.a.hum_th[base + k];
+        if (kPhase == 2) s_nv[k] = P.a.hum_nv[base + k];
+        else s_nv[k] = preferred_velocity(pv, gr);      // phase A replaces it with the new velocity of the same human
+        if (kPhase != 2 && need_th) s_th[k] = P.a.hum_th[base + k];
     }
-    if (cfg.robot_visible) {
+    if (kPhase != 2 && cfg.robot_visible) {
         for (int k = threadIdx.x; k < ne; k += STEP_THREADS) {
             s_rob_pv[k] = P.a.rob_pv[e0 + k];
             s_rob_rt[k] = make_float2(P.a.rob_gr[e0 + k].z, P.a.rob_x[e0 + k].x);
@@ -934,7 +1028,7 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
     __syncthreads();
 
     // phase A: ORCA, one G-lane group per (env, human) task
-    {
+    if (kPhase != 2) {
         GroupOps<G> g;
         const int lane = threadIdx.x & 31;
         g.gl = lane % G;
@@ -955,12 +1049,16 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
             if (g.gl == 0) s_nv[task] = nv;
         }
     }
-    __syncthreads();
+    if (kPhase != 2) __syncthreads();
+    if (kPhase == 1) {
+        for (int k = threadIdx.x; k < ne * H; k += STEP_THREADS) P.a.hum_nv[base + k] = s_nv[k];
+        return;
+    }
 
     // phase B: one warp per env
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int el = warp; el < ne; el += STEP_THREADS / 32)
+        for (int el = warp; el < ne; el += nthreads / 32)
             env_tail<kOpt>(P, out, action, e0 + el, lane, s_pv + el * H, s_gr + el * H, s_nv + el * H, auto_reset);
     }
 }
@@ -1074,6 +1172,23 @@ static inline int pick_group(int M)
     return M <= 4 ? 4 : (M <= 8 ? 8 : (M <= 16 ? 16 : 32));
 }
 
+static bool step_has_options(const CnConfig &c)
+{
+    return c.human_policy != CN_POLICY_ORCA || c.random_policy_changing || c.random_unobservability || c.random_radii ||
+           c.random_v_pref || c.group_human;
+}
+
+// launches of one crowd step: 1, or 2 (ORCA kernel + env-tail kernel) with CN_STEP_SPLIT=1 -- a development switch: the two
+// forms take the same time (0.433 vs 0.438 ms at 16384 envs x 20 humans) and give the same bits (tests/test_gpu_crowd_step.py
+// runs both); the split form is what shows each phase on its own in a profile (profiles/r2_ncu_final_kernels.txt).
+extern "C" int cn_crowd_step_launches(const EnvParams *P)
+{
+    if (step_has_options(P->cfg)) return 1;
+    if (const char *dbg = getenv("CN_STEP_SEQ")) if (atoi(dbg) != 0) return 1;
+    if (const char *dbg = getenv("CN_STEP_SPLIT")) return atoi(dbg) != 0 ? 2 : 1;
+    return 1;
+}
+
 // host launcher (called from c_abi.cu)
 extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, const float *action, int auto_reset, cudaStream_t stream)
 {
@@ -1086,8 +1201,7 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     // fewer instructions than the group form but is latency-bound at the ~15 solver warps per SM its 400 B of shared memory
     // per human allow, so it is no faster (0.49-0.53 vs 0.51 ms, profiles/README.md) and stays a development switch.
     // the optional human behaviours of SURVEY 8(f) N4 live in their own instantiation of the group form
-    const bool opt = P->cfg.human_policy != CN_POLICY_ORCA || P->cfg.random_policy_changing || P->cfg.random_unobservability ||
-                     P->cfg.random_radii || P->cfg.random_v_pref || P->cfg.group_human;
+    const bool opt = step_has_options(P->cfg);
     bool seq = false;
     if (const char *dbg = getenv("CN_STEP_SEQ")) seq = atoi(dbg) != 0 && M >= 1 && M <= 32 && !opt;
     if (seq) {
@@ -1120,18 +1234,30 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     const int grid = (P->n_envs + E - 1) / E;
     if (opt) {
         switch (G) {
-        case 4: crowd_step_kernel<4, true><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
-        case 8: crowd_step_kernel<8, true><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
-        case 16: crowd_step_kernel<16, true><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
-        default: crowd_step_kernel<32, true><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        case 4: crowd_step_kernel<4, true, 0><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        case 8: crowd_step_kernel<8, true, 0><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        case 16: crowd_step_kernel<16, true, 0><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        default: crowd_step_kernel<32, true, 0><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
         }
         return (int)cudaGetLastError();
     }
+    if (cn_crowd_step_launches(P) == 2) {
+        switch (G) {
+        case 4: crowd_step_kernel<4, false, 1><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        case 8: crowd_step_kernel<8, false, 1><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        case 16: crowd_step_kernel<16, false, 1><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        default: crowd_step_kernel<32, false, 1><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+        }
+        const int E2 = STEP_TAIL_THREADS / 32;            // one warp per env
+        const size_t smem2 = (size_t)E2 * H * (16 + 16 + 8 + 4) + STEP_THREADS * 16;
+        crowd_step_kernel<32, false, 2><<<(P->n_envs + E2 - 1) / E2, STEP_TAIL_THREADS, smem2, stream>>>(*P, *out, action, E2, auto_reset);
+        return (int)cudaGetLastError();
+    }
     switch (G) {
-    case 4: crowd_step_kernel<4, false><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
-    case 8: crowd_step_kernel<8, false><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
-    case 16: crowd_step_kernel<16, false><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
-    default: crowd_step_kernel<32, false><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    case 4: crowd_step_kernel<4, false, 0><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    case 8: crowd_step_kernel<8, false, 0><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    case 16: crowd_step_kernel<16, false, 0><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
+    default: crowd_step_kernel<32, false, 0><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
     }
     return (int)cudaGetLastError();
 }

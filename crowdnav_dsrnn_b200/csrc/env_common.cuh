@@ -42,6 +42,7 @@ struct EnvArrays {
     uint8_t *need_spare, *need_sync;
     int *sync_count;          // [0] envs flagged in need_sync, [1] CTAs done (sync), [2] entries of refill_list, [3] CTAs done (refill)
     int *refill_list;         // envs whose spare was consumed by the last step (compact: the refill launches a small grid)
+    float2 *hum_nv;           // [N*H] new velocities handed from the ORCA kernel to the env-tail kernel (split launch)
     float4 *grp, *sp_grp;     // group environment: [N * CN_MAX_GROUPS] radius, centre x, centre y, valid of the episode's circle groups
 };
 
@@ -85,6 +86,7 @@ static inline size_t cn_carve(EnvArrays *a, void *base, int n, int H)
     CN_TAKE(need_sync, uint8_t, n);
     CN_TAKE(sync_count, int, 4);
     CN_TAKE(refill_list, int, n);
+    CN_TAKE(hum_nv, float2, nh);
     CN_TAKE(grp, float4, (size_t)n * CN_MAX_GROUPS);
     CN_TAKE(sp_grp, float4, (size_t)n * CN_MAX_GROUPS);
 #undef CN_TAKE

@@ -14,14 +14,15 @@ import gpu_helpers as G
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["group", "thread"])
+@pytest.fixture(autouse=True, params=["group", "thread", "split"])
 def phase_a_form(request, monkeypatch):
-    """Every case runs with both forms of the kernel's ORCA phase: one lane group per human (the default) and one thread
-    per human (CN_STEP_SEQ=1, read by the launcher at every call) -- they must give the same bits."""
+    """Every case runs with the three forms of the step: one lane group per human in one launch (the default below 4096
+    envs), one thread per human (CN_STEP_SEQ=1), and the two-launch form of large batches (ORCA kernel + env-tail kernel,
+    CN_STEP_SPLIT=1) -- the switches are read by the launcher at every call, and all forms must give the same bits."""
+    monkeypatch.delenv("CN_STEP_SEQ", raising=False)
+    monkeypatch.setenv("CN_STEP_SPLIT", "1" if request.param == "split" else "0")
     if request.param == "thread":
         monkeypatch.setenv("CN_STEP_SEQ", "1")
-    else:
-        monkeypatch.delenv("CN_STEP_SEQ", raising=False)
     return request.param
 
 

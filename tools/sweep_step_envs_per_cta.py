@@ -24,7 +24,20 @@ def main():
     act = torch.randn(N, 2, device=dev, generator=g) * 0.5
     for _ in range(150):
         eng.step(act, auto_reset=True)
-    for E in (0, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16):
+    for split in ("0", "1", "0", "1"):
+        os.environ["CN_STEP_SPLIT"] = split
+        os.environ.pop("CN_STEP_ENVS_PER_CTA", None)
+        for _ in range(10):
+            eng.step(act, auto_reset=True)
+        lib.cn_env_enable_timing(eng.handle, 1)
+        for _ in range(40):
+            eng.step(act, auto_reset=True)
+        ms, n = C.c_float(), C.c_int()
+        lib.cn_env_time_ms(eng.handle, C.byref(ms), C.byref(n))
+        lib.cn_env_enable_timing(eng.handle, 0)
+        print("CN_STEP_SPLIT=%s  step %.4f ms" % (split, ms.value / n.value), flush=True)
+    os.environ.pop("CN_STEP_SPLIT", None)
+    for E in (0, 6, 7, 8, 10):
         if E:
             os.environ["CN_STEP_ENVS_PER_CTA"] = str(E)
         else:
