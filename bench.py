@@ -43,8 +43,8 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch.  NOT sampled in this run: constants copied from ONE earlier
 # `ncu --set full` capture of the same kernels at the default sizes (the file named in `traffic_source`); only reported for that
 # workload / batch, null otherwise
-NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 361.40e6 + 309.38e6, "crowd_step_kernel": 16.97e6 + 4.86e6}}
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_final_kernels.txt (one ncu --set full capture, round 1; not re-measured by this run)"
+NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 357.76e6 + 310.53e6, "crowd_step_kernel": 17.73e6 + 6.31e6}}
+NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_final_kernels.txt (one ncu --set full capture, round 2; not re-measured by this run)"
 
 
 def reference_python_baseline(workload):
@@ -351,8 +351,8 @@ def run_ours(args, wl):
                  "unit": "GB/s", "kernel": "crowd_step_kernel", "ms_per_launch": step_avg_ms, "traffic": None,
                  "algorithmic_bytes_per_env_step": step_bytes(H), "share_of_step": step_avg_ms / (ms / args.steps)}
     roof_step["frac"] = roof_step["achieved"] / roof_step["peak"]
-    roof_step["note"] = ("nominally HBM-bound (SURVEY 8(d)); measured: instruction-issue bound at every H (H=1..20: 0.012-0.015 of "
-                         "the HBM peak, profiles/r2_k1_sweep.txt; at H=20 ncu shows issue slots 77 % busy, dram 0.4 %)")
+    roof_step["note"] = ("nominally HBM-bound (SURVEY 8(d)); measured: instruction-issue bound at every H (H=1..20: 0.012-0.017 of "
+                         "the HBM peak, profiles/r2_k1_sweep.txt; ncu at H=20: the ORCA solves keep 83 % of the issue slots busy, dram 0.4 %)")
     traffic = NCU_TRAFFIC_BYTES.get((args.workload, N), {})
     roof_step["traffic"] = traffic.get("crowd_step_kernel")
     roof_step["traffic_source"] = NCU_TRAFFIC_SOURCE if traffic else None

@@ -39,12 +39,10 @@ template <int G> struct GroupOps {
     __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(gmask, p) >> gbase) & kLow; }
     // group-relative mask of the lanes holding the same value
     __device__ __forceinline__ unsigned match(int v) const { return (__match_any_sync(gmask, v) >> gbase) & kLow; }
-    // min/max over the group in ONE redux.sync each: floats are mapped to integers with the same total order
-    // (exact: a reduction only selects one of its inputs; the LP never feeds NaNs here)
-    static __device__ __forceinline__ int ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
-    static __device__ __forceinline__ float unord(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
-    __device__ __forceinline__ float rmax(float v) const { return unord(__reduce_max_sync(gmask, ord(v))); }
-    __device__ __forceinline__ float rmin(float v) const { return unord(__reduce_min_sync(gmask, ord(v))); }
+    // min/max over the group in ONE instruction each: sm_100a reduces floats directly (redux.sync.{min,max}.f32 -> CREDUX.F32).
+    // Exact: a reduction only selects one of its inputs, and the LP never feeds NaNs here.
+    __device__ __forceinline__ float rmax(float v) const { float r; asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(gmask)); return r; }
+    __device__ __forceinline__ float rmin(float v) const { float r; asm volatile("redux.sync.min.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(gmask)); return r; }
 };
 
 struct Line { float px, py, dx, dy; };
