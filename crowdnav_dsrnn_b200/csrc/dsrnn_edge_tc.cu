@@ -486,6 +486,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                 for (int ct = 0; ct < kColTiles; ++ct)
                     for (int kb = 0; kb < kKBlocks; ++kb)
                         for (int part = 0; part < parts; ++part) {
+                            if (DBG(64) && kb > 0 && part == 1) continue;   // what-if (timing only): 2 pass-equivalents per hidden k-block
                             PROF_T0(tw);
                             mbar_wait(bar(kBarEmpty + slot), empty_parity);
                             PROF_ADD(p_wait, tw);
@@ -563,7 +564,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                             if (a.three_pass) mma_kblock(dcol, a_lo, b_lo, false);
                         }
                         release_chunk();
-                        if (a.three_pass) {
+                        if (a.three_pass && !(DBG(64) && kb > 0)) {
                             next_chunk(b_lo);                               // B_lo
                             if (!DBG(2)) mma_kblock(dcol, a_hi, b_lo, false);
                             release_chunk();
