@@ -609,6 +609,22 @@ __device__ __forceinline__ bool goal_collides(const CnConfig &cfg, int H, int i,
         if (norm2d_lt(gx - (double)rob_pv.x, gy - (double)rob_pv.y, md) ||
             norm2d_lt(gx - (double)rob_gr.x, gy - (double)rob_gr.y, md)) return true;
     }
+    // fp32 pass over the other humans (positions and goals are stored as floats): a squared distance outside a 1e-4 band around
+    // the threshold decides the fp64 rule for certain (fp32 error of the squared distance < 1e-5 relative there); the exact rule
+    // only runs for a candidate that lands inside some band without a certain hit
+    const float gxf = (float)gx, gyf = (float)gy, rdf = (float)(ri + dd);
+    bool hit = false, band = false;
+    for (int k = 0; k < H; ++k) {
+        if (k == i) continue;
+        const float4 p = s_pv[k], q = s_gr[k];
+        const float md = rdf + q.z, md2 = md * md, lo = md2 * (1.0f - 1e-4f), hi = md2 * (1.0f + 1e-4f);
+        const float ax = gxf - p.x, ay = gyf - p.y, bx = gxf - q.x, by = gyf - q.y;
+        const float sa = ax * ax + ay * ay, sb = bx * bx + by * by;
+        hit |= (md > 0.0f) & ((sa < lo) | (sb < lo));
+        band |= !(md > 1e-3f) | ((sa >= lo) & (sa <= hi)) | ((sb >= lo) & (sb <= hi));
+    }
+    if (hit) return true;
+    if (!band) return false;
     for (int k = 0; k < H; ++k) {
         if (k == i) continue;
         const float4 p = s_pv[k], q = s_gr[k];
