@@ -240,9 +240,19 @@ __device__ __forceinline__ float2 orca_group(const CnConfig &cfg, const GroupOps
     // float; out-of-range slots get the largest key and never count.  Ties (equal distSq, lower index first) come from one
     // MATCH instruction instead of a second comparison per candidate.
     const int key = in ? __float_as_int(dist_sq) : 0x7fffffff;
+    // the keys go through the group's scratch: every lane reads them back four at a time (broadcast LDS.128) instead of one
+    // shuffle per candidate
     int rank = 0;
-#pragma unroll 8
-    for (int k = 0; k < M; ++k) rank += (g.shfl_i(key, k) < key) ? 1 : 0;   // slots >= M are never in range
+    {
+        int *s_keys = reinterpret_cast<int *>(s_scratch);
+        s_keys[g.gl] = key;                                     // slots >= M hold the out-of-range key and never count
+        __syncwarp(g.gmask);
+        for (int k4 = 0; k4 < (M + 3) >> 2; ++k4) {
+            const int4 kk = reinterpret_cast<const int4 *>(s_keys)[k4];
+            rank += (kk.x < key ? 1 : 0) + (kk.y < key ? 1 : 0) + (kk.z < key ? 1 : 0) + (kk.w < key ? 1 : 0);
+        }
+        __syncwarp(g.gmask);                                    // the scratch is reused for the ranked half-planes below
+    }
     rank += __popc(g.match(key) & in_bits & ((1u << g.gl) - 1u));
 
     // computeNewVelocity: this lane's half-plane
