@@ -50,11 +50,13 @@ struct Line { float px, py, dx, dy; };
 __device__ __forceinline__ float det2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
 
 // linearProgram1: optimise on line k subject to the valid lines of lanes < k and the speed disc
+// (`s_lines`: the same lines in shared memory, slot = lane: line k is one broadcast LDS.128 instead of four shuffles)
 template <int G>
 __device__ __forceinline__ bool lp1_group(const GroupOps<G> &g, const Line &ln, bool valid, int k, float radius,
-                                          float optx, float opty, bool dir_opt, float &rx, float &ry)
+                                          float optx, float opty, bool dir_opt, float &rx, float &ry, const float4 *s_lines)
 {
-    const float kpx = g.shfl(ln.px, k), kpy = g.shfl(ln.py, k), kdx = g.shfl(ln.dx, k), kdy = g.shfl(ln.dy, k);
+    const float4 lk = s_lines[k];
+    const float kpx = lk.x, kpy = lk.y, kdx = lk.z, kdy = lk.w;
     const float dp = kpx * kdx + kpy * kdy;
     const float disc = dp * dp + radius * radius - (kpx * kpx + kpy * kpy);
     if (disc < 0.0f) return false;
@@ -90,7 +92,7 @@ __device__ __forceinline__ bool lp1_group(const GroupOps<G> &g, const Line &ln, 
 // linearProgram2 over the lanes' lines in lane order; returns the failing index or -1 when all lines hold
 template <int G>
 __device__ __forceinline__ int lp2_group(const GroupOps<G> &g, const Line &ln, bool valid, float radius,
-                                         float optx, float opty, bool dir_opt, float &rx, float &ry)
+                                         float optx, float opty, bool dir_opt, float &rx, float &ry, const float4 *s_lines)
 {
     if (dir_opt) { rx = radius * optx; ry = radius * opty; }
     else if (optx * optx + opty * opty > radius * radius) {
@@ -104,15 +106,16 @@ __device__ __forceinline__ int lp2_group(const GroupOps<G> &g, const Line &ln, b
         if (b == 0u) return -1;
         const int k = __ffs(b) - 1;
         const float tx = rx, ty = ry;
-        if (!lp1_group<G>(g, ln, valid, k, radius, optx, opty, dir_opt, rx, ry)) { rx = tx; ry = ty; return k; }
+        if (!lp1_group<G>(g, ln, valid, k, radius, optx, opty, dir_opt, rx, ry, s_lines)) { rx = tx; ry = ty; return k; }
         next = k + 1;
     }
 }
 
 // linearProgram3 (no obstacle lines): minimise the maximum penetration from line `begin` on
+// (`s_lines`: the lanes' lines in shared memory; `s_proj`: scratch of the same size for the projected lines)
 template <int G>
 __device__ __forceinline__ void lp3_group(const GroupOps<G> &g, const Line &ln, int n, int begin, float radius,
-                                          float &rx, float &ry)
+                                          float &rx, float &ry, const float4 *s_lines, float4 *s_proj)
 {
     float distance = 0.0f;
     // RVO2 walks the lines from `begin` and re-solves at every line that is penetrated by more than `distance`; between two
@@ -121,7 +124,8 @@ __device__ __forceinline__ void lp3_group(const GroupOps<G> &g, const Line &ln, 
         const unsigned pen = g.ballot(g.gl >= i && g.gl < n && det2(ln.dx, ln.dy, ln.px - rx, ln.py - ry) > distance);
         if (pen == 0u) break;
         i = __ffs(pen) - 1;
-        const float kpx = g.shfl(ln.px, i), kpy = g.shfl(ln.py, i), kdx = g.shfl(ln.dx, i), kdy = g.shfl(ln.dy, i);
+        const float4 li = s_lines[i];
+        const float kpx = li.x, kpy = li.y, kdx = li.z, kdy = li.w;
         {
             Line pl; pl.px = pl.py = pl.dx = pl.dy = 0.0f;
             bool pvalid = false;
@@ -141,8 +145,11 @@ __device__ __forceinline__ void lp3_group(const GroupOps<G> &g, const Line &ln, 
                     pl.dx = ex * inv; pl.dy = ey * inv;
                 }
             }
+            __syncwarp(g.gmask);                  // the previous round's readers are done with s_proj
+            s_proj[g.gl] = make_float4(pl.px, pl.py, pl.dx, pl.dy);
+            __syncwarp(g.gmask);
             const float tx = rx, ty = ry;
-            if (lp2_group<G>(g, pl, pvalid, radius, -kdy, kdx, true, rx, ry) >= 0) { rx = tx; ry = ty; }
+            if (lp2_group<G>(g, pl, pvalid, radius, -kdy, kdx, true, rx, ry, s_proj) >= 0) { rx = tx; ry = ty; }
             distance = det2(kdx, kdy, kpx - rx, kpy - ry);
         }
     }
@@ -306,8 +313,8 @@ __device__ __forceinline__ float2 orca_group(const CnConfig &cfg, const GroupOps
     __syncwarp(g.gmask);
 
     float rx, ry;
-    const int fail = lp2_group<G>(g, ln, valid, max_speed, prefx, prefy, false, rx, ry);
-    if (fail >= 0) lp3_group<G>(g, ln, n, fail, max_speed, rx, ry);
+    const int fail = lp2_group<G>(g, ln, valid, max_speed, prefx, prefy, false, rx, ry, s_scratch);
+    if (fail >= 0) lp3_group<G>(g, ln, n, fail, max_speed, rx, ry, s_scratch, s_scratch + STEP_THREADS);
     return make_float2(rx, ry);
 }
 
@@ -1005,7 +1012,7 @@ __device__ __forceinline__ void env_tail(const EnvParams &P, const CnStepOut &ou
 
 // ---------------------------------------------------------------------------------------------- the kernel
 // grid: ceil(N / E) CTAs of 256 threads, each owning E consecutive envs.
-// dynamic smem: E*H*(float4 pv + float4 gr + float2 nv + float th) + 256 float4 sort scratch
+// dynamic smem: E*H*(float4 pv + float4 gr + float2 nv + float th) + 2 x 256 float4 line scratch
 // kPhase 0: the whole step in one launch (the default).  kPhase 1 / 2: the same code as TWO launches -- 1 = staging + phase A
 // (the new velocities go to hum_nv), 2 = staging (+ hum_nv) + phase B -- behind CN_STEP_SPLIT=1: no faster, but it isolates the
 // ORCA solves (issue-bound: 83 % of the issue slots) from the env tail (instruction-fetch and latency bound) in a profile.
@@ -1026,7 +1033,7 @@ crowd_step_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ C
     float4 *s_pv = reinterpret_cast<float4 *>(smem_raw);
     float4 *s_gr = s_pv + EH;
     float4 *s_scr = s_gr + EH;
-    float2 *s_nv = reinterpret_cast<float2 *>(s_scr + STEP_THREADS);
+    float2 *s_nv = reinterpret_cast<float2 *>(s_scr + 2 * STEP_THREADS);     // scratch: ranked lines + projected lines of every group
     float *s_th = reinterpret_cast<float *>(s_nv + EH);
     __shared__ float4 s_rob_pv[64];
     __shared__ float2 s_rob_rt[64];   // radius, theta
@@ -1112,6 +1119,7 @@ crowd_step_seq_kernel(const __grid_constant__ EnvParams P, const __grid_constant
     __shared__ float4 s_rob_pv[64];
     __shared__ float2 s_rob_rt[64];   // radius, theta
     __shared__ int s_fail[STEP_THREADS];   // queue of humans for linearProgram3: thread | n << 8 | first failed line << 16
+    __shared__ float4 s_lp3[STEP_THREADS / 32][2][32];
     __shared__ int s_ctl[3];
 
     const size_t base = (size_t)e0 * H;
@@ -1178,9 +1186,12 @@ crowd_step_seq_kernel(const __grid_constant__ EnvParams P, const __grid_constant
             if (rec < 0) break;
             const int owner = rec & 0xff, n = (rec >> 8) & 0xff, fail = rec >> 16, t = task0 + owner;
             Line ln; ln.px = ln.py = ln.dx = ln.dy = 0.0f;
-            if (g.gl < n) { const float4 v = s_lines[g.gl * S + owner]; ln.px = v.x; ln.py = v.y; ln.dx = v.z; ln.dy = v.w; }
+            float4 (*lp3)[32] = s_lp3[threadIdx.x >> 5];      // this warp's contiguous copy of the lines + projected-line scratch
+            __syncwarp();
+            if (g.gl < n) { const float4 v = s_lines[g.gl * S + owner]; ln.px = v.x; ln.py = v.y; ln.dx = v.z; ln.dy = v.w; lp3[0][g.gl] = v; }
+            __syncwarp();
             float2 r = s_nv[t];
-            lp3_group<32>(g, ln, n, fail, s_gr[t].w, r.x, r.y);
+            lp3_group<32>(g, ln, n, fail, s_gr[t].w, r.x, r.y, lp3[0], lp3[1]);
             if (g.gl == 0) s_nv[t] = r;
         }
         __syncthreads();
@@ -1254,7 +1265,7 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
     // there are not enough CTAs to fill the GPU anyway -- spread the envs over at least ~4 CTAs per SM
     if (num_sms > 0 && P->n_envs < E * 4 * num_sms) { E = P->n_envs / (4 * num_sms); E = E < 1 ? 1 : E; }
     if (const char *dbg = getenv("CN_STEP_ENVS_PER_CTA")) { const int v = atoi(dbg); if (v >= 1 && v <= 64) E = v; }   // tuning knob
-    const size_t smem = (size_t)E * H * (16 + 16 + 8 + 4) + STEP_THREADS * 16;
+    const size_t smem = (size_t)E * H * (16 + 16 + 8 + 4) + 2 * STEP_THREADS * 16;
     const int grid = (P->n_envs + E - 1) / E;
     if (opt) {
         switch (G) {
@@ -1273,7 +1284,7 @@ extern "C" int cn_launch_crowd_step(const EnvParams *P, const CnStepOut *out, co
         default: crowd_step_kernel<32, false, 1><<<grid, STEP_THREADS, smem, stream>>>(*P, *out, action, E, auto_reset); break;
         }
         const int E2 = STEP_TAIL_THREADS / 32;            // one warp per env
-        const size_t smem2 = (size_t)E2 * H * (16 + 16 + 8 + 4) + STEP_THREADS * 16;
+        const size_t smem2 = (size_t)E2 * H * (16 + 16 + 8 + 4) + 2 * STEP_THREADS * 16;
         crowd_step_kernel<32, false, 2><<<(P->n_envs + E2 - 1) / E2, STEP_TAIL_THREADS, smem2, stream>>>(*P, *out, action, E2, auto_reset);
         return (int)cudaGetLastError();
     }
