@@ -195,7 +195,7 @@ def run_reference_arm(args, wl):
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -396,7 +396,7 @@ def run_ours(args, wl):
         "gpu_launches": launches, "clocks": clocks, "roofline": dominant, "roofline_other": other, "cpu_baseline": cpu,
         "cpu_baseline_reference_python": reference_python_baseline(args.workload),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -554,12 +554,35 @@ def run_train(args, wl):
                 "note": "crowdnav_dsrnn_b200.train.train(): the same cycle through the public API, with its per-update host reads"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when the
+    communicator is created lazily), so everything the process writes to fd 1 during the run goes to stderr and only the
+    result line is written to the real stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    text = json.dumps(line) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text.encode())
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default 200; 3 update cycles for c5)")
