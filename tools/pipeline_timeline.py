@@ -1,5 +1,5 @@
 """Kernel timeline (CUPTI through torch.profiler) of a few replays of rollout.PipelinedRollout / GraphedRollout.
-usage: python tools/pipeline_timeline.py [plain|pipe] [n_envs] [split]"""
+usage: python tools/pipeline_timeline.py [plain|pipe] [n_envs] [split] [workload]"""
 import json
 import os
 import sys
@@ -19,8 +19,8 @@ from crowdnav_dsrnn_b200.spaces import crowd_spaces  # noqa: E402
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "pipe"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
-    split = int(sys.argv[3]) if len(sys.argv) > 3 else None
-    wl = bench.WORKLOADS["c3"]
+    split = int(sys.argv[3]) if len(sys.argv) > 3 and int(sys.argv[3]) > 0 else None
+    wl = bench.WORKLOADS[sys.argv[4] if len(sys.argv) > 4 else "c3"]
     dev = torch.device("cuda:0")
     cfg = bench.make_config(wl)
     H = wl["human_num"]
