@@ -351,7 +351,7 @@ def run_ours(args, wl):
                  "unit": "GB/s", "kernel": "crowd_step_kernel", "ms_per_launch": step_avg_ms, "traffic": None,
                  "algorithmic_bytes_per_env_step": step_bytes(H), "share_of_step": step_avg_ms / (ms / args.steps)}
     roof_step["frac"] = roof_step["achieved"] / roof_step["peak"]
-    roof_step["note"] = ("nominally HBM-bound (SURVEY 8(d)); measured: instruction-issue bound at every H (H=1..20: 0.012-0.017 of "
+    roof_step["note"] = ("nominally HBM-bound (SURVEY 8(d)); measured: instruction-issue bound at every H (H=1..20: 0.015-0.026 of "
                          "the HBM peak, profiles/r2_k1_sweep.txt; ncu at H=20: the ORCA solves keep 83 % of the issue slots busy, dram 0.4 %)")
     traffic = NCU_TRAFFIC_BYTES.get((args.workload, N), {})
     roof_step["traffic"] = traffic.get("crowd_step_kernel")
