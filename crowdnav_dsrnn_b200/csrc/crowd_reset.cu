@@ -9,6 +9,7 @@
 // because every candidate is a pure function of (episode key, human, try) under the counter-based
 // Philox4x32-10 contract (oracle/crowd_oracle.c restates the same contract sequentially).
 #include <cstdio>
+#include <cstdlib>
 #include "env_common.cuh"
 
 #define RESET_THREADS 256
@@ -23,7 +24,7 @@ __device__ __forceinline__ int cta_first_ok(bool ok, int *s_vote)
     __syncthreads();
     int first = 0x7fffffff;
 #pragma unroll
-    for (int w = 0; w < RESET_THREADS / 32; ++w) first = min(first, s_vote[w]);
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) first = min(first, s_vote[w]);
     return first == 0x7fffffff ? -1 : first;
 }
 
@@ -55,7 +56,7 @@ __device__ __noinline__ void reset_group_env(const EnvParams &P, int e, uint64_t
                 const float radius_f = (float)radius;
                 SpawnCand c;
                 c.px = c.py = c.gx = c.gy = c.heading = c.v_pref = 0.0;
-                for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += RESET_THREADS) {
+                for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += (int)blockDim.x) {
                     const int t = t0 + tid;
                     const uint4 xa = philox4x32(key, (uint32_t)t, (uint32_t)idx, 0, RNG_SPAWN);
                     const uint4 xb = philox4x32(key, (uint32_t)t, (uint32_t)idx, 1, RNG_SPAWN);
@@ -64,7 +65,7 @@ __device__ __noinline__ void reset_group_env(const EnvParams &P, int e, uint64_t
                     const bool ok = t < cfg.max_spawn_tries &&
                                     !collides_with_groups(s_grp, c.px, c.py, (double)radius_f, 2 * 0.5, s_pv, s_gr, idx, true);
                     int src = cta_first_ok(ok, s_vote);
-                    if (src < 0 && t0 + RESET_THREADS >= cfg.max_spawn_tries) src = (cfg.max_spawn_tries - 1) - t0;     // keep the last try
+                    if (src < 0 && t0 + (int)blockDim.x >= cfg.max_spawn_tries) src = (cfg.max_spawn_tries - 1) - t0;     // keep the last try
                     if (src >= 0) {
                         if (tid == src) { s_pick[0] = c.px; s_pick[1] = c.py; s_pick[2] = c.gx; s_pick[3] = c.gy; s_pick[4] = c.heading; s_pick[5] = c.v_pref; }
                         __syncthreads();
@@ -88,7 +89,7 @@ __device__ __noinline__ void reset_group_env(const EnvParams &P, int e, uint64_t
             if (circum > max_rand - 1) circum = max_rand - 1;
             const double g_radius = cfg.human_radius * 2.0 * circum / (2.0 * CN_PI);
             double cx = 0.0, cy = 0.0;
-            for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += RESET_THREADS) {
+            for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += (int)blockDim.x) {
                 const int t = t0 + tid;
                 const uint4 x = philox4x32(key, (uint32_t)t, (uint32_t)ng, 1, RNG_GROUP);
                 cx = -3.0 + 6.0 * u01(x.x); cy = -3.0 + 6.0 * u01(x.y);
@@ -98,7 +99,7 @@ __device__ __noinline__ void reset_group_env(const EnvParams &P, int e, uint64_t
                     if (norm2d(cx - (double)q.y, cy - (double)q.z) < g_radius + (double)q.x + 2.0 * cfg.human_radius) ok = false;
                 }
                 int src = cta_first_ok(ok, s_vote);
-                if (src < 0 && t0 + RESET_THREADS >= cfg.max_spawn_tries) src = (cfg.max_spawn_tries - 1) - t0;
+                if (src < 0 && t0 + (int)blockDim.x >= cfg.max_spawn_tries) src = (cfg.max_spawn_tries - 1) - t0;
                 if (src >= 0) {
                     if (tid == src) { s_pick[0] = cx; s_pick[1] = cy; }
                     __syncthreads();
@@ -228,7 +229,7 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
         const bool uni = cfg.kinematics == CN_UNICYCLE;
         const double angle = u01(g0.y) * CN_PI * 2.0;
         double cpx = R * cos(angle), cpy = R * sin(angle), cgx = 0.0, cgy = 0.0;
-        for (int t0 = 0; t0 < cfg.max_robot_tries; t0 += RESET_THREADS) {
+        for (int t0 = 0; t0 < cfg.max_robot_tries; t0 += (int)blockDim.x) {
             const int t = t0 + tid;
             const uint4 x = philox4x32(key, (uint32_t)t, 1, 0, RNG_RESET);
             if (uni) { cgx = -R + 2.0 * R * u01(x.x); cgy = -R + 2.0 * R * u01(x.y); }
@@ -238,7 +239,7 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
             }
             const bool ok = t < cfg.max_robot_tries && !norm2d_lt(cpx - cgx, cpy - cgy, 6.0);
             int src = cta_first_ok(ok, s_vote);
-            const bool last_round = t0 + RESET_THREADS >= cfg.max_robot_tries;
+            const bool last_round = t0 + (int)blockDim.x >= cfg.max_robot_tries;
             if (src < 0 && last_round) src = (cfg.max_robot_tries - 1) - t0;        // keep the last try
             if (src >= 0) {
                 if (tid == src) { s_pick[0] = cpx; s_pick[1] = cpy; s_pick[2] = cgx; s_pick[3] = cgy; }
@@ -278,7 +279,7 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
         __syncthreads();
         SpawnCand c;
         c.px = c.py = c.gx = c.gy = c.heading = c.v_pref = 0.0;
-        for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += RESET_THREADS) {
+        for (int t0 = 0; t0 < cfg.max_spawn_tries; t0 += (int)blockDim.x) {
             const int t = t0 + tid;
 #ifdef RESET_PROFILE
             ++prounds;
@@ -324,7 +325,7 @@ crowd_reset_kernel(const __grid_constant__ EnvParams P, const __grid_constant__ 
             const long long q3 = clock64();
             pq[0] += q1 - q0; pq[1] += q2 - q1; pq[2] += q3 - q2;
 #endif
-            const bool last_round = t0 + RESET_THREADS >= cfg.max_spawn_tries;
+            const bool last_round = t0 + (int)blockDim.x >= cfg.max_spawn_tries;
             if (src < 0 && last_round) src = (cfg.max_spawn_tries - 1) - t0;        // keep the last try
             if (src >= 0) {
                 if (tid == src) { s_pick[0] = c.px; s_pick[1] = c.py; s_pick[2] = c.gx; s_pick[3] = c.gy; s_pick[4] = c.heading; s_pick[5] = c.v_pref; }
@@ -479,8 +480,15 @@ extern "C" int cn_launch_crowd_reset(const EnvParams *P, const CnObsOut *obs, co
     // the fall-back normally finds nothing to do: a small grid that strides over the envs keeps its launch cheap
     const int small = mode == CN_RESET_SPARE_LIST ? 1184 : 592;
     const int grid = (mode == CN_RESET_SYNC || mode == CN_RESET_SPARE_LIST) ? (P->n_envs < small ? P->n_envs : small) : P->n_envs;
-    if (P->cfg.group_human) crowd_reset_kernel<true><<<grid, RESET_THREADS, 0, stream>>>(*P, obs ? *obs : none, mask, mode);
-    else crowd_reset_kernel<false><<<grid, RESET_THREADS, 0, stream>>>(*P, obs ? *obs : none, mask, mode);
+    // The refill of the spare episodes runs beside the forward's attention kernel: smaller CTAs (thread t = try t, t + threads, ...;
+    // a spawn rarely needs more than a few tries) keep less of an SM away from it.  Same candidates, same first accepted try.
+    int threads = RESET_THREADS;
+    if (!P->cfg.group_human && (mode == CN_RESET_SPARE || mode == CN_RESET_SPARE_LIST)) {
+        threads = 64;
+        if (const char *dbg = getenv("CN_REFILL_THREADS")) { const int v = atoi(dbg); if (v == 32 || v == 64 || v == 128 || v == 256) threads = v; }
+    }
+    if (P->cfg.group_human) crowd_reset_kernel<true><<<grid, threads, 0, stream>>>(*P, obs ? *obs : none, mask, mode);
+    else crowd_reset_kernel<false><<<grid, threads, 0, stream>>>(*P, obs ? *obs : none, mask, mode);
     return (int)cudaGetLastError();
 }
 
