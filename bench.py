@@ -284,6 +284,14 @@ def run_ours(args, wl):
         ev1.record()
         barrier()
         launches = args.steps * roll.launches_per_step
+        # per-kernel durations for the roofline: CUDA events recorded by the library around the dominant kernels on the
+        # launching stream, over a short EAGER continuation of the same step schedule (events cannot be read back from a
+        # graph replay; the eager launches keep the refill where the graph has it, beside the attention kernel)
+        lib.cn_dsrnn_enable_timing(policy._handle, 1)
+        lib.cn_env_enable_timing(eng.handle, 1)
+        for _ in range(min(args.steps, 50)):
+            buf = roll.step_eager()
+        torch.cuda.synchronize()
         obs = buf.obs()
         hx, masks = roll.hidden()
         roll.close()
@@ -291,12 +299,11 @@ def run_ours(args, wl):
         masks = masks.clone()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
-    # per-kernel durations for the roofline: CUDA events recorded by the library around the dominant kernels on the
-    # launching stream, over a short eager continuation of the same rollout (events cannot be read back from a graph)
-    lib.cn_dsrnn_enable_timing(policy._handle, 1)
-    lib.cn_env_enable_timing(eng.handle, 1)
-    obs, hx, masks = rollout(min(args.steps, 50), obs, hx, masks)
-    torch.cuda.synchronize()
+    if args.no_graph:
+        lib.cn_dsrnn_enable_timing(policy._handle, 1)
+        lib.cn_env_enable_timing(eng.handle, 1)
+        obs, hx, masks = rollout(min(args.steps, 50), obs, hx, masks)
+        torch.cuda.synchronize()
     edge_ms, n_fw, step_ms, n_st = C.c_float(), C.c_int(), C.c_float(), C.c_int()
     lib.cn_dsrnn_time_ms(policy._handle, C.byref(edge_ms), C.byref(n_fw))
     lib.cn_env_time_ms(eng.handle, C.byref(step_ms), C.byref(n_st))

@@ -77,6 +77,15 @@ class GraphedRollout(object):
         self.steps += 1
         return self.eng.bufs[self.parity]
 
+    def step_eager(self):
+        """The same step launched eagerly (same kernels, same schedule incl. the refill forked beside the attention kernel):
+        what bench.py uses to time individual kernels with CUDA events, which cannot be read back from a graph replay."""
+        p = self.parity
+        dst = self._one_step(p)
+        self.parity = p ^ 1
+        self.steps += 1
+        return dst
+
     def close(self):
         """Detach the forward from the env: eager `act` / `step` calls behave as usual afterwards."""
         self.policy.start_refill_of(None)
