@@ -364,6 +364,15 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                 const float *x = t.spatial ? a.spatial_edges + 2 * (size_t)m_l : a.temporal_edges + 2 * (size_t)m_l;
                 x0_l = x[0]; x1_l = x[1];
             }
+            if (DBG(128) && it > 0) {              // what-if (timing only): a perfect A staging -- hand every piece back at once
+                for (int piece = 0; piece < 3; ++piece) {
+                    mbar_wait(bar(kBarAFree + piece), (it - 1) & 1u);
+                    if (piece == 2) mbar_wait(bar(kBarHprev), (it - 1) & 1u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(ready_remote + 8u * piece);
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {   // hidden units [0,128) = k-blocks 1-2, then [128,256) = k-blocks 3-4
                 float4 hv[16];
