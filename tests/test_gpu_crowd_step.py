@@ -157,10 +157,13 @@ def test_rollout_tracks_oracle(kw, steps):
     assert n_done > 0
 
 
-def test_spare_and_fallback_resets_track_oracle():
+@pytest.mark.parametrize("refill_threads", ["64", "32", "256"])
+def test_spare_and_fallback_resets_track_oracle(refill_threads, monkeypatch):
     """Episodes that end are replaced by their pre-generated spare episode inside the step kernel; envs whose counters
     were changed behind the spares' back (cn_env_set_state) must fall back to the synchronous reset.  Both paths in one
-    batch, in lock-step with the oracle's plain reset."""
+    batch, in lock-step with the oracle's plain reset -- whatever the CTA size of the refill (thread t = try t, t + threads,
+    ...: the first accepted try is the same)."""
+    monkeypatch.setenv("CN_REFILL_THREADS", refill_threads)
     n = 512
     cfg_obj = _cfg(human_num=5)
     eng = G.make_engine(cfg_obj, n, seed=11)
