@@ -31,6 +31,7 @@ SYMBOLS = {
     "cn_env_refill": (C.c_int, [_P, _P]),
     "cn_dsrnn_set_refill_env": (C.c_int, [_P, _P]),
     "cn_dsrnn_set_edge_event": (C.c_int, [_P, _P]),
+    "cn_dsrnn_set_edge_image": (C.c_int, [_P, _P, _P, _P, _P]),
     "cn_env_last_launches": (C.c_int, [_P]),
     "cn_dsrnn_create": (C.c_int, [C.POINTER(abi.CnDsrnnWeights), C.c_int, _P, C.POINTER(_P)]),
     "cn_dsrnn_destroy": (C.c_int, [_P]),

@@ -384,6 +384,15 @@ extern "C" int cn_dsrnn_set_edge_event(CnDsrnn *m, void *event)
     return CN_OK;
 }
 
+extern "C" int cn_dsrnn_set_edge_image(CnDsrnn *m, void *in_hi, void *in_lo, void *out_hi, void *out_lo)
+{
+    if (!m) return fail(CN_ERR_ARG, "model is NULL");
+    if ((in_hi == nullptr) != (in_lo == nullptr) || (out_hi == nullptr) != (out_lo == nullptr))
+        return fail(CN_ERR_ARG, "the hi and lo halves of an image come in pairs");
+    dsrnn_set_edge_image(m, in_hi, in_lo, out_hi, out_lo);
+    return CN_OK;
+}
+
 extern "C" int cn_dsrnn_enable_timing(CnDsrnn *m, int enable)
 {
     if (!m) return fail(CN_ERR_ARG, "model is NULL");

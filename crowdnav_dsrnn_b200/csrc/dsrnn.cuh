@@ -17,4 +17,5 @@ const char *dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, cons
 void dsrnn_enable_timing(CnDsrnn *m, int enable);
 void dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env);
 void dsrnn_set_edge_event(CnDsrnn *m, void *event);
+void dsrnn_set_edge_image(CnDsrnn *m, void *in_hi, void *in_lo, void *out_hi, void *out_lo);
 float dsrnn_time_ms(CnDsrnn *m, int *count);

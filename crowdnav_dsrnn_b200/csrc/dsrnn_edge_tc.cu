@@ -40,7 +40,10 @@ constexpr int kRegsEpi = 128, kRegsStage = 96, kRegsMisc = 32;   // setmaxnreg b
 static_assert(256 * kRegsEpi + 256 * kRegsStage + 128 * kRegsMisc <= 640 * 96, "setmaxnreg only moves registers inside the CTA's launch allocation");
 // mbarrier map
 constexpr int kBarFull = 0, kBarEmpty = kBSlots, kBarAReady = 2 * kBSlots, kBarAFree = kBarAReady + 3,
-              kBarTmemFull = kBarAFree + 3, kBarTmemEmpty = kBarTmemFull + 2, kBarHprev = kBarTmemEmpty + 2, kNumBars = kBarHprev + 1;
+              kBarTmemFull = kBarAFree + 3, kBarTmemEmpty = kBarTmemFull + 2, kBarHprev = kBarTmemEmpty + 2,
+              kBarALoaded = kBarHprev + 1,      // resident-image path: TMA of k-blocks 1-2 / 3-4 of this CTA's rows has landed
+              kNumBars = kBarALoaded + 2;
+constexpr int kWarpAProducer = 18;             // resident-image path: issues the TMA loads of the A image
 
 constexpr int kOffAHi = 0;
 constexpr int kOffALo = kOffAHi + kKBlocks * kABlockBytes;        //  81920
@@ -57,6 +60,7 @@ struct TcState {
     float *enc;            // [2][192]
     int num_sms;
     CUtensorMap wmap;      // the weight images as a [rows x 64] 16-bit tensor, box = 96 rows (one CTA's half of a chunk)
+    void *encode_tiled;    // cuTensorMapEncodeTiled (resolved at run time): the resident-image path encodes two maps per forward
 };
 
 using namespace tc;
@@ -148,13 +152,17 @@ struct EdgeTcArgs {
     float *ws;                         // [rows, 4, 256] r | z | n | W_hn hm + b_hn
     __nv_bfloat16 *hm_hi, *hm_lo;      // [rows, 256] masked previous state
     __nv_bfloat16 *e_hi, *e_lo;        // [rows, 72] encoded input | 1 | 0 x 7
+    // resident split-bf16 image of the hidden state, LOGICAL row order (spatial rows env * H + human, then N * H + env):
+    // written by the epilogue when img_out_hi != NULL; read by TMA instead of the fp32 staging in the kImg instantiation
+    __nv_bfloat16 *img_out_hi, *img_out_lo;
 };
 
 struct TileInfo { bool spatial; int p, row0, M; };
 
-template <bool kTrain>
+template <bool kTrain, bool kImg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__ CUtensorMap wmap)
+edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__ CUtensorMap wmap,
+                   const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
@@ -182,6 +190,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
             mbar_init(bar(kBarAFree + i), 1);
         }
         mbar_init(bar(kBarHprev), kEpiWarps);     // this CTA's epilogue warps took h_prev of column tiles 2, 3 out of the A image
+        mbar_init(bar(kBarALoaded), 1); mbar_init(bar(kBarALoaded + 1), 1);
         mbar_init(bar(kBarTmemFull), 1); mbar_init(bar(kBarTmemFull + 1), 1);
         mbar_init(bar(kBarTmemEmpty), 2 * kEpiWarps); mbar_init(bar(kBarTmemEmpty + 1), 2 * kEpiWarps);   // leader only
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -241,6 +250,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
             size_t mem_row = 0;
             if (ok) { int env; mem_row = kTrain ? seq_out_row(t, m) : (size_t)mem_row_of(t, m, env); }
             float *wsrow = kTrain ? a.ws + mem_row * 1024 : nullptr;
+            const size_t img_row = (size_t)(t.spatial ? 0 : a.N * H) + (size_t)m;      // logical row of the resident image
             if (t.p != bias_p) {                  // at most twice per CTA: spatial pairs come first, then temporal ones
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 reinterpret_cast<float4 *>(s_bias)[threadIdx.x] = __ldg(reinterpret_cast<const float4 *>(a.bias4 + t.p * 4 * 256) + threadIdx.x);
@@ -299,6 +309,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     const int c0 = ct * 64 + c16 * 16;
                     if (ok && !DBG(4)) {
                         float o8[8], r8[8], z8[8], n8[8], h8[8];
+                        uint32_t ih[8], il[8];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int c = c0 + q * 4;
@@ -321,6 +332,16 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                             // 32-byte form halves the LSU work of the epilogue
                             if (q & 1) {
                                 st_global_v8(orow + c0 + (q - 1) * 4, o8);
+                                if (!kTrain && a.img_out_hi) {          // the same values as split bf16, for the next step's TMA:
+                                    const int w0 = (q >> 1) * 4;        // 16 columns = one 32-byte store per half (full sectors)
+                                    split_bf16x2(o8[0], o8[1], ih[w0], il[w0]); split_bf16x2(o8[2], o8[3], ih[w0 + 1], il[w0 + 1]);
+                                    split_bf16x2(o8[4], o8[5], ih[w0 + 2], il[w0 + 2]); split_bf16x2(o8[6], o8[7], ih[w0 + 3], il[w0 + 3]);
+                                    if (q == 3) {
+                                        const size_t io = img_row * 256 + (size_t)c0;
+                                        st_global_v8_b32(a.img_out_hi + io, ih);
+                                        st_global_v8_b32(a.img_out_lo + io, il);
+                                    }
+                                }
                                 if (kTrain && !DBG(16)) {
                                     float *w8 = wsrow + c0 + (q - 1) * 4;
                                     st_global_v8(w8, r8); st_global_v8(w8 + 256, z8); st_global_v8(w8 + 512, n8); st_global_v8(w8 + 768, h8);
@@ -370,6 +391,51 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     if (piece == 2) mbar_wait(bar(kBarHprev), (it - 1) & 1u);
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(ready_remote + 8u * piece);
+                }
+                continue;
+            }
+            if (kImg) {
+                // Resident-image path: k-blocks 1-4 arrive by TMA (warp kWarpAProducer) from the split-bf16 image the previous
+                // forward's epilogue wrote; this warp only encodes k-block 0 and zeroes the rows of finished envs (mask 0: the
+                // reference's h * mask) and the rows beyond the problem in shared memory before handing each piece on.
+                PROF_T0(t_f0);
+                if (it > 0) mbar_wait(bar(kBarAFree), (it - 1) & 1u);
+                PROF_ADD(p_wfree, t_f0);
+#pragma unroll
+                for (int b = 0; b < 16; ++b) {
+                    const int r = sw * 16 + b;
+                    const float x0 = __shfl_sync(0xffffffffu, x0_l, b), x1 = __shfl_sync(0xffffffffu, x1_l, b);
+                    const bool okb = __shfl_sync(0xffffffffu, (int)ok_l, b) != 0;
+                    float e[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int k = 2 * lane + i;
+                        e[i] = okb ? fmaxf(fmaf(enc[64 + k], x1, enc[k] * x0) + enc[128 + k], 0.f) : 0.f;
+                    }
+                    uint32_t hi, lo;
+                    split_bf16x2(e[0], e[1], hi, lo);
+                    const int off = sw128_offset(r, 2 * lane);
+                    *reinterpret_cast<uint32_t *>(smem + kOffAHi + off) = hi;
+                    *reinterpret_cast<uint32_t *>(smem + kOffALo + off) = lo;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ready_remote);
+                const unsigned dead = __ballot_sync(0xffffffffu, !ok_l || mk_l == 0.0f) & 0xffffu;      // lanes 0-15 <-> this warp's rows
+#pragma unroll 1
+                for (int p = 1; p <= 2; ++p) {
+                    PROF_T0(t_f);
+                    mbar_wait(bar(kBarALoaded + p - 1), it & 1u);
+                    PROF_ADD(p_wfree, t_f);
+                    for (unsigned todo = dead; todo; todo &= todo - 1u) {
+                        const int r = sw * 16 + (__ffs(todo) - 1);
+                        const int kb = 2 * p - 1 + (lane >> 4);
+                        unsigned char *row = smem + ((lane >> 3) & 1 ? kOffALo : kOffAHi) + kb * kABlockBytes + (r >> 3) * 1024 + (r & 7) * 128;
+                        *reinterpret_cast<uint4 *>(row + (lane & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(ready_remote + 8u * p);
                 }
                 continue;
             }
@@ -508,8 +574,30 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
             PROF_ADD(p_total, t_all);
             PROF_OUT(16, p_wait); PROF_OUT(17, p_total);
         }
+      } else if (warp == kWarpAProducer) {
+        // =============================================================== resident-image path: TMA loads of the A image.
+        // A piece (k-blocks 1-2 / 3-4: 2 x 2 boxes of 128 rows x 64 bf16) is fetched as soon as the MMAs of the previous tile
+        // (and the epilogue's h_prev reads) are done with it.
+        if (kImg && lane == 0) {
+            uint32_t it = 0;
+            for (int pair = cluster_id; pair < a.pairs_total; pair += num_clusters, ++it) {
+                const TileInfo t = tile_info(pair);
+                const int img_row0 = (t.spatial ? 0 : a.N * H) + t.row0;
+                for (int p = 1; p <= 2; ++p) {
+                    if (it > 0) {
+                        mbar_wait(bar(kBarAFree + p), (it - 1) & 1u);
+                        if (p == 2) mbar_wait(bar(kBarHprev), (it - 1) & 1u);
+                    }
+                    mbar_expect_tx(bar(kBarALoaded + p - 1), 4 * kABlockBytes);
+                    for (int kb = 2 * p - 1; kb <= 2 * p; ++kb) {
+                        tma_load_2d(s_base + kOffAHi + kb * kABlockBytes, &amap_hi, (kb - 1) * 64, img_row0, bar(kBarALoaded + p - 1));
+                        tma_load_2d(s_base + kOffALo + kb * kABlockBytes, &amap_lo, (kb - 1) * 64, img_row0, bar(kBarALoaded + p - 1));
+                    }
+                }
+            }
+        }
       } else if (warp != kWarpMma) {
-        // warps 18, 19 only pad the last warpgroup
+        // warp 19 only pads the last warpgroup
       } else if (rank != 0) {
         // the peer's lane of this warp has nothing to issue: cta_group::2 MMAs come from the leader alone
       } else {
@@ -635,6 +723,7 @@ const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void *
             dsrnn_tc_destroy(st);
             return "cuTensorMapEncodeTiled is not available from this driver";
         }
+        st->encode_tiled = fn;
         const cuuint64_t dims[2] = {64, (cuuint64_t)(img_bytes / 128)};      // 128-byte rows of the pre-swizzled images
         const cuuint64_t strides[1] = {128};
         const cuuint32_t box[2] = {64, kBChunkRows / 2}, estr[2] = {1, 1};
@@ -648,8 +737,9 @@ const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void *
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(edge_gru_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(edge_gru_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(edge_gru_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(edge_gru_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(edge_gru_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess) {
         dsrnn_tc_destroy(st);
         return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     }
@@ -682,8 +772,11 @@ void dsrnn_tc_destroy(void *state)
     delete st;
 }
 
+// `img`: resident split-bf16 image of the hidden state in logical row order -- img[0], img[1] = hi / lo of THIS forward's input
+// (valid only if the caller got them from the previous forward's img[2], img[3] for the same h_edge_in; masks must be 0 / 1),
+// img[2], img[3] = where to write the output's image; NULL members switch the respective half off.
 const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *, int n_envs, int H, const CnDsrnnIO *io, int precision,
-                                  cudaStream_t stream, int *launches)
+                                  cudaStream_t stream, int *launches, void *const img[4])
 {
     TcState *st = static_cast<TcState *>(state);
     if (!st) return "tensor-core edge stage was not initialised";
@@ -706,7 +799,27 @@ const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *, int n_env
 #endif
     const int max_pairs = st->num_sms / 2;                        // one CTA pair (cluster of 2) per TPC, persistent
     const int grid = 2 * (a.pairs_total < max_pairs ? a.pairs_total : max_pairs);
-    edge_gru_tc_kernel<false><<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap);
+    const bool three = precision == CN_PREC_BF16X3;
+    a.img_out_hi = three && img ? static_cast<__nv_bfloat16 *>(img[2]) : nullptr;
+    a.img_out_lo = three && img ? static_cast<__nv_bfloat16 *>(img[3]) : nullptr;
+    if (!a.img_out_lo) a.img_out_hi = nullptr;
+    if (three && img && img[0] && img[1] && a.debug == 0) {
+        typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        CUtensorMap mh, ml;
+        const cuuint64_t dims[2] = {256, (cuuint64_t)n_envs * (cuuint64_t)(H + 1)};
+        const cuuint64_t strides[1] = {512};
+        const cuuint32_t box[2] = {64, (cuuint32_t)kRows}, estr[2] = {1, 1};
+        for (int k = 0; k < 2; ++k)
+            if (reinterpret_cast<EncodeTiled>(st->encode_tiled)(k ? &ml : &mh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, img[k], dims, strides, box, estr,
+                                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return "cuTensorMapEncodeTiled failed for the hidden-state image";
+        edge_gru_tc_kernel<false, true><<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap, mh, ml);
+    } else {
+        edge_gru_tc_kernel<false, false><<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap, st->wmap, st->wmap);
+    }
     ++*launches;
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
@@ -738,7 +851,8 @@ const char *dsrnn_tc_edge_sequence_step(void *state, int n_envs, int H, const Cn
     a.e_hi = static_cast<__nv_bfloat16 *>(io->e_hi); a.e_lo = static_cast<__nv_bfloat16 *>(io->e_lo);
     const int max_pairs = st->num_sms / 2;
     const int grid = 2 * (a.pairs_total < max_pairs ? a.pairs_total : max_pairs);
-    edge_gru_tc_kernel<true><<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap);
+    a.img_out_hi = a.img_out_lo = nullptr;
+    edge_gru_tc_kernel<true, false><<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap, st->wmap, st->wmap);
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }

@@ -35,6 +35,7 @@ struct CnDsrnn {
     bool unfused_node = false;    // CN_NODE_UNFUSED=1: one launch per layer (development A/B switch)
     CnEnv *refill_env = nullptr;  // cn_dsrnn_set_refill_env: start this env's spare-episode refill beside the attention kernel
     cudaEvent_t edge_done = nullptr;   // cn_dsrnn_set_edge_event: recorded behind the edge stage of the next forwards
+    void *edge_img[4] = {nullptr, nullptr, nullptr, nullptr};   // cn_dsrnn_set_edge_image: resident split-bf16 image of the edge state
     bool timing;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;   // events around the edge stage
     int num_sms;
@@ -65,7 +66,7 @@ const char *dsrnn_tc_create(const CnDsrnnWeights *w, cudaStream_t stream, void *
 const char *dsrnn_tc_repack(void *state, const CnDsrnnWeights *w, cudaStream_t stream);
 void dsrnn_tc_destroy(void *state);
 const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *w, int n_envs, int H, const CnDsrnnIO *io,
-                                  int precision, cudaStream_t stream, int *launches);
+                                  int precision, cudaStream_t stream, int *launches, void *const img[4]);
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
@@ -491,6 +492,10 @@ const char *dsrnn_edge_sequence_step(CnDsrnn *m, int n_envs, int human_num, cons
 }
 void dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env) { m->refill_env = env; }
 void dsrnn_set_edge_event(CnDsrnn *m, void *event) { m->edge_done = (cudaEvent_t)event; }
+void dsrnn_set_edge_image(CnDsrnn *m, void *in_hi, void *in_lo, void *out_hi, void *out_lo)
+{
+    m->edge_img[0] = in_hi; m->edge_img[1] = in_lo; m->edge_img[2] = out_hi; m->edge_img[3] = out_lo;
+}
 
 // one linear layer, on CUDA cores (fp32) or tensor cores (bf16x3 / bf16)
 struct LinearRun {
@@ -547,7 +552,7 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
         edge_gru_simt_kernel<<<dim3((sp.M + LBM - 1) / LBM, 256 / LBN), 256, 0, s>>>(sp);
         launches += 2;
     } else {
-        const char *msg = dsrnn_tc_edge_forward(m->tc_state, &w, N, H, io, precision, s, &launches);
+        const char *msg = dsrnn_tc_edge_forward(m->tc_state, &w, N, H, io, precision, s, &launches, m->edge_img);
         if (msg) return msg;
     }
     if (m->timing) cudaEventRecord(m->pending.back().second, s);

@@ -416,6 +416,20 @@ class Policy(nn.Module):
         _lib.check(_lib.load().cn_dsrnn_set_edge_event(self._handle, C.c_void_p(event.cuda_event) if event is not None else None),
                    "cn_dsrnn_set_edge_event")
 
+    def set_edge_image(self, image_in=None, image_out=None):
+        """Resident split-bf16 image of the edge hidden state for the next forwards (rollout.GraphedRollout): `image_out` =
+        (hi, lo) bfloat16 tensors [N * (H + 1), 256] the forward fills for its h_edge output; `image_in` = the pair a previous
+        forward filled for exactly the h_edge tensor passed in (masks must be 0 / 1).  None switches either half off."""
+        if self._handle is None:
+            raise _lib.CrowdNavLibraryError("set_edge_image needs the library handle: run one forward first")
+        ptrs = []
+        for pair in (image_in, image_out):
+            for t in (pair if pair is not None else (None, None)):
+                if t is not None and (t.dtype is not torch.bfloat16 or not t.is_contiguous() or not t.is_cuda):
+                    raise ValueError("edge images are contiguous CUDA bfloat16 tensors")
+                ptrs.append(_ptr(t))
+        _lib.check(_lib.load().cn_dsrnn_set_edge_image(self._handle, *ptrs), "cn_dsrnn_set_edge_image")
+
     def cuda_forward(self, inputs, rnn_hxs, masks, need_features=True, out=None, workspace=None):
         """One rollout-step forward on the GPU. Returns (value[N,1], mean[N,2], features[N,256]|None, h_node, h_edge).
         `out` = dict of preallocated outputs (h_node, h_edge, value, mean) for callers that need static addresses

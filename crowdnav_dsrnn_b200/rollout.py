@@ -10,7 +10,7 @@ import torch
 
 
 class GraphedRollout(object):
-    def __init__(self, policy, venv, obs, hx=None, masks=None):
+    def __init__(self, policy, venv, obs, hx=None, masks=None, edge_image=True):
         """`obs` must be the observation returned by the engine's LAST reset()/step() (it lives in its current buffer)."""
         self.policy, self.venv = policy, venv
         eng = venv.engine
@@ -18,6 +18,13 @@ class GraphedRollout(object):
         self.eng = eng
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
         self.sets = [dict(h_node=z(n, 1, 128), h_edge=z(n, H + 1, 256), masks=z(n, 1), value=z(n, 1), mean=z(n, 2)) for _ in range(2)]
+        # resident split-bf16 image of each edge-state buffer (bf16x3 forward only): the forward that writes h_edge of a set also
+        # writes its image, the next forward reads its A operand from the image by TMA instead of converting the fp32 state
+        self.use_image = bool(edge_image) and policy.precision == "bf16x3"
+        self.image_mode = edge_image if edge_image in ("in", "out") else "both"      # "in" / "out": timing experiments only (stale images)
+        if self.use_image:
+            for s_ in self.sets:
+                s_["image"] = tuple(torch.zeros(n * (H + 1), 256, dtype=torch.bfloat16, device=dev) for _ in range(2))
         cur = eng.cur
         assert obs["robot_node"].data_ptr() == eng.bufs[cur].robot_node.data_ptr(), "obs must be the engine's current buffer"
         hx0 = {"human_node_rnn": z(n, 1, 128) if hx is None else hx["human_node_rnn"].reshape(n, 1, 128),
@@ -37,8 +44,12 @@ class GraphedRollout(object):
             a, b = self.sets[cur], self.sets[cur ^ 1]
             eng.join()
             b["masks"].copy_(m0)
-            policy.cuda_forward(obs, hx0, m0, need_features=False,
+            policy.cuda_forward(obs, hx0, m0, need_features=False,       # (creates the library handle)
                                 out=dict(h_node=b["h_node"], h_edge=b["h_edge"], value=a["value"], mean=a["mean"]))
+            if self.use_image:       # once more, now also writing the image of b's edge state (same inputs, same outputs)
+                policy.set_edge_image(None, b["image"])
+                policy.cuda_forward(obs, hx0, m0, need_features=False,
+                                    out=dict(h_node=b["h_node"], h_edge=b["h_edge"], value=a["value"], mean=a["mean"]))
             eng.join()
             policy.start_refill_of(eng)        # from here on the forward starts the refill of the step before it
             # eager warm-up of both parities (lazy handle / workspace creation must not happen inside a capture)
@@ -62,6 +73,9 @@ class GraphedRollout(object):
         with torch.no_grad():
             dst = eng.step(a["mean"], auto_reset=True, defer_refill=True)   # flips eng.cur to p ^ 1, writes bufs[p ^ 1]
             b["masks"] = dst.not_done                             # 1 - done, written by the step kernel itself
+            if self.use_image:       # this forward reads the image the previous one wrote for b's state and writes a's
+                self.policy.set_edge_image(None if self.image_mode == "out" else b["image"],
+                                           None if self.image_mode == "in" else a["image"])
             self.policy.cuda_forward(dst.obs(), {"human_node_rnn": b["h_node"], "human_human_edge_rnn": b["h_edge"]},
                                      b["masks"], need_features=False,
                                      out=dict(h_node=a["h_node"], h_edge=a["h_edge"], value=b["value"], mean=b["mean"]))
@@ -89,6 +103,8 @@ class GraphedRollout(object):
     def close(self):
         """Detach the forward from the env: eager `act` / `step` calls behave as usual afterwards."""
         self.policy.start_refill_of(None)
+        if self.use_image:
+            self.policy.set_edge_image(None, None)
         self.eng.join()
 
     def hidden(self):

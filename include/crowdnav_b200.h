@@ -255,6 +255,13 @@ int cn_dsrnn_set_refill_env(CnDsrnn *m, CnEnv *env);
  * the forward's stream right behind the edge-GRU stage -- the last part of a forward that fills the machine -- so another
  * stream can start the crowd step of an independent half batch beside the projection / attention / node kernels. */
 int cn_dsrnn_set_edge_event(CnDsrnn *m, void *event);
+/* Resident image of the edge hidden state for rollouts that feed a forward's output straight into the next forward
+ * (rollout.GraphedRollout): bfloat16 hi / lo matrices [n_envs * (human_num + 1), 256] in LOGICAL row order (spatial rows
+ * env * human_num + human first, then the temporal rows), x ~= hi + lo.  With out_hi / out_lo set, the next forwards (bf16x3)
+ * also write the image of h_edge_out; with in_hi / in_lo set they read their A operand from it by TMA instead of converting
+ * h_edge_in -- the caller guarantees that the image was written by the forward that produced exactly this h_edge_in and that
+ * the masks are 0 or 1.  Same results bit for bit.  NULL pairs switch either half off. */
+int cn_dsrnn_set_edge_image(CnDsrnn *m, void *in_hi, void *in_lo, void *out_hi, void *out_lo);
 /* number of kernels the last forward / step call launched (bench.py's gpu_launches claim) */
 int cn_dsrnn_last_launches(const CnDsrnn *m);
 int cn_env_last_launches(const CnEnv *env);

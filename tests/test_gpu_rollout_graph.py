@@ -14,8 +14,11 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
 
 
+@pytest.mark.parametrize("edge_image", [True, False])
 @pytest.mark.parametrize("H,n,kin", [(5, 64, "holonomic"), (10, 300, "unicycle")])
-def test_graph_replay_equals_eager_loop(H, n, kin):
+def test_graph_replay_equals_eager_loop(H, n, kin, edge_image):
+    """edge_image=True (the default): every forward of the replayed loop reads its hidden-state operand by TMA from the
+    split-bf16 image the previous forward's epilogue wrote (cn_dsrnn_set_edge_image) -- same bits as converting the fp32 state."""
     cfg = Config(kinematics=kin, human_num=H)
     obs_space, act_space = crowd_spaces(H)
     policy = Policy(obs_space.spaces, act_space, base="srnn", base_kwargs=cfg)
@@ -41,7 +44,8 @@ def test_graph_replay_equals_eager_loop(H, n, kin):
     def graphed():
         venv = CrowdVecEnv(cfg, n, DEV, seed=5, phase="train")
         obs = venv.reset()
-        roll = GraphedRollout(policy, venv, obs)            # the constructor already plays 2 (eager) steps
+        roll = GraphedRollout(policy, venv, obs, edge_image=edge_image)      # the constructor already plays 2 (eager) steps
+        assert roll.use_image == edge_image
         for _ in range(steps - roll.steps):
             buf = roll.step()
         st = {k: v.clone() for k, v in venv.engine.get_state().items()}

@@ -35,10 +35,16 @@ def main():
            "spatial_edges": torch.randn(N, H, 2, device=dev)}
     hx = {"human_node_rnn": torch.randn(N, 1, 128, device=dev) * 0.3, "human_human_edge_rnn": torch.randn(N, H + 1, 256, device=dev) * 0.3}
     masks = torch.ones(N, 1, device=dev)
+    # resident-image path (timing only: the input image holds arbitrary values): argv[3] = none | in | out | both
+    img_mode = sys.argv[3] if len(sys.argv) > 3 else "none"
+    imgs = [tuple((torch.randn(N * (H + 1), 256, device=dev) * s).to(torch.bfloat16) for s in (0.3, 0.001)) for _ in range(2)]
     for prec in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["bf16x3", "fp16"]):
         policy.precision = prec
         for _ in range(3):
             policy.act(obs, dict(hx), masks, deterministic=True)
+        if img_mode != "none" and prec == "bf16x3":
+            policy.set_edge_image(imgs[0] if img_mode in ("in", "both") else None, imgs[1] if img_mode in ("out", "both") else None)
+            print("== resident image: %s" % img_mode)
         torch.cuda.synchronize()
         fn(None, 1)
         for _ in range(iters):

@@ -31,7 +31,8 @@ def main():
     policy = policy.to(dev)
     if mode == "plain":
         venv = CrowdVecEnv(cfg, n, dev, seed=0, phase="train")
-        roll = GraphedRollout(policy, venv, venv.reset())
+        img = os.environ.get("CN_IMG_MODE", "both")          # both | off | in | out (in / out: timing only, stale images)
+        roll = GraphedRollout(policy, venv, venv.reset(), edge_image={"both": True, "off": False}.get(img, img))
     else:
         roll = PipelinedRollout(policy, cfg, n, dev, seed=0, phase="train", split=split)
     for _ in range(150):
