@@ -214,6 +214,10 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
+    // programmatic dependent launch: everything above (barriers, TMEM, the encoder table packed long before this forward)
+    // may run beside the tail of the previous kernel; the hidden state, masks and edge inputs are read from here on
+    pdl_wait();
+    pdl_launch_dependents();
 
     auto tile_info = [&](int pair) {
         TileInfo t;
@@ -800,6 +804,7 @@ const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *, int n_env
     const int max_pairs = st->num_sms / 2;                        // one CTA pair (cluster of 2) per TPC, persistent
     const int grid = 2 * (a.pairs_total < max_pairs ? a.pairs_total : max_pairs);
     const bool three = precision == CN_PREC_BF16X3;
+    cudaError_t lerr = cudaSuccess;
     a.img_out_hi = three && img ? static_cast<__nv_bfloat16 *>(img[2]) : nullptr;
     a.img_out_lo = three && img ? static_cast<__nv_bfloat16 *>(img[3]) : nullptr;
     if (!a.img_out_lo) a.img_out_hi = nullptr;
@@ -816,10 +821,11 @@ const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *, int n_env
                                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return "cuTensorMapEncodeTiled failed for the hidden-state image";
-        edge_gru_tc_kernel<false, true><<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap, mh, ml);
+        lerr = cn_launch(edge_gru_tc_kernel<false, true>, dim3(grid), dim3(kThreads), kSmemBytes + 1024, stream, CN_PDL_EDGE, a, st->wmap, mh, ml);
     } else {
-        edge_gru_tc_kernel<false, false><<<grid, kThreads, kSmemBytes + 1024, stream>>>(a, st->wmap, st->wmap, st->wmap);
+        lerr = cn_launch(edge_gru_tc_kernel<false, false>, dim3(grid), dim3(kThreads), kSmemBytes + 1024, stream, CN_PDL_EDGE, a, st->wmap, st->wmap, st->wmap);
     }
+    if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     ++*launches;
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

@@ -70,6 +70,12 @@ const char *dsrnn_tc_edge_forward(void *state, const CnDsrnnWeights *w, int n_en
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
+int cn_pdl_mask()
+{
+    static const int mask = [] { const char *e = getenv("CN_PDL"); return e ? atoi(e) : 0; }();
+    return mask;
+}
+
 // ---------------------------------------------------------------------------------------------- generic linear
 struct LinArgs {
     const float *X; int ldx;
@@ -276,6 +282,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * 4 + warp;
+    pdl_wait();                       // qt / h_edge come from the two kernels before this one
+    pdl_launch_dependents();          // the node / heads kernel may set itself up beside this (bandwidth-bound) kernel
     if (e >= N) return;
     const float4 qa = *reinterpret_cast<const float4 *>(qt + (size_t)e * 256 + lane * 8);
     const float4 qb = *reinterpret_cast<const float4 *>(qt + (size_t)e * 256 + lane * 8 + 4);
@@ -573,7 +581,8 @@ const char *dsrnn_forward(CnDsrnn *m, int N, int H, const CnDsrnnIO *io, int pre
             if (cn_env_refill(m->refill_env, s) != CN_OK) return "cn_env_refill (refill hook) failed";
             ++launches;
         }
-        attention_kernel<<<(N + 3) / 4, 128, 0, s>>>(io->h_edge_out, ws.qt, ws.cat, N, H);
+        if (cn_launch(attention_kernel, dim3((N + 3) / 4), dim3(128), 0, s, CN_PDL_ATTENTION, (const float *)io->h_edge_out, (const float *)ws.qt, ws.cat, N, H) != cudaSuccess)
+            return "attention_kernel launch failed";
         ++launches;
     }
 

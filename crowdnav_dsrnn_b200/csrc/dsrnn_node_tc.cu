@@ -236,6 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) node_heads_tc_kernel(const __grid
             }
         };
 
+        // the prologue above, the constant table and the weight stream of warp 8 (packed long before this forward) overlap the
+        // tail of the attention kernel; its output is read from here on
+        pdl_wait();
         for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
             const int row0 = tile * kRows;
             const int e = row0 + tid;
@@ -553,7 +556,8 @@ const char *dsrnn_node_tc_forward(void *state, int n_envs, const CnDsrnnIO *io, 
     a.three_pass = precision == CN_PREC_BF16X3 ? 1 : 0;
     a.fp16 = precision == CN_PREC_FP16 ? 1 : 0;
     const int grid = a.tiles < st->num_sms ? a.tiles : st->num_sms;
-    node_heads_tc_kernel<<<grid, kThreads, kSmemBytes + 1024, stream>>>(a);
+    const cudaError_t lerr = cn_launch(node_heads_tc_kernel, dim3(grid), dim3(kThreads), kSmemBytes + 1024, stream, CN_PDL_NODE, a);
+    if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     ++*launches;
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

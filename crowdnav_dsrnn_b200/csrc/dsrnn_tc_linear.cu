@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    pdl_wait();                       // everything above touched only this CTA's shared memory / TMEM
+    pdl_launch_dependents();
 
     if (warp < 8) {
         // =============================================================== A staging + epilogue
@@ -302,7 +304,8 @@ const char *tc_linear_run(const TcLinear *L, const TcLinearCall &c, int num_sms,
     a.m_tiles = (c.M + kRows - 1) / kRows;
     a.Y = c.Y; a.ldy = c.ldy; a.ycol0 = c.ycol0; a.act = c.act; a.three_pass = c.fp16 ? 0 : c.three_pass; a.fp16 = c.fp16;
     const int items = a.m_tiles * a.n_blocks;
-    linear_tc_kernel<<<items < num_sms ? items : num_sms, kThreads, kSmemBytes + 1024, stream>>>(a);
+    const cudaError_t lerr = cn_launch(linear_tc_kernel, dim3(items < num_sms ? items : num_sms), dim3(kThreads), kSmemBytes + 1024, stream, CN_PDL_LINEAR, a);
+    if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }
