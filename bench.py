@@ -43,8 +43,11 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch.  NOT sampled in this run: constants copied from ONE earlier
 # `ncu --set full` capture of the same kernels at the default sizes (the file named in `traffic_source`); only reported for that
 # workload / batch, null otherwise
-NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 357.76e6 + 310.53e6, "crowd_step_kernel": 17.73e6 + 6.31e6}}
-NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_final_kernels.txt (one ncu --set full capture, round 2; not re-measured by this run)"
+# edge kernel: the resident-image instantiation the graph rollout runs (reads the 352 MB split-bf16 image, writes the fp32 state
+# and the next image: 358 MB + 671 MB, profiles/r2_ncu_edge_image.txt); step kernel: profiles/r2_ncu_final_kernels.txt
+NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 358.05e6 + 670.93e6, "crowd_step_kernel": 17.73e6 + 6.31e6}}
+NCU_TRAFFIC_SOURCE = ("profiles/r2_ncu_edge_image.txt / profiles/r2_ncu_final_kernels.txt (one ncu --set full capture each, round 2; "
+                      "not re-measured by this run)")
 
 
 def reference_python_baseline(workload):
