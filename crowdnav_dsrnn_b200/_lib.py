@@ -95,3 +95,20 @@ def check(rc, what):
     if rc != 0:
         msg = load().cn_last_error()
         raise CrowdNavLibraryError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def raw_stream(device_index):
+    """cudaStream_t of torch's current stream on `device_index` as a c_void_p.  This sits on the host's critical path
+    of every step (right after the synchronisation of a train.py-style loop): the raw getter costs ~0.2 us, building a
+    torch.cuda.Stream object ~3 us."""
+    try:
+        return C.c_void_p(_raw_stream(device_index))
+    except NameError:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+try:
+    from torch._C import _cuda_getCurrentRawStream as _raw_stream
+except ImportError:      # older / CPU-only torch builds: raw_stream() falls back to torch.cuda.current_stream
+    pass

@@ -23,25 +23,46 @@ class StepBuffers:
     """One set of per-step outputs (torch-owned device tensors in the reference's shapes)."""
 
     # per-step records a caller may keep beyond the next step (infos): carved out of ONE block so that a single
-    # device-side clone snapshots them all (envs.LazyInfos)
-    INFO_FIELDS = (("info", torch.float32, abi.INFO_DIM), ("reward", torch.float32, 1), ("episode_return", torch.float32, 1),
+    # device-side clone snapshots them all (envs.LazyInfos).  reward | done come last and next to each other: they are what
+    # the reference-facing step() brings to the host, in one copy (envs.CrowdVecEnv.step_wait)
+    INFO_FIELDS = (("info", torch.float32, abi.INFO_DIM), ("episode_return", torch.float32, 1),
                    ("event", torch.int32, 1), ("scenario", torch.int32, 1), ("episode_length", torch.int32, 1),
-                   ("done", torch.uint8, 1))
+                   ("reward", torch.float32, 1), ("done", torch.uint8, 1))
+    _ITEMSIZE = {torch.float32: 4, torch.int32: 4, torch.uint8: 1}
+    _layouts = {}
+
+    @classmethod
+    def info_layout(cls, n):
+        """((name, dtype, width, byte offset, byte length), ...), total bytes -- every field starts on a 256-byte boundary."""
+        lay = cls._layouts.get(n)
+        if lay is None:
+            fields, off = [], 0
+            for name, dtype, width in cls.INFO_FIELDS:
+                nbytes = n * width * cls._ITEMSIZE[dtype]
+                fields.append((name, dtype, width, off, nbytes))
+                off += (nbytes + 255) & ~255
+            lay = cls._layouts[n] = (tuple(fields), off)
+        return lay
 
     @classmethod
     def carve_info(cls, block, n):
-        """Typed views (name -> tensor) into an info block; every view starts on a 256-byte boundary."""
-        views, off = {}, 0
-        for name, dtype, width in cls.INFO_FIELDS:
-            nbytes = n * width * torch.empty(0, dtype=dtype).element_size()
+        """Typed views (name -> tensor) into an info block."""
+        views = {}
+        for name, dtype, width, off, nbytes in cls.info_layout(n)[0]:
             v = block[off:off + nbytes].view(dtype)
             views[name] = v.view(n, width) if width > 1 else v
-            off += (nbytes + 255) & ~255
         return views
 
     @classmethod
     def info_block_bytes(cls, n):
-        return sum(((n * width * torch.empty(0, dtype=dtype).element_size()) + 255) & ~255 for _, dtype, width in cls.INFO_FIELDS)
+        return cls.info_layout(n)[1]
+
+    @classmethod
+    def host_range(cls, n):
+        """Byte range of the info block that holds reward | done, and done's offset inside it."""
+        lay = {f[0]: f for f in cls.info_layout(n)[0]}
+        lo, hi = lay["reward"][3], lay["done"][3] + lay["done"][4]
+        return lo, hi, lay["done"][3] - lo
 
     def __init__(self, n, h, device):
         f32 = dict(dtype=torch.float32, device=device)
@@ -53,6 +74,8 @@ class StepBuffers:
         self.info_block = torch.zeros(self.info_block_bytes(n), dtype=torch.uint8, device=device)
         for name, view in self.carve_info(self.info_block, n).items():
             setattr(self, name, view)
+        lo, hi, _ = self.host_range(n)
+        self.host_bytes = self.info_block[lo:hi]           # reward | done as one contiguous byte range
         self.goal_changed = torch.zeros(n, dtype=torch.int32, device=device)
         self.not_done = torch.ones(n, 1, **f32)            # 1 - done: the masks of the next Policy.act
         self.obs_struct = abi.CnObsOut(_ptr(self.robot_node), _ptr(self.temporal_edges), _ptr(self.spatial_edges),
@@ -106,7 +129,7 @@ class CrowdEngine:
     __del__ = close
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return _lib.raw_stream(self.device_index)
 
     # ------------------------------------------------------------------ API
     def reset(self, mask=None):

@@ -34,11 +34,20 @@ class LazyInfos(object):
         # The engine double-buffers its outputs, so `buf` is overwritten by the step after next.  The reference returns
         # materialised dicts that stay valid for ever (train.py keeps them for logging), so the per-step records are
         # snapshotted here -- one device-side clone of the block they are carved from, no synchronisation.
-        snap = StepBuffers.carve_info(buf.info_block.clone(), buf.n)
-        self.tensors = {k: snap[k] for k in ("event", "scenario", "info", "done", "episode_return", "episode_length")}
+        # The typed views are carved out of the snapshot on first use: a training loop that never looks at `infos` pays
+        # for one clone per step and nothing else.
+        self._block, self._n = buf.info_block.clone(), buf.n
+        self._tensors = None
         self._side = side_preference
         self._host = None
         self._t0 = t0
+
+    @property
+    def tensors(self):
+        if self._tensors is None:
+            snap = StepBuffers.carve_info(self._block, self._n)
+            self._tensors = {k: snap[k] for k in ("event", "scenario", "info", "done", "episode_return", "episode_length")}
+        return self._tensors
 
     def _fetch(self):
         if self._host is None:
@@ -46,7 +55,7 @@ class LazyInfos(object):
         return self._host
 
     def __len__(self):
-        return self.tensors["event"].shape[0]
+        return self._n
 
     def __getitem__(self, i):
         h = self._fetch()
@@ -111,7 +120,7 @@ class CrowdVecEnv(object):
         self._side = bool(config.test.side_preference)
         self._t0 = time.time()
         self._pending = None
-        self._pin_reward = self._pin_done = None
+        self._pin_reward = self._pin_done = self._pin_host = None
         self._test_case = test_case
         envs = [SimpleNamespace(env=_EnvView(self, i)) for i in range(min(self.num_envs, 64))]
         self.venv = SimpleNamespace(envs=envs, num_envs=self.num_envs)
@@ -133,17 +142,19 @@ class CrowdVecEnv(object):
         # VecPyTorch.step_wait keeps reward on the CPU and done as a numpy array (envs.py:231-239): both cross PCIe in
         # ONE synchronisation through pinned staging buffers (fresh host tensors are returned, like the reference)
         if self._pin_reward is None:
-            self._pin_reward = torch.empty(self.num_envs, dtype=torch.float32)
-            self._pin_done = torch.empty(self.num_envs, dtype=torch.uint8)
+            lo, hi, done_off = StepBuffers.host_range(self.num_envs)
+            pin = torch.empty(hi - lo, dtype=torch.uint8)
             if self.device.type == "cuda":
-                self._pin_reward, self._pin_done = self._pin_reward.pin_memory(), self._pin_done.pin_memory()
-        self._pin_reward.copy_(buf.reward, non_blocking=True)
-        self._pin_done.copy_(buf.done, non_blocking=True)
+                pin = pin.pin_memory()
+            self._pin_host = pin
+            self._pin_reward = pin[:4 * self.num_envs].view(torch.float32)
+            self._pin_done = pin[done_off:done_off + self.num_envs].numpy()
+        self._pin_host.copy_(buf.host_bytes, non_blocking=True)
         infos = LazyInfos(buf, self._side, self._t0)      # its device-side snapshot is enqueued BEFORE the host waits
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
         reward = self._pin_reward.clone().unsqueeze(1)
-        done = self._pin_done.numpy().astype(bool)
+        done = self._pin_done.astype(bool)
         return buf.obs(), reward, done, infos
 
     def step(self, actions):

@@ -338,7 +338,7 @@ class Policy(nn.Module):
         sd = dict(self.named_parameters())
         return [sd[abi.DSRNN_STATE_DICT_KEYS[f]] for f in abi.DSRNN_WEIGHT_FIELDS]
 
-    _TRANSIENT = ("_handle", "_weights_key", "_workspace", "_workspace_key", "_param_list", "_gauss_cache", "_refill_engine")
+    _TRANSIENT = ("_handle", "_weights_key", "_workspace", "_workspace_key", "_param_list", "_gauss_cache", "_refill_engine", "_spare_out")
 
     def __getstate__(self):                     # copy.deepcopy / torch.save(policy): library handles and caches stay behind
         state = dict(self.__dict__)
@@ -448,10 +448,14 @@ class Policy(nn.Module):
             raise ValueError("inconsistent batch shapes for the DS-RNN forward")
         opts = dict(dtype=torch.float32, device=device)
         if out is None:
-            hn_out = torch.empty(N, 1, 128, **opts)
-            he_out = torch.empty(N, H + 1, 256, **opts)
-            value = torch.empty(N, 1, **opts)
-            mean = torch.empty(N, 2, **opts)
+            # fresh output tensors every call (the reference returns new tensors); they were allocated at the END of the
+            # previous call, while the GPU was busy, so the allocator is off the critical path of a train.py-style loop
+            stream = _lib.raw_stream(device.index if device.index is not None else torch.cuda.current_device())
+            spare = self.__dict__.pop("_spare_out", None)
+            if spare is not None and spare[0] == (N, H, device, stream.value):      # same stream: the allocator's own ordering holds
+                hn_out, he_out, value, mean = spare[1]
+            else:
+                hn_out, he_out, value, mean = self._alloc_out(N, H, opts)
         else:
             hn_out, he_out, value, mean = out["h_node"], out["h_edge"], out["value"], out["mean"]
             for t_, numel in ((hn_out, N * 128), (he_out, N * (H + 1) * 256), (value, N), (mean, 2 * N)):
@@ -468,11 +472,18 @@ class Policy(nn.Module):
             workspace = self._workspace
         io = abi.CnDsrnnIO(_ptr(rn), _ptr(te), _ptr(se), _ptr(hn), _ptr(he), _ptr(mk), _ptr(hn_out), _ptr(he_out),
                            _ptr(value), _ptr(mean), _ptr(feat))
-        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        if out is not None:
+            stream = _lib.raw_stream(device.index if device.index is not None else torch.cuda.current_device())
         _lib.check(lib.cn_dsrnn_forward(self._handle, N, H, C.byref(io), abi.PRECISIONS[self.precision],
                                         _ptr(workspace), workspace.numel(), stream), "cn_dsrnn_forward")
         self.gpu_launches += lib.cn_dsrnn_last_launches(self._handle)
+        if out is None:
+            self.__dict__["_spare_out"] = ((N, H, device, stream.value), self._alloc_out(N, H, opts))
         return value, mean, feat, hn_out, he_out
+
+    @staticmethod
+    def _alloc_out(N, H, opts):
+        return (torch.empty(N, 1, 128, **opts), torch.empty(N, H + 1, 256, **opts), torch.empty(N, 1, **opts), torch.empty(N, 2, **opts))
 
     # ------------------------------------------------------------------ reference API
     def act(self, inputs, rnn_hxs, masks, deterministic=False):
