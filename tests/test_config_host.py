@@ -106,6 +106,30 @@ def test_lazy_infos_reference_shape():
     assert "bad_transition" not in c
 
 
+def test_info_block_layout_and_host_range():
+    """reward | done sit next to each other at the end of the info block (one host copy in CrowdVecEnv.step_wait); every field
+    starts on a 256-byte boundary; LazyInfos snapshots the block and carves its views on first use."""
+    from crowdnav_dsrnn_b200.engine import StepBuffers
+    for n in (1, 3, 16, 1000):
+        fields, total = StepBuffers.info_layout(n)
+        assert [f[0] for f in fields][-2:] == ["reward", "done"] and total == StepBuffers.info_block_bytes(n)
+        assert all(f[3] % 256 == 0 for f in fields) and total % 256 == 0
+        lo, hi, done_off = StepBuffers.host_range(n)
+        by = {f[0]: f for f in fields}
+        assert lo == by["reward"][3] and lo + done_off == by["done"][3] and hi == by["done"][3] + n and hi <= total
+        block = (torch.arange(total) % 251).to(torch.uint8)
+        views = StepBuffers.carve_info(block, n)
+        host = block[lo:hi]
+        assert torch.equal(host[:4 * n].view(torch.float32), views["reward"]) and torch.equal(host[done_off:done_off + n], views["done"])
+        assert views["info"].shape == (n, abi.INFO_DIM) and views["event"].dtype is torch.int32
+    buf = _FakeBuf()
+    infos = LazyInfos(buf, side_preference=False, t0=0.0)
+    assert infos._tensors is None and len(infos) == 3          # nothing carved yet
+    buf.event.zero_()                                           # the engine reuses its buffer two steps later ...
+    assert infos.tensors["event"].tolist() == [abi.EV_NOTHING, abi.EV_DANGER, abi.EV_COLLISION]      # ... the snapshot does not care
+    assert infos.tensors is infos.tensors
+
+
 def test_policy_state_dict_is_checkpoint_compatible_and_cpu_act_fails_loudly():
     obs, act = crowd_spaces(5)
     p = Policy(obs.spaces, act, base="srnn", base_kwargs=Config())
