@@ -605,8 +605,10 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
       } else if (rank != 0) {
         // the peer's lane of this warp has nothing to issue: cta_group::2 MMAs come from the leader alone
       } else {
-        // =============================================================== MMA issuer (one lane of the leader CTA)
-        if (lane == 0) {
+        // =============================================================== MMA issuer (warp 17 of the leader CTA)
+        // warp-uniform control flow; the elected lane issues (see elect_one_sync in tc_common.cuh)
+        {
+            const uint32_t lead = elect_one_sync();
             uint32_t ctg = 0, it = 0;
             const uint32_t id192 = a.fp16 ? idesc_f16_m256(192) : idesc_bf16_m256(192);
             // shared-memory descriptors: the high word is constant, the low word is (address >> 4) | LBO; stepping K by 16
@@ -621,10 +623,10 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
             uint32_t slot = 0, full_parity = 0;       // ring position, advanced incrementally (no division in the loop)
             // four K=16 steps of one 64-wide k-block: D[dcol..+192) (+)= A(a_lo) * B(b_lo)^T on both CTAs of the pair
             auto mma_kblock = [&](uint32_t dcol, uint32_t a_lo, uint32_t b_lo, bool overwrite_first) {
-                umma2_f16(dcol, make_desc(a_lo), make_desc(b_lo), id192, overwrite_first ? 0u : 1u);
-                umma2_f16(dcol, make_desc(a_lo + 2), make_desc(b_lo + 2), id192, 1u);
-                umma2_f16(dcol, make_desc(a_lo + 4), make_desc(b_lo + 4), id192, 1u);
-                umma2_f16(dcol, make_desc(a_lo + 6), make_desc(b_lo + 6), id192, 1u);
+                umma2_f16_if(lead, dcol, make_desc(a_lo), make_desc(b_lo), id192, overwrite_first ? 0u : 1u);
+                umma2_f16_if(lead, dcol, make_desc(a_lo + 2), make_desc(b_lo + 2), id192, 1u);
+                umma2_f16_if(lead, dcol, make_desc(a_lo + 4), make_desc(b_lo + 4), id192, 1u);
+                umma2_f16_if(lead, dcol, make_desc(a_lo + 6), make_desc(b_lo + 6), id192, 1u);
             };
             auto next_chunk = [&](uint32_t &b_lo) {     // wait for the next weight chunk (both halves), return its descriptor word
                 PROF_T0(twb);
@@ -636,7 +638,7 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
             PROF_DECL(p_commit);
             auto release_chunk = [&]() {
                 PROF_T0(tc0);
-                umma2_commit_pair(bar(kBarEmpty + slot));
+                umma2_commit_pair_if(lead, bar(kBarEmpty + slot));
                 PROF_ADD(p_commit, tc0);
                 if (++slot == kBSlots) { slot = 0; full_parity ^= 1u; }
             };
@@ -670,15 +672,15 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                             if (!DBG(2)) mma_kblock(dcol, a_hi, b_lo, false);
                             release_chunk();
                         }
-                        if (ct == kColTiles - 1 && kb == 0) umma2_commit_pair(bar(kBarAFree));            // k-block 0 of A is free
-                        if (ct == kColTiles - 1 && kb == 2) umma2_commit_pair(bar(kBarAFree + 1));        // k-blocks 1-2 are free
+                        if (ct == kColTiles - 1 && kb == 0) umma2_commit_pair_if(lead, bar(kBarAFree));            // k-block 0 of A is free
+                        if (ct == kColTiles - 1 && kb == 2) umma2_commit_pair_if(lead, bar(kBarAFree + 1));        // k-blocks 1-2 are free
                     }
-                    umma2_commit_pair(bar(kBarTmemFull + buf));     // accumulators of this column tile are complete in both CTAs
+                    umma2_commit_pair_if(lead, bar(kBarTmemFull + buf));     // accumulators of this column tile are complete in both CTAs
                 }
-                umma2_commit_pair(bar(kBarAFree + 2));              // every MMA that reads this tile's A image has retired
+                umma2_commit_pair_if(lead, bar(kBarAFree + 2));              // every MMA that reads this tile's A image has retired
             }
             PROF_ADD(p_total, t_all);
-            PROF_OUT(8, p_wa); PROF_OUT(9, p_we); PROF_OUT(10, p_wb); PROF_OUT(11, p_commit); PROF_OUT(12, p_total);
+            if (lane == 0) { PROF_OUT(8, p_wa); PROF_OUT(9, p_we); PROF_OUT(10, p_wb); PROF_OUT(11, p_commit); PROF_OUT(12, p_total); }
         }
       }
     }

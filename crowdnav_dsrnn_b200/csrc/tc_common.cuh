@@ -102,6 +102,28 @@ __device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Warp-uniform issue: the WHOLE issuing warp runs the loop (so the compiler keeps descriptors, TMEM addresses and loop counters
+// in uniform registers and steps them with the uniform datapath); only the lane elected once by elect_one_sync() executes the
+// instruction.  Inside an `if (lane == 0)` region the same code is divergent control flow: every operand is then moved to uniform
+// registers with an ELECT / R2UR.BROADCAST waterfall loop in front of every single UTCHMMA (16 instructions, ~40 cycles).
+__device__ __forceinline__ uint32_t elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void umma2_f16_if(uint32_t lead, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_pair_if(uint32_t lead, uint32_t bar)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+                 ::"r"(bar), "h"((uint16_t)3), "r"(lead) : "memory");
+}
 // completion of all prior MMAs of this thread arrives on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma2_commit_pair(uint32_t bar)
 {
