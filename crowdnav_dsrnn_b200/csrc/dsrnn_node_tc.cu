@@ -400,25 +400,27 @@ __global__ void __launch_bounds__(kThreads, 1) node_heads_tc_kernel(const __grid
                 }
         }
     } else {
-        // =============================================================== MMA issuer (one lane)
-        if (lane == 0) {
+        // =============================================================== MMA issuer: warp-uniform control flow, the elected lane
+        // issues (elect_one_sync in tc_common.cuh: keeps the descriptors in uniform registers)
+        {
+            const uint32_t lead = elect_one_sync();
             constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
             auto make_desc = [](uint32_t lo) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi)); return d; };
             const uint32_t a_hi_desc_lo = ((s_base + kOffAHi) >> 4) | (1u << 16), a_lo_desc_lo = ((s_base + kOffALo) >> 4) | (1u << 16);
             const uint32_t b_desc_lo = ((s_base + kOffB) >> 4) | (1u << 16);
             uint32_t slot = 0, full_parity = 0, ready_count = 0;
             auto mma_kblock = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool overwrite_first) {
-                umma_bf16(d, make_desc(a_lo), make_desc(b_lo), idesc, overwrite_first ? 0u : 1u);
-                umma_bf16(d, make_desc(a_lo + 2), make_desc(b_lo + 2), idesc, 1u);
-                umma_bf16(d, make_desc(a_lo + 4), make_desc(b_lo + 4), idesc, 1u);
-                umma_bf16(d, make_desc(a_lo + 6), make_desc(b_lo + 6), idesc, 1u);
+                umma_bf16_if(lead, d, make_desc(a_lo), make_desc(b_lo), idesc, overwrite_first ? 0u : 1u);
+                umma_bf16_if(lead, d, make_desc(a_lo + 2), make_desc(b_lo + 2), idesc, 1u);
+                umma_bf16_if(lead, d, make_desc(a_lo + 4), make_desc(b_lo + 4), idesc, 1u);
+                umma_bf16_if(lead, d, make_desc(a_lo + 6), make_desc(b_lo + 6), idesc, 1u);
             };
             for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
                 int epoch = -1;
                 for (int c = 0; c < kNumChunks; ++c) {
                     const NodeChunk ch = c_chunks[c];
                     if ((int)ch.epoch != epoch) {
-                        if (epoch >= 0) umma_commit(bar(kBarEpochDone));
+                        if (epoch >= 0) umma_commit_if(lead, bar(kBarEpochDone));
                         epoch = ch.epoch;
                         mbar_wait(bar(kBarAReady), ready_count & 1u);
                         ++ready_count;
@@ -437,11 +439,11 @@ __global__ void __launch_bounds__(kThreads, 1) node_heads_tc_kernel(const __grid
                         } else {
                             mma_kblock(d, a_hi, b_lo, idesc, false);
                         }
-                        umma_commit(bar(kBarEmpty + slot));
+                        umma_commit_if(lead, bar(kBarEmpty + slot));
                         if (++slot == kBSlots) { slot = 0; full_parity ^= 1u; }
                     }
                 }
-                umma_commit(bar(kBarEpochDone));
+                umma_commit_if(lead, bar(kBarEpochDone));
             }
         }
     }

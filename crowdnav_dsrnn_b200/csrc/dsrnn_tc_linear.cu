@@ -189,8 +189,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
             }
         }
     } else {
-        // =============================================================== MMA issuer
-        if (lane == 0) {
+        // =============================================================== MMA issuer: warp-uniform control flow, the elected lane issues
+        {
+            const uint32_t lead = elect_one_sync();
             uint32_t it = 0, item_iter = 0;
             const uint32_t idesc = a.fp16 ? idesc_f16(a.n_tile) : idesc_bf16(a.n_tile);
             // descriptor high word is constant; K steps / slots / hi-lo images only add to the low word (address >> 4 | LBO)
@@ -212,12 +213,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
                         const uint32_t aa = ps == 1 ? a_lo : a_hi, bb = ps == 2 ? b_lo : b_hi;
 #pragma unroll
                         for (int k16 = 0; k16 < 4; ++k16)
-                            umma_bf16(tmem_base, make_desc(aa + 2 * k16), make_desc(bb + 2 * k16), idesc, (kb | ps | k16) != 0 ? 1u : 0u);
+                            umma_bf16_if(lead, tmem_base, make_desc(aa + 2 * k16), make_desc(bb + 2 * k16), idesc, (kb | ps | k16) != 0 ? 1u : 0u);
                     }
-                    umma_commit(bar(2 + slot));
-                    umma_commit(bar(6 + slot));
+                    umma_commit_if(lead, bar(2 + slot));
+                    umma_commit_if(lead, bar(6 + slot));
                 }
-                umma_commit(bar(8));
+                umma_commit_if(lead, bar(8));
             }
         }
     }

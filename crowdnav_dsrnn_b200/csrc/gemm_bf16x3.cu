@@ -91,6 +91,12 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
 }
+__device__ __forceinline__ void umma_commit_mc_if(uint32_t lead, uint32_t bar, uint16_t mask)      // warp-uniform issue form
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+                 ::"r"(bar), "h"(mask), "r"(lead) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_nctarank()
 {
     uint32_t r;
@@ -212,8 +218,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        // =============================================================== MMA issuer
-        if (lane == 0) {
+        // =============================================================== MMA issuer: warp-uniform control flow, the elected lane issues
+        // (elect_one_sync in tc_common.cuh: descriptors stay in uniform registers, no R2UR waterfall per UTCHMMA)
+        {
+            const uint32_t lead = elect_one_sync();
             constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO = 1024 B, version 1, SWIZZLE_128B
             auto make_desc = [](uint32_t lo) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi)); return d; };
             uint32_t stage = 0, parity = 0, iter = 0;
@@ -244,22 +252,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
                     const uint32_t b_hi = (sb >> 4) | b_lbo, b_lo = ((sb + a.b_off_lo) >> 4) | b_lbo;
 #pragma unroll
                     for (int k16 = 0; k16 < 4; ++k16) {
-                        umma_bf16(d, make_desc(a_hi + k16 * a_step), make_desc(b_hi + k16 * b_step), idesc, first ? 0u : 1u);
+                        umma_bf16_if(lead, d, make_desc(a_hi + k16 * a_step), make_desc(b_hi + k16 * b_step), idesc, first ? 0u : 1u);
                         first = 0;
                     }
                     if (g.a_lo_on) {
 #pragma unroll
-                        for (int k16 = 0; k16 < 4; ++k16) umma_bf16(d, make_desc(a_lo + k16 * a_step), make_desc(b_hi + k16 * b_step), idesc, 1u);
+                        for (int k16 = 0; k16 < 4; ++k16) umma_bf16_if(lead, d, make_desc(a_lo + k16 * a_step), make_desc(b_hi + k16 * b_step), idesc, 1u);
                     }
                     if (g.b_lo_on) {
 #pragma unroll
-                        for (int k16 = 0; k16 < 4; ++k16) umma_bf16(d, make_desc(a_hi + k16 * a_step), make_desc(b_lo + k16 * b_step), idesc, 1u);
+                        for (int k16 = 0; k16 < 4; ++k16) umma_bf16_if(lead, d, make_desc(a_hi + k16 * a_step), make_desc(b_lo + k16 * b_step), idesc, 1u);
                     }
-                    if (csize == 1) umma_commit(bar_empty(stage));
-                    else umma_commit_mc(bar_empty(stage), cmask);       // frees the stage in every CTA of the cluster
+                    if (csize == 1) umma_commit_if(lead, bar_empty(stage));
+                    else umma_commit_mc_if(lead, bar_empty(stage), cmask);       // frees the stage in every CTA of the cluster
                     if (++stage == (uint32_t)a.stages) { stage = 0; parity ^= 1u; }
                 }
-                umma_commit(bar_tfull(buf));
+                umma_commit_if(lead, bar_tfull(buf));
             }
         }
     } else {
