@@ -310,6 +310,17 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                     tmem_ld16(t0 + 2 * 64 + c16 * 16, zg);
                     tmem_ld16(t0 + 3 * 64 + c16 * 16, nh);
                     tmem_ld_wait();
+                    if (cc == 1) {
+                        // everything this warp needs from the accumulator buffer is in registers now: clear n_h for the next column
+                        // tile and hand the buffer back BEFORE the gate math and the stores of the second half, so the MMAs of the
+                        // column tile after next can start that much earlier
+                        tmem_st16_zero(t0 + 192u + (uint32_t)chalf * 32u);          // n_h starts the next column tile from zero
+                        tmem_st16_zero(t0 + 192u + (uint32_t)chalf * 32u + 16u);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_remote_cta(empty_remote + 8u * buf);
+                    }
                     const int c0 = ct * 64 + c16 * 16;
                     if (ok && !DBG(4)) {
                         float o8[8], r8[8], z8[8], n8[8], h8[8];
@@ -354,12 +365,6 @@ edge_gru_tc_kernel(const __grid_constant__ EdgeTcArgs a, const __grid_constant__
                         }
                     }
                 }
-                tmem_st16_zero(t0 + 192u + (uint32_t)chalf * 32u);          // n_h starts the next column tile from zero
-                tmem_st16_zero(t0 + 192u + (uint32_t)chalf * 32u + 16u);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote_cta(empty_remote + 8u * buf);
                 PROF_ADD(p_epi, t_e);
             }
         }
