@@ -44,8 +44,8 @@ WORKLOADS = {
 # `ncu --set full` capture of the same kernels at the default sizes (the file named in `traffic_source`); only reported for that
 # workload / batch, null otherwise
 # edge kernel: the resident-image instantiation the graph rollout runs (reads the 352 MB split-bf16 image, writes the fp32 state
-# and the next image: 358 MB + 671 MB, profiles/r2_ncu_edge_image.txt); step kernel: profiles/r2_ncu_final_other_kernels.txt
-NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 358.05e6 + 670.93e6, "crowd_step_kernel": 18.12e6 + 3.58e6}}
+# and the next image: 358 MB + 658 MB, profiles/r2_ncu_edge_image.txt); step kernel: profiles/r2_ncu_final_other_kernels.txt
+NCU_TRAFFIC_BYTES = {("c3", 16384): {"edge_gru_tc_kernel": 358.48e6 + 657.58e6, "crowd_step_kernel": 18.12e6 + 3.58e6}}
 NCU_TRAFFIC_SOURCE = ("profiles/r2_ncu_edge_image.txt / profiles/r2_ncu_final_other_kernels.txt (one ncu --set full capture each, "
                       "end of round 2; not re-measured by this run)")
 
