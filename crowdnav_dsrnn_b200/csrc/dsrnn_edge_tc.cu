@@ -14,7 +14,9 @@
 //   warp 16     streams this CTA's half (96 of 192 rows, 12 KB) of the pre-swizzled weight chunks with
 //               cp.async.bulk.tensor .cta_group::2 into a 5-slot ring; both CTAs' copies complete on the leader's mbarrier.
 //   warp 17     (leader CTA) issues every tcgen05.mma (N = 192, K = 16) and the multicast tcgen05.commit's; TMEM (512 columns)
-//               is allocated for the pair by this warp of both CTAs.
+//               is allocated for the pair by this warp of both CTAs.  The WHOLE warp runs the issue loop and the elect.sync lane
+//               executes the instructions (warp-uniform control flow keeps descriptors in uniform registers: tc_common.cuh).
+//   warp 18     resident-image instantiation only: issues the TMA loads of the A image (k-blocks 1-4) as the MMAs release it.
 // Precision: CN_PREC_BF16X3 runs A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (fp32 accumulate in TMEM, ~2^-16 relative operand
 // error); CN_PREC_BF16 / CN_PREC_FP16 run one pass.
 // Development aids: -DEDGE_PROFILE adds per-role clock64 counters (tools/edge_profile.py) and CN_EDGE_DEBUG what-if switches.
