@@ -132,11 +132,22 @@ class ClockSampler(threading.Thread):
         except Exception:  # noqa: BLE001 - nvidia-smi missing: report no clocks rather than fail the bench
             pass
 
+    def begin(self, timeout=3.0):
+        """Start sampling and return once nvidia-smi delivers (its start-up can take longer than a short timed region); the
+        samples taken from here on are the ones reported."""
+        self.start()
+        t_end = time.time() + timeout
+        while not self.rows and time.time() < t_end and self.is_alive():
+            time.sleep(0.02)
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        first = getattr(self, "first", 0)
+        rows = self.rows[first:] if len(self.rows) > first else self.rows      # a region shorter than one period: what there is
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -260,8 +271,7 @@ def run_ours(args, wl):
     if args.no_graph:
         launches0 = eng.launches + policy.gpu_launches
         if rank == 0:
-            sampler.start()
-            time.sleep(0.3)
+            sampler.begin()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -277,8 +287,7 @@ def run_ours(args, wl):
         for _ in range(max(3, args.warmup)):
             roll.step()
         if rank == 0:
-            sampler.start()
-            time.sleep(0.3)
+            sampler.begin()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -491,8 +500,7 @@ def run_train(args, wl):
         cycle()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
+        sampler.begin()
     launches0 = venv.engine.launches + policy.gpu_launches + native.COUNTERS["gemm_launches"] + native.COUNTERS["kernel_launches"]
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
